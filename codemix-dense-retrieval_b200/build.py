@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Build libcmx.so (hand-written CUDA for sm_100a) in-tree with nvcc.
+
+    python codemix-dense-retrieval_b200/build.py [--force] [--verbose]
+
+Output: codemix-dense-retrieval_b200/lib/libcmx.so (git-ignored; travels to the GPU box).
+nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import hashlib
+import pathlib
+import shutil
+import subprocess
+import sys
+
+HERE = pathlib.Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB = HERE / "lib" / "libcmx.so"
+STAMP = HERE / "lib" / ".libcmx.stamp"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fvisibility=hidden",
+    "--threads", "0",
+]
+
+
+def _sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "cmx.h"]):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
+    LIB.parent.mkdir(parents=True, exist_ok=True)
+    dig = _digest()
+    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text() == dig:
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc, *NVCC_FLAGS]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", str(LIB), *map(str, _sources())]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libcmx.so")
+    STAMP.write_text(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,226 @@
+"""Thin object wrapper over the C ABI: one ``Shard`` = one ``cmx_index`` on one GPU.
+
+Accepts numpy arrays (host memory) and torch tensors (host or CUDA; CUDA tensors
+are used zero-copy through ``data_ptr()``).  PyTorch is plumbing only: device
+memory, streams.  All arithmetic happens in libcmx.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import PATH_AUTO, PATH_STREAM, PATH_TENSOR, check
+
+try:  # torch is optional for pure-numpy callers
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+_PATHS = {"auto": PATH_AUTO, "stream": PATH_STREAM, "tensor": PATH_TENSOR,
+          PATH_AUTO: PATH_AUTO, PATH_STREAM: PATH_STREAM, PATH_TENSOR: PATH_TENSOR, None: PATH_AUTO}
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _stream(device: int) -> int:
+    if torch is not None and torch.cuda.is_available():
+        return int(torch.cuda.current_stream(device).cuda_stream)
+    return 0
+
+
+def _as_f32_2d(x, d: Optional[int], what: str):
+    """Coerce like faiss' Python layer: float32, C-contiguous, 2-D; assert the dim."""
+    if _is_torch(x):
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.to(torch.float32).contiguous()
+        if x.dim() == 1:
+            x = x.reshape(1, -1)
+        assert x.dim() == 2, f"{what} must be 2-D"
+    else:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim == 1:
+            x = x.reshape(1, -1)
+        assert x.ndim == 2, f"{what} must be 2-D"
+    if d is not None:
+        assert x.shape[1] == d, f"{what} has dim {x.shape[1]}, index has d={d}"
+    return x
+
+
+def _ptr(x) -> Tuple[int, int]:
+    """(address, on_device)"""
+    if _is_torch(x):
+        return int(x.data_ptr()), 1 if x.is_cuda else 0
+    return int(x.ctypes.data), 0
+
+
+class Shard:
+    """A flat inner-product row store resident on one GPU."""
+
+    def __init__(self, d: int, device: int = 0):
+        self._h = C.c_void_p()
+        check(_lib.lib().cmx_index_create(int(d), int(device), C.byref(self._h)))
+        self.d = int(d)
+        self.device = int(device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().cmx_index_free(h)
+            except Exception:
+                pass
+            self._h = C.c_void_p()
+
+    close = __del__
+
+    # ---- storage -----------------------------------------------------------
+    @property
+    def ntotal(self) -> int:
+        n = C.c_int64(0)
+        check(_lib.lib().cmx_index_ntotal(self._h, C.byref(n)))
+        return int(n.value)
+
+    def reserve(self, n: int) -> None:
+        check(_lib.lib().cmx_index_reserve(self._h, int(n)))
+
+    def reset(self) -> None:
+        check(_lib.lib().cmx_index_reset(self._h))
+
+    def add(self, x) -> None:
+        x = _as_f32_2d(x, self.d, "add(x)")
+        if _is_torch(x) and x.is_cuda:
+            assert x.device.index == self.device, "tensor lives on another GPU than the shard"
+            torch.cuda.current_stream(self.device).synchronize()
+        p, on_dev = _ptr(x)
+        check(_lib.lib().cmx_index_add(self._h, p, int(x.shape[0]), on_dev))
+
+    def reconstruct_n(self, i0: int, n: int, out=None):
+        if out is None:
+            out = np.empty((int(n), self.d), dtype=np.float32)
+        p, on_dev = _ptr(out)
+        check(_lib.lib().cmx_index_reconstruct(self._h, int(i0), int(n), p, on_dev))
+        return out
+
+    def data_ptr(self) -> int:
+        p = C.c_void_p()
+        check(_lib.lib().cmx_index_data(self._h, C.byref(p)))
+        return int(p.value or 0)
+
+    def set_cand_capacity(self, cap: int) -> None:
+        check(_lib.lib().cmx_index_set_cand_capacity(self._h, int(cap)))
+
+    # ---- search ------------------------------------------------------------
+    def _alloc_out(self, like, shape_d, shape_i):
+        if _is_torch(like) and like.is_cuda:
+            D = torch.empty(shape_d, dtype=torch.float32, device=like.device)
+            I = torch.empty(shape_i, dtype=torch.int64, device=like.device)
+        elif _is_torch(like):
+            D = torch.empty(shape_d, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+            I = torch.empty(shape_i, dtype=torch.int64, pin_memory=torch.cuda.is_available())
+        else:
+            D = np.empty(shape_d, dtype=np.float32)
+            I = np.empty(shape_i, dtype=np.int64)
+        return D, I
+
+    def search(self, x, k: int, id_base: int = 0, path="auto", out=None):
+        x = _as_f32_2d(x, self.d, "search(x)")
+        k = int(k)
+        assert k > 0
+        nq = int(x.shape[0])
+        D, I = out if out is not None else self._alloc_out(x, (nq, k), (nq, k))
+        if nq == 0:
+            return D, I
+        px, xdev = _ptr(x)
+        pd, ddev = _ptr(D)
+        pi, idev = _ptr(I)
+        assert xdev == ddev == idev, "inputs and outputs must all be host or all be device"
+        check(_lib.lib().cmx_index_search(self._h, px, nq, k, pd, pi, xdev, int(id_base), _PATHS[path], _stream(self.device)))
+        return D, I
+
+    def search_mixed(self, P, S, alphas: Sequence[float], k: int, id_base: int = 0, path="auto", out=None,
+                     want_flags: bool = False):
+        """Fused mix+normalise prologue and search for a batch of alphas -> D,I [nA,nq,k]."""
+        P = _as_f32_2d(P, self.d, "P")
+        S = _as_f32_2d(S, self.d, "S")
+        assert tuple(P.shape) == tuple(S.shape)
+        nq, nA, k = int(P.shape[0]), len(alphas), int(k)
+        D, I = out if out is not None else self._alloc_out(P, (nA, nq, k), (nA, nq, k))
+        a = (C.c_double * nA)(*[float(v) for v in alphas])
+        pp, pdev = _ptr(P)
+        ps, sdev = _ptr(S)
+        pd, ddev = _ptr(D)
+        pi, idev = _ptr(I)
+        assert pdev == sdev == ddev == idev, "inputs and outputs must all be host or all be device"
+        flags = None
+        pf = None
+        if want_flags:
+            if pdev:
+                flags = torch.empty((nA, nq), dtype=torch.uint8, device=P.device)
+                pf = int(flags.data_ptr())
+            else:
+                flags = np.empty((nA, nq), dtype=np.uint8)
+                pf = int(flags.ctypes.data)
+        check(_lib.lib().cmx_search_mixed(self._h, pp, ps, nq, a, nA, k, pd, pi, pf, pdev, int(id_base), _PATHS[path],
+                                          _stream(self.device)))
+        return (D, I, flags) if want_flags else (D, I)
+
+    def last_stats(self) -> dict:
+        st = _lib.SearchStats()
+        check(_lib.lib().cmx_index_last_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+
+def mix_normalize(P, S, alphas: Sequence[float], device: int = 0, want_flags: bool = False):
+    """Batched safe_mix: out[a, q] = normalise((1-alpha_a) P[q] + alpha_a S[q]) with the
+    reference's endpoint pass-through and non-finite fallback.  [nA, nq, d]."""
+    P = _as_f32_2d(P, None, "P")
+    S = _as_f32_2d(S, None, "S")
+    assert tuple(P.shape) == tuple(S.shape)
+    nq, d = int(P.shape[0]), int(P.shape[1])
+    nA = len(alphas)
+    on_dev = _is_torch(P) and P.is_cuda
+    if on_dev:
+        assert _is_torch(S) and S.is_cuda and S.device == P.device
+        device = P.device.index
+        out = torch.empty((nA, nq, d), dtype=torch.float32, device=P.device)
+        flags = torch.zeros((nA, nq), dtype=torch.uint8, device=P.device)
+    else:
+        if _is_torch(P):
+            P = P.numpy()
+        if _is_torch(S):
+            S = S.numpy()
+        out = np.empty((nA, nq, d), dtype=np.float32)
+        flags = np.zeros((nA, nq), dtype=np.uint8)
+    a = (C.c_double * nA)(*[float(v) for v in alphas])
+    check(_lib.lib().cmx_mix_normalize(_ptr(P)[0], _ptr(S)[0], nq, d, a, nA, _ptr(out)[0], _ptr(flags)[0],
+                                       1 if on_dev else 0, int(device), _stream(device)))
+    return (out, flags) if want_flags else out
+
+
+def merge_topk(D_parts, I_parts, k: Optional[int] = None, device: int = 0):
+    """k-way merge of per-shard results [G, nq, k] -> [nq, k] (score desc, shard, position)."""
+    on_dev = _is_torch(D_parts) and D_parts.is_cuda
+    if on_dev:
+        D_parts = D_parts.contiguous()
+        I_parts = I_parts.contiguous()
+        device = D_parts.device.index
+    else:
+        D_parts = np.ascontiguousarray(D_parts, dtype=np.float32)
+        I_parts = np.ascontiguousarray(I_parts, dtype=np.int64)
+    G, nq, kk = (int(v) for v in D_parts.shape)
+    k = kk if k is None else int(k)
+    assert k == kk, "merge keeps k"
+    if on_dev:
+        D = torch.empty((nq, k), dtype=torch.float32, device=D_parts.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=D_parts.device)
+    else:
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+    check(_lib.lib().cmx_merge_topk(_ptr(D_parts)[0], _ptr(I_parts)[0], G, nq, k, _ptr(D)[0], _ptr(I)[0],
+                                    1 if on_dev else 0, int(device), _stream(device)))
+    return D, I

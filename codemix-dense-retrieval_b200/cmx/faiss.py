@@ -1,0 +1,455 @@
+"""The subset of the Python ``faiss`` API the reference's run scripts use, backed by
+libcmx.so on B200.  ``import cmx.faiss as faiss`` is the drop-in.
+
+Symbols used by the reference and provided here:
+``IndexFlatIP``, ``IndexIDMap`` (+ ``.index``, ``.d``, ``.ntotal``, ``.id_map``),
+``add`` / ``add_with_ids`` / ``search`` / ``reconstruct``, ``read_index`` /
+``write_index``, ``downcast_index``, ``StandardGpuResources``,
+``index_cpu_to_gpu``, ``index_gpu_to_cpu``; plus the faiss-named multi-GPU
+entry points ``index_cpu_to_all_gpus`` / ``index_cpu_to_gpus_list`` and
+``GpuIndexFlatIP``.
+
+Reference call sites: onepass_dense_mix_run_custom_lang.py:250,265-269,604,
+658-664,719,878; onepass_bilingual_mix_hub_custom_lang.py:558,644-646,931-936,950;
+encode_multilingual_corpus.py:367-373,440,469-471; onepass_dense_run.py:305-312,427.
+
+Semantics kept: ``search(x, k) -> (D [n,k] float32 descending, I [n,k] int64)``,
+``-1`` / lowest-float padding when k > ntotal, AssertionError on a dimension
+mismatch, RuntimeError for engine errors, ``add`` copies, ``index_cpu_to_gpu``
+leaves the CPU index valid and independent.
+
+There is no CPU search: a "CPU" ``IndexFlatIP`` keeps its rows in host memory
+(like faiss) but ``search`` on it promotes the rows to the default GPU and runs
+the CUDA path; with no GPU / no libcmx.so it raises RuntimeError.
+"""
+from __future__ import annotations
+
+import os
+from concurrent.futures import ThreadPoolExecutor
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .engine import Shard, _as_f32_2d, _is_torch, merge_topk
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+METRIC_INNER_PRODUCT = 0
+METRIC_L2 = 1
+
+
+def get_num_gpus() -> int:
+    return _lib.device_count()
+
+
+def _default_device() -> int:
+    return int(os.environ.get("CMX_DEVICE", "0"))
+
+
+class StandardGpuResources:
+    """Placeholder with faiss' name: libcmx sizes its own bounded workspace per index
+    (candidate buffers + operand planes), so there is no temp-memory arena to manage.
+    Constructing it verifies that a GPU and the CUDA library are usable."""
+
+    def __init__(self):
+        if get_num_gpus() < 1:
+            raise RuntimeError("cmx.faiss.StandardGpuResources: no usable CUDA device")
+
+    def setTempMemory(self, nbytes):  # noqa: N802 (faiss naming)
+        pass
+
+    def noTempMemory(self):  # noqa: N802
+        pass
+
+    def setDefaultNullStreamAllDevices(self):  # noqa: N802
+        pass
+
+
+class GpuClonerOptions:
+    def __init__(self):
+        self.useFloat16 = False
+        self.shard = False
+
+
+GpuMultipleClonerOptions = GpuClonerOptions
+
+
+class _Searchable:
+    """search-path selection shared by all index classes ('auto' | 'stream' | 'tensor')."""
+
+    path = "auto"
+
+
+class GpuIndexFlatIP(_Searchable):
+    """Flat inner-product index resident in one GPU's HBM (faiss.GpuIndexFlatIP)."""
+
+    is_trained = True
+    metric_type = METRIC_INNER_PRODUCT
+
+    def __init__(self, res_or_d, d: Optional[int] = None, config=None, device: Optional[int] = None):
+        if d is None:  # GpuIndexFlatIP(d)
+            d = res_or_d
+        if device is None:
+            device = getattr(config, "device", None)
+        if device is None:
+            device = _default_device()
+        self.d = int(d)
+        self._shard = Shard(self.d, int(device))
+
+    # faiss attribute / method names
+    @property
+    def ntotal(self) -> int:
+        return self._shard.ntotal
+
+    def getDevice(self) -> int:  # noqa: N802
+        return self._shard.device
+
+    def reserveMemory(self, n: int) -> None:  # noqa: N802
+        self._shard.reserve(n)
+
+    def add(self, x) -> None:
+        self._shard.add(x)
+
+    def reset(self) -> None:
+        self._shard.reset()
+
+    def search(self, x, k: int):
+        return self._shard.search(x, k, path=self.path)
+
+    def search_mixed(self, P, S, alphas, k: int):
+        return self._shard.search_mixed(P, S, alphas, k, path=self.path)
+
+    def reconstruct(self, i: int, out=None):
+        i = int(i)
+        if not 0 <= i < self.ntotal:
+            raise RuntimeError(f"reconstruct: index {i} out of range [0, {self.ntotal})")
+        if out is None:
+            return self._shard.reconstruct_n(i, 1)[0]
+        self._shard.reconstruct_n(i, 1, out.reshape(1, -1))
+        return out
+
+    def reconstruct_n(self, i0: int = 0, n: int = -1, out=None):
+        if n < 0:
+            n = self.ntotal - i0
+        return self._shard.reconstruct_n(i0, n, out)
+
+    def last_stats(self) -> dict:
+        return self._shard.last_stats()
+
+
+class IndexFlatIP(_Searchable):
+    """faiss.IndexFlatIP: rows kept in host memory; search runs on the GPU."""
+
+    is_trained = True
+    metric_type = METRIC_INNER_PRODUCT
+
+    def __init__(self, d: int):
+        self.d = int(d)
+        self._blocks: List[np.ndarray] = []
+        self._n = 0
+        self._gpu: Optional[GpuIndexFlatIP] = None  # lazily promoted copy
+        self._gpu_rows = 0
+
+    @property
+    def ntotal(self) -> int:
+        return self._n
+
+    def add(self, x) -> None:
+        if _is_torch(x):
+            x = x.detach().cpu().numpy()
+        x = _as_f32_2d(x, self.d, "add(x)")
+        self._blocks.append(np.array(x, dtype=np.float32, copy=True))  # faiss copies
+        self._n += x.shape[0]
+
+    def reset(self) -> None:
+        self._blocks, self._n = [], 0
+        self._gpu, self._gpu_rows = None, 0
+
+    def _rows(self) -> np.ndarray:
+        if len(self._blocks) != 1:
+            self._blocks = [np.concatenate(self._blocks, axis=0)] if self._blocks else [np.empty((0, self.d), np.float32)]
+        return self._blocks[0]
+
+    def reconstruct(self, i: int, out=None):
+        i = int(i)
+        if not 0 <= i < self._n:
+            raise RuntimeError(f"reconstruct: index {i} out of range [0, {self._n})")
+        row = self._rows()[i]
+        if out is None:
+            return row.copy()
+        out[...] = row
+        return out
+
+    def reconstruct_n(self, i0: int = 0, n: int = -1, out=None):
+        if n < 0:
+            n = self._n - i0
+        rows = self._rows()[i0 : i0 + n]
+        if out is None:
+            return rows.copy()
+        out[...] = rows
+        return out
+
+    def _promote(self, device: Optional[int] = None) -> GpuIndexFlatIP:
+        if self._gpu is None or (device is not None and self._gpu.getDevice() != device):
+            self._gpu = GpuIndexFlatIP(self.d, device=device)
+            self._gpu_rows = 0
+        if self._gpu_rows < self._n:
+            if self._gpu_rows == 0:
+                self._gpu.reserveMemory(self._n)
+            self._gpu.add(self._rows()[self._gpu_rows :])
+            self._gpu_rows = self._n
+        self._gpu.path = self.path
+        return self._gpu
+
+    def search(self, x, k: int):
+        return self._promote().search(x, k)
+
+    def search_mixed(self, P, S, alphas, k: int):
+        return self._promote().search_mixed(P, S, alphas, k)
+
+
+def _map_ids(I, id_map: np.ndarray):
+    """I = id_map[I], -1 stays -1 (faiss IndexIDMap::search)."""
+    if _is_torch(I):
+        if I.is_cuda:
+            idm = torch.from_numpy(id_map).to(I.device)
+            return torch.where(I >= 0, idm[I.clamp_min(0)], I)
+        I = I.numpy()
+        out = np.where(I >= 0, id_map[np.clip(I, 0, None)], -1)
+        return torch.from_numpy(out)
+    return np.where(I >= 0, id_map[np.clip(I, 0, None)], -1)
+
+
+class IndexIDMap(_Searchable):
+    """faiss.IndexIDMap: user ids on top of a flat index (ids live host-side)."""
+
+    is_trained = True
+    metric_type = METRIC_INNER_PRODUCT
+
+    def __init__(self, index):
+        if index.ntotal != 0:
+            raise RuntimeError("IndexIDMap: index must be empty on input")
+        self.index = index
+        self.d = index.d
+        self._ids: List[np.ndarray] = []
+
+    @property
+    def ntotal(self) -> int:
+        return self.index.ntotal
+
+    @property
+    def id_map(self) -> np.ndarray:
+        if len(self._ids) != 1:
+            self._ids = [np.concatenate(self._ids)] if self._ids else [np.empty((0,), np.int64)]
+        return self._ids[0]
+
+    def add(self, x):
+        raise RuntimeError("add not implemented for IndexIDMap: use add_with_ids")  # faiss behaviour
+
+    def add_with_ids(self, x, ids) -> None:
+        ids = np.ascontiguousarray(ids, dtype=np.int64).reshape(-1)
+        n = x.shape[0] if hasattr(x, "shape") and len(x.shape) == 2 else 1
+        assert ids.shape[0] == n, "add_with_ids: one id per row"
+        self.index.add(x)
+        self._ids.append(ids.copy())
+
+    def reset(self) -> None:
+        self.index.reset()
+        self._ids = []
+
+    def search(self, x, k: int):
+        self.index.path = self.path
+        D, I = self.index.search(x, k)
+        return D, _map_ids(I, self.id_map)
+
+    def search_mixed(self, P, S, alphas, k: int):
+        self.index.path = self.path
+        D, I = self.index.search_mixed(P, S, alphas, k)
+        return D, _map_ids(I, self.id_map)
+
+    def reconstruct(self, key, out=None):
+        # faiss: only IndexIDMap2 can reconstruct by user id; the reference probes the
+        # *base* index instead (onepass_dense_mix_run_custom_lang.py:264-269)
+        raise RuntimeError("reconstruct not implemented for IndexIDMap (use the base index / IndexIDMap2)")
+
+
+def downcast_index(index):
+    """faiss.downcast_index: our Python objects already have their concrete type."""
+    return index
+
+
+def _clone_flat_to_gpu(index, device: int) -> GpuIndexFlatIP:
+    if isinstance(index, GpuIndexFlatIP):
+        g = GpuIndexFlatIP(index.d, device=device)
+        n = index.ntotal
+        if n:
+            g.reserveMemory(n)
+            step = max(1, (1 << 28) // (4 * index.d))
+            for i0 in range(0, n, step):
+                g.add(index.reconstruct_n(i0, min(step, n - i0)))
+        return g
+    if isinstance(index, IndexFlatIP):
+        g = GpuIndexFlatIP(index.d, device=device)
+        if index.ntotal:
+            g.reserveMemory(index.ntotal)
+            g.add(index._rows())
+        return g
+    raise RuntimeError(f"index_cpu_to_gpu: unsupported index type {type(index).__name__}")
+
+
+def index_cpu_to_gpu(res, device: int, index, options=None):
+    """Clone onto ONE GPU; the source index stays valid and independent."""
+    if isinstance(index, IndexIDMap):
+        out = IndexIDMap(GpuIndexFlatIP(index.d, device=device))
+        out.index = _clone_flat_to_gpu(index.index, device)
+        out._ids = [index.id_map.copy()]
+        return out
+    return _clone_flat_to_gpu(index, int(device))
+
+
+def index_gpu_to_cpu(index):
+    if isinstance(index, IndexIDMap):
+        out = IndexIDMap(IndexFlatIP(index.d))
+        out.index = index_gpu_to_cpu(index.index)
+        out._ids = [index.id_map.copy()]
+        return out
+    if isinstance(index, IndexShardsIP):
+        cpu = IndexFlatIP(index.d)
+        for sh in index.shards:
+            if sh.ntotal:
+                cpu.add(sh.reconstruct_n(0, sh.ntotal))
+        return cpu
+    if isinstance(index, GpuIndexFlatIP):
+        cpu = IndexFlatIP(index.d)
+        n = index.ntotal
+        step = max(1, (1 << 28) // (4 * index.d))
+        for i0 in range(0, n, step):
+            cpu.add(index.reconstruct_n(i0, min(step, n - i0)))
+        return cpu
+    if isinstance(index, IndexFlatIP):
+        return index
+    raise RuntimeError(f"index_gpu_to_cpu: unsupported index type {type(index).__name__}")
+
+
+class IndexShardsIP(_Searchable):
+    """Row-sharded flat IP index over several GPUs driven from ONE process
+    (faiss.index_cpu_to_all_gpus(..., shard=True) analogue; new capability, the
+    reference never shards).  Shard g holds the contiguous rows
+    [bounds[g], bounds[g+1]); every shard searches the full query batch
+    concurrently, partial results are merged on shards[0]'s device by the k-way
+    merge kernel.  Result == the single-GPU result exactly (same tie order)."""
+
+    is_trained = True
+    metric_type = METRIC_INNER_PRODUCT
+
+    def __init__(self, d: int, devices: Sequence[int]):
+        self.d = int(d)
+        self.devices = [int(v) for v in devices]
+        self.shards = [GpuIndexFlatIP(d, device=dev) for dev in self.devices]
+        self._pool = ThreadPoolExecutor(max_workers=len(self.devices))
+
+    @property
+    def ntotal(self) -> int:
+        return sum(s.ntotal for s in self.shards)
+
+    @property
+    def bounds(self) -> List[int]:
+        b = [0]
+        for s in self.shards:
+            b.append(b[-1] + s.ntotal)
+        return b
+
+    @staticmethod
+    def split(n: int, g: int) -> List[int]:
+        """row i -> shard floor(i*g/n): contiguous, sizes differ by at most one."""
+        return [(n * j) // g for j in range(g + 1)]
+
+    def add(self, x) -> None:
+        """Appends to the LAST shard (keeps global row order = add order)."""
+        self.shards[-1].add(x)
+
+    def add_sharded(self, rows: np.ndarray) -> None:
+        assert self.ntotal == 0, "add_sharded needs an empty index"
+        b = self.split(rows.shape[0], len(self.shards))
+        for g, sh in enumerate(self.shards):
+            if b[g + 1] > b[g]:
+                sh.reserveMemory(b[g + 1] - b[g])
+                sh.add(rows[b[g] : b[g + 1]])
+
+    def reset(self) -> None:
+        for s in self.shards:
+            s.reset()
+
+    def reconstruct(self, i: int, out=None):
+        b = self.bounds
+        for g, sh in enumerate(self.shards):
+            if b[g] <= i < b[g + 1]:
+                return sh.reconstruct(i - b[g], out)
+        raise RuntimeError(f"reconstruct: index {i} out of range [0, {b[-1]})")
+
+    def _fanout(self, fn):
+        b = self.bounds
+        futs = [self._pool.submit(fn, sh, b[g]) for g, sh in enumerate(self.shards)]
+        parts = [f.result() for f in futs]
+        Dp = np.stack([np.asarray(p[0]) for p in parts])
+        Ip = np.stack([np.asarray(p[1]) for p in parts])
+        return Dp, Ip
+
+    def search(self, x, k: int):
+        if _is_torch(x):
+            x = x.detach().cpu().numpy()
+        x = _as_f32_2d(x, self.d, "search(x)")
+        path = self.path
+        Dp, Ip = self._fanout(lambda sh, base: sh._shard.search(x, k, id_base=base, path=path))
+        return merge_topk(Dp, Ip, k, device=self.devices[0])
+
+    def search_mixed(self, P, S, alphas, k: int):
+        P = _as_f32_2d(P.detach().cpu().numpy() if _is_torch(P) else P, self.d, "P")
+        S = _as_f32_2d(S.detach().cpu().numpy() if _is_torch(S) else S, self.d, "S")
+        path = self.path
+        Dp, Ip = self._fanout(lambda sh, base: sh._shard.search_mixed(P, S, alphas, k, id_base=base, path=path))
+        G, nA, nq, kk = Dp.shape
+        D, I = merge_topk(Dp.reshape(G, nA * nq, kk), Ip.reshape(G, nA * nq, kk), k, device=self.devices[0])
+        return D.reshape(nA, nq, kk), I.reshape(nA, nq, kk)
+
+
+def index_cpu_to_gpus_list(index, co=None, gpus: Optional[Sequence[int]] = None, ngpu: int = -1):
+    """Row-shard a CPU index over several GPUs (one process)."""
+    if gpus is None:
+        n = get_num_gpus() if ngpu is None or ngpu < 0 else ngpu
+        gpus = list(range(n))
+    if len(gpus) < 1:
+        raise RuntimeError("index_cpu_to_gpus_list: no GPU")
+    if isinstance(index, IndexIDMap):
+        out = IndexIDMap(IndexShardsIP(index.d, gpus))
+        out.index = index_cpu_to_gpus_list(index.index, co, gpus)
+        out._ids = [index.id_map.copy()]
+        return out
+    if isinstance(index, GpuIndexFlatIP):
+        index = index_gpu_to_cpu(index)
+    if not isinstance(index, IndexFlatIP):
+        raise RuntimeError(f"index_cpu_to_gpus_list: unsupported index type {type(index).__name__}")
+    sh = IndexShardsIP(index.d, gpus)
+    if index.ntotal:
+        sh.add_sharded(index._rows())
+    return sh
+
+
+def index_cpu_to_all_gpus(index, co=None, ngpu: int = -1):
+    return index_cpu_to_gpus_list(index, co=co, gpus=None, ngpu=ngpu)
+
+
+def write_index(index, path) -> None:
+    from .io import write_index as _w
+
+    _w(index, path)
+
+
+def read_index(path, io_flags: int = 0):
+    from .io import read_index as _r
+
+    return _r(path)

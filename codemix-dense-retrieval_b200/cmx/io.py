@@ -1,0 +1,206 @@
+"""File formats on either side of the hot path.
+
+* ``index.faiss``   -- FAISS's on-disk layout for ``IndexIDMap(IndexFlatIP)`` /
+  ``IndexFlatIP`` as written by ``faiss.write_index``
+  (encode_multilingual_corpus.py:471) and read by ``faiss.read_index``
+  (onepass_dense_mix_run_custom_lang.py:250).  faiss itself is not installable
+  here, so this follows the published format of faiss 1.8 (index_write.cpp /
+  index_read.cpp) and is verified only by round trips -- best effort until checked
+  against a file written by real faiss:
+      "IxMp" | header | <nested index> | u64 n | n x i64 id_map
+      "IxFI" | header | u64 count (= ntotal*d, in 4-byte units) | count x f32
+      header = i32 d | i64 ntotal | i64 dummy(1<<20) | i64 dummy(1<<20) |
+               u8 is_trained | i32 metric_type (0 = inner product)
+* ``docid_map.tsv`` -- header ``int_id\\tderived_id\\tbase_id\\tlang``
+  (encode_multilingual_corpus.py:474-478; readers
+  onepass_dense_mix_run_custom_lang.py:632-644,
+  onepass_bilingual_mix_hub_custom_lang.py:629-641)
+* ``queries.npz``   -- ``np.savez_compressed(qids=<unicode array>, vecs=[n,d])``
+  (onepass_dense_mix_run_custom_lang.py:196-235, cache_queries_for_mix.py:166-176)
+"""
+from __future__ import annotations
+
+import pathlib
+import struct
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HDR = struct.Struct("<iqqqBi")  # d, ntotal, dummy, dummy, is_trained, metric_type
+_DUMMY = 1 << 20
+_CHUNK_ROWS = 1 << 16
+
+
+def _write_header(fh, d: int, ntotal: int) -> None:
+    fh.write(_HDR.pack(int(d), int(ntotal), _DUMMY, _DUMMY, 1, 0))
+
+
+def _read_header(fh) -> Tuple[int, int]:
+    raw = fh.read(_HDR.size)
+    if len(raw) != _HDR.size:
+        raise RuntimeError("read_index: truncated header")
+    d, ntotal, _d1, _d2, _trained, metric = _HDR.unpack(raw)
+    if d <= 0 or ntotal < 0:
+        raise RuntimeError(f"read_index: bad header (d={d}, ntotal={ntotal})")
+    if metric != 0:
+        raise RuntimeError(f"read_index: only METRIC_INNER_PRODUCT (0) is supported, file has metric {metric}")
+    return d, ntotal
+
+
+def write_index(index, path) -> None:
+    from . import faiss as F
+
+    path = pathlib.Path(path)
+    with open(path, "wb") as fh:
+        if isinstance(index, F.IndexIDMap):
+            fh.write(b"IxMp")
+            _write_header(fh, index.d, index.ntotal)
+            _write_flat(fh, index.index)
+            ids = np.ascontiguousarray(index.id_map, dtype="<i8")
+            fh.write(struct.pack("<Q", ids.shape[0]))
+            fh.write(ids.tobytes())
+        else:
+            _write_flat(fh, index)
+
+
+def _write_flat(fh, flat) -> None:
+    n, d = flat.ntotal, flat.d
+    fh.write(b"IxFI")
+    _write_header(fh, d, n)
+    fh.write(struct.pack("<Q", n * d))
+    for i0 in range(0, n, _CHUNK_ROWS):
+        rows = flat.reconstruct_n(i0, min(_CHUNK_ROWS, n - i0))
+        fh.write(np.ascontiguousarray(rows, dtype="<f4").tobytes())
+
+
+def read_index(path, device: Optional[int] = None):
+    """Returns a host-resident IndexFlatIP / IndexIDMap(IndexFlatIP) like faiss.read_index
+    (rows are streamed in chunks; promote with index_cpu_to_gpu / search)."""
+    from . import faiss as F
+
+    path = pathlib.Path(path)
+    with open(path, "rb") as fh:
+        fourcc = fh.read(4)
+        if fourcc == b"IxMp":
+            d, ntotal = _read_header(fh)
+            flat = _read_flat(fh, F)
+            raw = fh.read(8)
+            if len(raw) != 8:
+                raise RuntimeError("read_index: truncated id_map")
+            (n_ids,) = struct.unpack("<Q", raw)
+            if n_ids != flat.ntotal or flat.d != d:
+                raise RuntimeError(f"read_index: id_map has {n_ids} ids for {flat.ntotal} rows")
+            ids = np.fromfile(fh, dtype="<i8", count=n_ids)
+            if ids.shape[0] != n_ids:
+                raise RuntimeError("read_index: truncated id_map")
+            out = F.IndexIDMap(F.IndexFlatIP(d))
+            out.index = flat
+            out._ids = [ids.astype(np.int64, copy=False)]
+            return out
+        if fourcc == b"IxFI":
+            fh.seek(0)
+            fh.read(4)
+            return _read_flat(fh, F, fourcc_read=True)
+        raise RuntimeError(f"read_index: unsupported index type {fourcc!r} (only IxMp / IxFI)")
+
+
+def _read_flat(fh, F, fourcc_read: bool = False):
+    if not fourcc_read:
+        fourcc = fh.read(4)
+        if fourcc != b"IxFI":
+            raise RuntimeError(f"read_index: nested index {fourcc!r} is not IndexFlatIP (IxFI)")
+    d, ntotal = _read_header(fh)
+    raw = fh.read(8)
+    if len(raw) != 8:
+        raise RuntimeError("read_index: truncated vector block")
+    (count,) = struct.unpack("<Q", raw)
+    if count != ntotal * d:
+        raise RuntimeError(f"read_index: vector block holds {count} floats, expected {ntotal}*{d}")
+    flat = F.IndexFlatIP(d)
+    rows = np.fromfile(fh, dtype="<f4", count=count)
+    if rows.shape[0] != count:
+        raise RuntimeError("read_index: truncated vector block")
+    if ntotal:
+        flat._blocks = [rows.reshape(ntotal, d)]
+        flat._n = ntotal
+    return flat
+
+
+# ---- docid_map.tsv ------------------------------------------------------------
+def write_docid_map(path, int_ids: Sequence[int], derived: Sequence[str], base: Sequence[str], lang: str) -> None:
+    with open(path, "w", encoding="utf-8") as fh:
+        print("int_id\tderived_id\tbase_id\tlang", file=fh)
+        for i, de, b in zip(int_ids, derived, base):
+            print(f"{i}\t{de}\t{b}\t{lang}", file=fh)
+
+
+def read_docid_map(path) -> Tuple[Dict[int, str], List[str], List[str]]:
+    """-> (id_lookup {int_id: base_id}, kept [base_id...], derived [derived_id...]);
+    malformed lines are skipped exactly as the reference readers do."""
+    id_lookup: Dict[int, str] = {}
+    kept: List[str] = []
+    derived: List[str] = []
+    with open(path, "r", encoding="utf-8") as fh:
+        next(fh, None)  # header
+        for line in fh:
+            parts = line.rstrip("\n").split("\t")
+            if len(parts) < 3:
+                continue
+            try:
+                local_id = int(parts[0])
+            except ValueError:
+                continue
+            id_lookup[local_id] = str(parts[2])
+            kept.append(str(parts[2]))
+            derived.append(parts[1])
+    return id_lookup, kept, derived
+
+
+# ---- queries.npz ----------------------------------------------------------------
+def save_query_cache(cache_dir, lang: str, qids: Sequence[str], vecs) -> None:
+    """vecs: [n,d] array in qid order, or a dict qid -> row."""
+    lang_dir = pathlib.Path(cache_dir) / lang
+    lang_dir.mkdir(parents=True, exist_ok=True)
+    if isinstance(vecs, dict):
+        if not vecs:
+            return
+        vecs = np.stack([vecs[q] for q in qids if q in vecs], axis=0)
+    np.savez_compressed(lang_dir / "queries.npz", qids=np.array(list(qids)), vecs=np.asarray(vecs))
+
+
+def load_query_cache(cache_dir, lang: str, qids: Sequence[str]) -> Optional[np.ndarray]:
+    """-> vecs [n,d] float32 in the requested order, or None when the cache is absent or
+    its qids differ from the request (same acceptance rule as the reference)."""
+    cache_file = pathlib.Path(cache_dir) / lang / "queries.npz"
+    if not cache_file.exists():
+        return None
+    try:
+        data = np.load(cache_file)
+        cached = [str(x) for x in data["qids"].tolist()]
+        if cached != list(qids):
+            return None
+        vecs = data["vecs"].astype(np.float32, copy=False)
+        if vecs.shape[0] != len(qids):
+            return None
+        return np.ascontiguousarray(vecs)
+    except Exception:
+        return None
+
+
+def read_queries_tsv(path, qid_field: str = "id", text_field: str = "text") -> List[Tuple[str, str]]:
+    """qid<TAB>text rows; an optional header line naming the two fields is skipped and a
+    malformed line ends the job (onepass_dense_mix_run_custom_lang.py:72-91)."""
+    rows: List[Tuple[str, str]] = []
+    with open(path, "r", encoding="utf-8") as fh:
+        for ln, line in enumerate(fh, 1):
+            line = line.rstrip("\n")
+            if not line:
+                continue
+            parts = line.split("\t")
+            if ln == 1 and len(parts) >= 2:
+                if parts[0].lower().startswith(qid_field.lower()) and parts[1].lower().startswith(text_field.lower()):
+                    continue
+            if len(parts) < 2:
+                raise SystemExit(f"[ERROR] Bad queries TSV line #{ln}: {line}")
+            rows.append((parts[0], parts[1]))
+    return rows

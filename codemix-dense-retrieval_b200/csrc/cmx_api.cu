@@ -1,0 +1,678 @@
+// C ABI of libcmx.so (see include/cmx.h): index storage in HBM, search
+// orchestration (slab schedule -> scoring kernel -> compaction), the vector-mix
+// prologue and the shard merge.  Host-side control only; all arithmetic is in the
+// kernels of prologue.cu / stream_score.cu / tc_score.cu / select.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cmx {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+int g_profiling = 0;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_error = buf;
+}
+
+struct DevGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DevGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+static int ensure_buf(T** ptr, int64_t* cap, int64_t need) {
+  if (need <= *cap && *ptr) return CMX_OK;
+  if (*ptr) { cudaFree(*ptr); *ptr = nullptr; *cap = 0; }
+  if (need <= 0) need = 1;
+  cudaError_t e = cudaMalloc((void**)ptr, (size_t)need * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("device allocation of %lld bytes failed: %s", (long long)(need * (int64_t)sizeof(T)), cudaGetErrorString(e));
+    *ptr = nullptr;
+    return CMX_ERR_NOMEM;
+  }
+  *cap = need;
+  return CMX_OK;
+}
+
+constexpr int kMaxSlabEvents = 64;
+constexpr int64_t kQueryChunk = 8192;  // queries per corpus pass (bounds workspace + Q L2 footprint)
+
+}  // namespace cmx
+
+using namespace cmx;
+
+struct cmx_index {
+  int d = 0, d_pad = 0, device = 0, sm_count = 148;
+  int64_t n = 0, cap_rows = 0;
+  float* X = nullptr;  // fp32 row store [cap_rows, d]
+  // fp16 hi/lo planes for the tensor path [cap_rows, d_pad], built lazily
+  __half* Bhi = nullptr;
+  __half* Blo = nullptr;
+  int64_t plane_cap = 0, plane_rows = 0;
+  float plane_scale = 0.f;
+  uint32_t absmax_bits = 0;  // max |x| over all finite stored elements
+  uint32_t* absmax_dev = nullptr;
+  // search workspace
+  SearchWs ws;
+  int64_t tau_cap = 0, cnt_cap = 0, cand_cap_elems = 0;
+  int cand_cap_override = 0;
+  float* q_dev = nullptr; int64_t q_cap = 0;        // staged / mixed queries
+  float* p_dev = nullptr; int64_t p_cap = 0;        // staged P
+  float* s_dev = nullptr; int64_t s_cap = 0;        // staged S
+  __half* Qhi = nullptr; int64_t qhi_cap = 0;
+  __half* Qlo = nullptr; int64_t qlo_cap = 0;
+  uint32_t* q_absmax = nullptr;
+  float* q_scale = nullptr;  // {scale, 1/scale}
+  float* D_dev = nullptr; int64_t D_cap = 0;
+  int64_t* I_dev = nullptr; int64_t I_cap = 0;
+  uint8_t* flags_dev = nullptr; int64_t flags_cap = 0;
+  float* w_dev = nullptr; int64_t w_cap = 0;  // w1[nA], w2[nA]
+  int* mode_dev = nullptr; int64_t mode_cap = 0;
+  cudaEvent_t ev[4 * kMaxSlabEvents];
+  bool ev_ready = false;
+  cmx_search_stats stats;
+};
+
+namespace cmx {
+
+static int ensure_events(cmx_index* ix) {
+  if (ix->ev_ready) return CMX_OK;
+  for (int i = 0; i < 4 * kMaxSlabEvents; ++i) CMX_CUDA(cudaEventCreate(&ix->ev[i]));
+  ix->ev_ready = true;
+  return CMX_OK;
+}
+
+static int grow_store(cmx_index* ix, int64_t need_rows) {
+  if (need_rows <= ix->cap_rows) return CMX_OK;
+  int64_t new_cap = std::max<int64_t>(need_rows, ix->cap_rows + ix->cap_rows / 2);
+  float* nx = nullptr;
+  cudaError_t e = cudaMalloc((void**)&nx, (size_t)new_cap * ix->d * sizeof(float));
+  if (e != cudaSuccess && new_cap > need_rows) {
+    new_cap = need_rows;
+    e = cudaMalloc((void**)&nx, (size_t)new_cap * ix->d * sizeof(float));
+  }
+  if (e != cudaSuccess) {
+    set_error("cannot allocate %.2f GB for %lld rows x %d: %s", (double)new_cap * ix->d * 4 / 1e9,
+              (long long)new_cap, ix->d, cudaGetErrorString(e));
+    return CMX_ERR_NOMEM;
+  }
+  if (ix->n > 0) CMX_CUDA(cudaMemcpy(nx, ix->X, (size_t)ix->n * ix->d * sizeof(float), cudaMemcpyDeviceToDevice));
+  if (ix->X) cudaFree(ix->X);
+  ix->X = nx;
+  ix->cap_rows = new_cap;
+  // planes follow the store lazily
+  if (ix->Bhi) { cudaFree(ix->Bhi); ix->Bhi = nullptr; }
+  if (ix->Blo) { cudaFree(ix->Blo); ix->Blo = nullptr; }
+  ix->plane_cap = 0;
+  ix->plane_rows = 0;
+  return CMX_OK;
+}
+
+// build / extend the fp16 hi/lo planes so they cover rows [0, n)
+static int ensure_planes(cmx_index* ix, cudaStream_t st) {
+  const float want_scale = host_scale_for_absmax_bits(ix->absmax_bits);
+  if (ix->plane_cap < ix->cap_rows || !ix->Bhi || !ix->Blo) {
+    if (ix->Bhi) { cudaFree(ix->Bhi); ix->Bhi = nullptr; }
+    if (ix->Blo) { cudaFree(ix->Blo); ix->Blo = nullptr; }
+    const size_t bytes = (size_t)ix->cap_rows * ix->d_pad * sizeof(__half);
+    cudaError_t e1 = cudaMalloc((void**)&ix->Bhi, bytes);
+    cudaError_t e2 = (e1 == cudaSuccess) ? cudaMalloc((void**)&ix->Blo, bytes) : e1;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      if (ix->Bhi) { cudaFree(ix->Bhi); ix->Bhi = nullptr; }
+      ix->Blo = nullptr;
+      ix->plane_cap = 0;
+      set_error("cannot allocate 2 x %.2f GB for the fp16 hi/lo planes (tensor path); shard the index over more GPUs",
+                (double)bytes / 1e9);
+      return CMX_ERR_NOMEM;
+    }
+    ix->plane_cap = ix->cap_rows;
+    ix->plane_rows = 0;
+  }
+  if (ix->plane_scale != want_scale) {
+    ix->plane_rows = 0;
+    ix->plane_scale = want_scale;
+  }
+  if (ix->plane_rows < ix->n) {
+    const int64_t r0 = ix->plane_rows;
+    CMX_TRY(launch_split_planes(ix->X + r0 * ix->d, ix->n - r0, ix->d, ix->d_pad, nullptr, ix->plane_scale,
+                                ix->Bhi + r0 * ix->d_pad, ix->Blo + r0 * ix->d_pad, st));
+    ix->plane_rows = ix->n;
+  }
+  return CMX_OK;
+}
+
+static int pick_cap(const cmx_index* ix, int k) {
+  int cap = ix->cand_cap_override;
+  if (cap <= 0) cap = (k <= 1024) ? 8192 : 16384;
+  int p = 256;
+  while (p < cap) p <<= 1;
+  cap = p;
+  while (cap < 2 * k) cap <<= 1;
+  return cap;
+}
+
+struct SlabPlan {
+  std::vector<int64_t> rows;  // slab sizes, in order; slab 0 is the dense one
+};
+
+// Geometric slab schedule: slab 0 fills the (empty) candidate buffers densely, every
+// later slab is sized so that, for rows arriving in exchangeable order, the expected
+// number of rows beating the stale threshold is half of the free room (cap - k).
+// safe = worst-case schedule (every row may pass): rows <= cap - k per slab.
+static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe) {
+  SlabPlan pl;
+  int64_t seen = 0;
+  const int64_t room = cap - k;
+  auto round_dn = [&](int64_t v) { return std::max<int64_t>(align, v / align * align); };
+  while (seen < N) {
+    int64_t rows;
+    if (seen == 0) {
+      rows = round_dn(cap);
+      if (rows > cap) rows = cap;  // align > cap cannot happen (cap >= 256)
+    } else if (safe) {
+      rows = round_dn(room);
+      if (rows > room) rows = room;
+    } else {
+      const double g = (double)seen * (double)room / (2.0 * (double)k);
+      rows = round_dn((int64_t)std::min<double>(g, 4e18));
+    }
+    rows = std::min(rows, N - seen);
+    pl.rows.push_back(rows);
+    seen += rows;
+  }
+  return pl;
+}
+
+// one pass over the corpus for queries q_d[0..nq) (nq <= kQueryChunk)
+static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d,
+                       int64_t id_base, int path, bool safe, cudaStream_t st, bool* overflowed) {
+  const int cap = pick_cap(ix, k);
+  const int64_t nq_pad = (nq + 127) / 128 * 128;
+  CMX_TRY(ensure_buf(&ix->ws.tau, &ix->tau_cap, nq_pad));
+  CMX_TRY(ensure_buf(&ix->ws.cnt, &ix->cnt_cap, nq_pad));
+  CMX_TRY(ensure_buf(&ix->ws.cand, &ix->cand_cap_elems, nq * (int64_t)cap));
+  if (!ix->ws.overflow) CMX_CUDA(cudaMalloc((void**)&ix->ws.overflow, sizeof(uint32_t)));
+  ix->ws.cap = cap;
+  CMX_TRY(launch_ws_init(ix->ws, nq, nq_pad, st));
+
+  if (path == CMX_PATH_TENSOR) {
+    CMX_TRY(ensure_planes(ix, st));
+    CMX_TRY(ensure_buf(&ix->Qhi, &ix->qhi_cap, nq_pad * (int64_t)ix->d_pad));
+    CMX_TRY(ensure_buf(&ix->Qlo, &ix->qlo_cap, nq_pad * (int64_t)ix->d_pad));
+    if (!ix->q_absmax) CMX_CUDA(cudaMalloc((void**)&ix->q_absmax, sizeof(uint32_t)));
+    if (!ix->q_scale) CMX_CUDA(cudaMalloc((void**)&ix->q_scale, 2 * sizeof(float)));
+    CMX_CUDA(cudaMemsetAsync(ix->q_absmax, 0, sizeof(uint32_t), st));
+    CMX_TRY(launch_absmax(q_d, nq * (int64_t)ix->d, ix->q_absmax, st));
+    CMX_TRY(launch_scale_from_absmax(ix->q_absmax, ix->q_scale, st));
+    if (nq_pad > nq) {
+      CMX_CUDA(cudaMemsetAsync(ix->Qhi + nq * (int64_t)ix->d_pad, 0, (size_t)(nq_pad - nq) * ix->d_pad * sizeof(__half), st));
+      CMX_CUDA(cudaMemsetAsync(ix->Qlo + nq * (int64_t)ix->d_pad, 0, (size_t)(nq_pad - nq) * ix->d_pad * sizeof(__half), st));
+    }
+    CMX_TRY(launch_split_planes(q_d, nq, ix->d, ix->d_pad, ix->q_scale, 1.0f, ix->Qhi, ix->Qlo, st));
+  }
+
+  const int align = (path == CMX_PATH_TENSOR) ? 256 : 32;
+  SlabPlan pl = plan_slabs(ix->n, k, cap, align, safe);
+  const bool prof = g_profiling && !safe && (int)pl.rows.size() <= kMaxSlabEvents;
+  if (prof) CMX_TRY(ensure_events(ix));
+  int64_t seen = 0;
+  const int nslabs = (int)pl.rows.size();
+  for (int s = 0; s < nslabs; ++s) {
+    const int64_t rows = pl.rows[s];
+    const int dense = (s == 0) ? 1 : 0;
+    if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 0], st));
+    if (path == CMX_PATH_TENSOR) {
+      CMX_TRY(launch_tensor_score(ix->Bhi, ix->Blo, ix->n, seen, rows, ix->d_pad, ix->Qhi, ix->Qlo, nq, nq_pad,
+                                  ix->q_scale + 1, 1.0f / ix->plane_scale, ix->ws, dense, seen, st, ix->sm_count));
+    } else {
+      CMX_TRY(launch_stream_score(ix->X, seen, rows, ix->d, q_d, (int)nq, ix->ws, 0, dense, seen, st, ix->sm_count));
+    }
+    if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 1], st));
+    if (dense) CMX_TRY(launch_set_counts(ix->ws, nq, (uint32_t)rows, st));
+    const int last = (s == nslabs - 1) ? 1 : 0;
+    CMX_TRY(launch_compact(ix->ws, nq, k, last, D_d, I_d, id_base, st));
+    if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 2], st));
+    seen += rows;
+  }
+  uint32_t ovf = 0;
+  CMX_CUDA(cudaMemcpyAsync(&ovf, ix->ws.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CMX_CUDA(cudaStreamSynchronize(st));
+  *overflowed = (ovf != 0);
+  ix->stats.slabs += nslabs;
+  ix->stats.score_launches += nslabs * ((path == CMX_PATH_TENSOR) ? 1 : (int)((nq + 7) / 8));
+  ix->stats.select_launches += nslabs;
+  if (prof) {
+    for (int s = 0; s < nslabs; ++s) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, ix->ev[4 * s + 0], ix->ev[4 * s + 1]);
+      cudaEventElapsedTime(&b, ix->ev[4 * s + 1], ix->ev[4 * s + 2]);
+      ix->stats.score_ms += a;
+      ix->stats.select_ms += b;
+    }
+  }
+  return CMX_OK;
+}
+
+static int fill_empty(float* D_d, int64_t* I_d, int64_t count, cudaStream_t st) {
+  std::vector<float> d((size_t)count, CMX_NEG_PAD);
+  std::vector<int64_t> i((size_t)count, -1);
+  CMX_CUDA(cudaMemcpyAsync(D_d, d.data(), count * sizeof(float), cudaMemcpyHostToDevice, st));
+  CMX_CUDA(cudaMemcpyAsync(I_d, i.data(), count * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  CMX_CUDA(cudaStreamSynchronize(st));
+  return CMX_OK;
+}
+
+// all pointers on the index's device
+static int search_device(cmx_index* ix, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d,
+                         int64_t id_base, int path, cudaStream_t st) {
+  if (nq == 0) return CMX_OK;
+  if (ix->n == 0) return fill_empty(D_d, I_d, nq * (int64_t)k, st);
+  if (path == CMX_PATH_AUTO) path = (nq <= 8) ? CMX_PATH_STREAM : CMX_PATH_TENSOR;
+  if (path == CMX_PATH_STREAM && (ix->d & 3) != 0) path = CMX_PATH_TENSOR;
+  ix->stats.path = path;
+  for (int64_t q0 = 0; q0 < nq; q0 += kQueryChunk) {
+    const int64_t nqc = std::min<int64_t>(kQueryChunk, nq - q0);
+    bool ovf = false;
+    CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, false, st, &ovf));
+    if (ovf) {
+      // some query's candidate buffer overflowed (rows arrived in an adversarial order for the
+      // stale threshold); redo this chunk with the worst-case-safe slab schedule
+      ix->stats.reruns = 1;
+      CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, true, st, &ovf));
+      if (ovf) { set_error("internal: candidate buffer overflow in safe mode"); return CMX_ERR_INTERNAL; }
+    }
+  }
+  return CMX_OK;
+}
+
+static void stats_begin(cmx_index* ix, int64_t nq) {
+  memset(&ix->stats, 0, sizeof(ix->stats));
+  ix->stats.nq = nq;
+  ix->stats.ntotal = ix->n;
+  ix->stats.launches = (int32_t)g_launches.load();
+}
+static void stats_end(cmx_index* ix) { ix->stats.launches = (int32_t)g_launches.load() - ix->stats.launches; }
+
+}  // namespace cmx
+
+// =============================== C ABI ===========================================
+extern "C" {
+
+const char* cmx_last_error(void) { return t_error.c_str(); }
+int cmx_version(void) { return 100; }
+uint64_t cmx_launch_count(void) { return g_launches.load(); }
+int cmx_set_profiling(int on) { g_profiling = on ? 1 : 0; return CMX_OK; }
+
+int cmx_device_count(int* out) {
+  CMX_CHECK(out != nullptr, "null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *out = 0;
+    set_error("no usable CUDA device: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return CMX_ERR_CUDA;
+  }
+  *out = n;
+  return CMX_OK;
+}
+
+int cmx_index_create(int d, int device, cmx_index** out) {
+  CMX_CHECK(out != nullptr, "null out");
+  *out = nullptr;
+  CMX_CHECK(d > 0 && d <= 65536, "bad dimension %d", d);
+  int ndev = 0;
+  CMX_TRY(cmx_device_count(&ndev));
+  CMX_CHECK(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+  DevGuard g(device);
+  CMX_CHECK(g.ok, "cannot select device %d", device);
+  cudaDeviceProp prop;
+  CMX_CUDA(cudaGetDeviceProperties(&prop, device));
+  CMX_CHECK(prop.major == 10, "libcmx is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+  cmx_index* ix = new cmx_index();
+  ix->d = d;
+  ix->d_pad = (d + 63) / 64 * 64;
+  ix->device = device;
+  ix->sm_count = prop.multiProcessorCount;
+  memset(&ix->stats, 0, sizeof(ix->stats));
+  cudaError_t e = cudaMalloc((void**)&ix->absmax_dev, sizeof(uint32_t));
+  if (e != cudaSuccess) { delete ix; set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return CMX_ERR_NOMEM; }
+  *out = ix;
+  return CMX_OK;
+}
+
+int cmx_index_free(cmx_index* ix) {
+  if (!ix) return CMX_OK;
+  DevGuard g(ix->device);
+  void* ptrs[] = {ix->X, ix->Bhi, ix->Blo, ix->absmax_dev, ix->ws.tau, ix->ws.cnt, ix->ws.cand, ix->ws.overflow,
+                  ix->q_dev, ix->p_dev, ix->s_dev, ix->Qhi, ix->Qlo, ix->q_absmax, ix->q_scale, ix->D_dev, ix->I_dev,
+                  ix->flags_dev, ix->w_dev, ix->mode_dev};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (ix->ev_ready)
+    for (int i = 0; i < 4 * kMaxSlabEvents; ++i) cudaEventDestroy(ix->ev[i]);
+  delete ix;
+  return CMX_OK;
+}
+
+int cmx_index_reserve(cmx_index* ix, int64_t n) {
+  CMX_CHECK(ix != nullptr, "null index");
+  CMX_CHECK(n >= 0 && n < (int64_t)0x7fffff00, "reserve: row count %lld out of range (max 2^31 rows per shard)", (long long)n);
+  DevGuard g(ix->device);
+  return grow_store(ix, n);
+}
+
+int cmx_index_add(cmx_index* ix, const float* x, int64_t n, int x_on_device) {
+  CMX_CHECK(ix != nullptr, "null index");
+  CMX_CHECK(n >= 0, "negative row count");
+  if (n == 0) return CMX_OK;
+  CMX_CHECK(x != nullptr, "null data");
+  CMX_CHECK(ix->n + n < (int64_t)0x7fffff00, "index would exceed 2^31 rows per shard");
+  DevGuard g(ix->device);
+  CMX_TRY(grow_store(ix, ix->n + n));
+  float* dst = ix->X + ix->n * ix->d;
+  CMX_CUDA(cudaMemcpy(dst, x, (size_t)n * ix->d * sizeof(float), x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  // track max |x| (finite) for the fp16 operand scale of the tensor path
+  CMX_CUDA(cudaMemset(ix->absmax_dev, 0, sizeof(uint32_t)));
+  CMX_TRY(launch_absmax(dst, n * (int64_t)ix->d, ix->absmax_dev, 0));
+  uint32_t bits = 0;
+  CMX_CUDA(cudaMemcpy(&bits, ix->absmax_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  ix->absmax_bits = std::max(ix->absmax_bits, bits);
+  ix->n += n;
+  return CMX_OK;
+}
+
+int cmx_index_reset(cmx_index* ix) {
+  CMX_CHECK(ix != nullptr, "null index");
+  ix->n = 0;
+  ix->plane_rows = 0;
+  ix->absmax_bits = 0;
+  return CMX_OK;
+}
+
+int cmx_index_ntotal(const cmx_index* ix, int64_t* out) {
+  CMX_CHECK(ix && out, "null argument");
+  *out = ix->n;
+  return CMX_OK;
+}
+int cmx_index_dim(const cmx_index* ix, int* out) {
+  CMX_CHECK(ix && out, "null argument");
+  *out = ix->d;
+  return CMX_OK;
+}
+int cmx_index_device(const cmx_index* ix, int* out) {
+  CMX_CHECK(ix && out, "null argument");
+  *out = ix->device;
+  return CMX_OK;
+}
+int cmx_index_data(const cmx_index* ix, const float** out) {
+  CMX_CHECK(ix && out, "null argument");
+  *out = ix->X;
+  return CMX_OK;
+}
+
+int cmx_index_reconstruct(const cmx_index* ix, int64_t i0, int64_t n, float* out, int out_on_device) {
+  CMX_CHECK(ix && out, "null argument");
+  CMX_CHECK(i0 >= 0 && n >= 0 && i0 + n <= ix->n, "reconstruct: rows [%lld, %lld) out of range (ntotal %lld)",
+            (long long)i0, (long long)(i0 + n), (long long)ix->n);
+  if (n == 0) return CMX_OK;
+  DevGuard g(ix->device);
+  CMX_CUDA(cudaMemcpy(out, ix->X + i0 * ix->d, (size_t)n * ix->d * sizeof(float),
+                      out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+  return CMX_OK;
+}
+
+int cmx_index_set_cand_capacity(cmx_index* ix, int cap) {
+  CMX_CHECK(ix != nullptr, "null index");
+  CMX_CHECK(cap >= 0 && cap <= 16384, "candidate capacity %d out of range [0, 16384]", cap);
+  ix->cand_cap_override = cap;
+  return CMX_OK;
+}
+
+int cmx_index_last_stats(const cmx_index* ix, cmx_search_stats* out) {
+  CMX_CHECK(ix && out, "null argument");
+  *out = ix->stats;
+  return CMX_OK;
+}
+
+int cmx_index_search(cmx_index* ix, const float* q, int64_t nq, int k, float* D, int64_t* I, int io_on_device,
+                     int64_t id_base, int path, void* stream) {
+  CMX_CHECK(ix != nullptr, "null index");
+  CMX_CHECK(nq >= 0, "negative query count");
+  CMX_CHECK(k >= 1 && k <= CMX_MAX_K, "k=%d out of range [1, %d]", k, CMX_MAX_K);
+  CMX_CHECK(path >= 0 && path <= 2, "bad path selector %d", path);
+  if (nq == 0) return CMX_OK;
+  CMX_CHECK(q && D && I, "null buffer");
+  DevGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  stats_begin(ix, nq);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_profiling) {
+    CMX_TRY(ensure_events(ix));
+    e0 = ix->ev[4 * kMaxSlabEvents - 1];
+    e1 = ix->ev[4 * kMaxSlabEvents - 2];
+    CMX_CUDA(cudaEventRecord(e0, st));
+  }
+  const float* q_d = q;
+  float* D_d = D;
+  int64_t* I_d = I;
+  if (!io_on_device) {
+    CMX_TRY(ensure_buf(&ix->q_dev, &ix->q_cap, nq * (int64_t)ix->d));
+    CMX_TRY(ensure_buf(&ix->D_dev, &ix->D_cap, nq * (int64_t)k));
+    CMX_TRY(ensure_buf(&ix->I_dev, &ix->I_cap, nq * (int64_t)k));
+    CMX_CUDA(cudaMemcpyAsync(ix->q_dev, q, (size_t)nq * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
+    q_d = ix->q_dev;
+    D_d = ix->D_dev;
+    I_d = ix->I_dev;
+  }
+  CMX_TRY(search_device(ix, q_d, nq, k, D_d, I_d, id_base, path, st));
+  if (!io_on_device) {
+    CMX_CUDA(cudaMemcpyAsync(D, D_d, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CMX_CUDA(cudaMemcpyAsync(I, I_d, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  }
+  if (g_profiling) CMX_CUDA(cudaEventRecord(e1, st));
+  CMX_CUDA(cudaStreamSynchronize(st));
+  if (g_profiling) cudaEventElapsedTime(&ix->stats.total_ms, e0, e1);
+  stats_end(ix);
+  return CMX_OK;
+}
+
+static int prepare_alphas(const double* alphas, int nA, std::vector<float>& w, std::vector<int>& mode) {
+  w.resize(2 * (size_t)nA);
+  mode.resize(nA);
+  for (int a = 0; a < nA; ++a) {
+    const double al = alphas[a];
+    // reference: weights are Python doubles cast to fp32 by numpy (onepass_dense_mix_run_custom_lang.py:356)
+    w[a] = (float)(1.0 - al);
+    w[nA + a] = (float)al;
+    int sel = 0;
+    if (std::fabs(al) <= 1e-8) sel = 1;
+    else if (std::fabs(al - 1.0) <= 1e-8) sel = 2;
+    const int fb = (std::fabs(al) > 0.5) ? 2 : 1;
+    mode[a] = sel | (fb << 4);
+  }
+  return CMX_OK;
+}
+
+// shared by cmx_mix_normalize (ix == NULL: temporary buffers) and cmx_search_mixed
+static int mix_on_device(const float* P_d, const float* S_d, int64_t nq, int d, const double* alphas, int nA,
+                         float* out_d, uint8_t* flags_d, float* w_d, int* mode_d, cudaStream_t st) {
+  std::vector<float> w;
+  std::vector<int> mode;
+  prepare_alphas(alphas, nA, w, mode);
+  CMX_CUDA(cudaMemcpyAsync(w_d, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  CMX_CUDA(cudaMemcpyAsync(mode_d, mode.data(), mode.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CMX_CUDA(cudaStreamSynchronize(st));  // w/mode are stack-owned host vectors
+  return launch_mix_normalize(P_d, S_d, nq, d, w_d, w_d + nA, mode_d, nA, out_d, flags_d, st);
+}
+
+int cmx_mix_normalize(const float* P, const float* S, int64_t nq, int d, const double* alphas, int nA, float* out,
+                      uint8_t* flags, int io_on_device, int device, void* stream) {
+  CMX_CHECK(nq >= 0 && d > 0 && nA >= 0, "bad shape");
+  if (nq == 0 || nA == 0) return CMX_OK;
+  CMX_CHECK(P && S && alphas && out, "null buffer");
+  int ndev = 0;
+  CMX_TRY(cmx_device_count(&ndev));
+  CMX_CHECK(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+  DevGuard g(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t in_bytes = (size_t)nq * d * sizeof(float);
+  const size_t out_elems = (size_t)nA * nq * d;
+  float *P_d = nullptr, *S_d = nullptr, *out_d = nullptr, *w_d = nullptr;
+  uint8_t* f_d = nullptr;
+  int* m_d = nullptr;
+  int rc = CMX_OK;
+  auto cleanup = [&]() {
+    if (!io_on_device) { cudaFree(P_d); cudaFree(S_d); cudaFree(out_d); cudaFree(f_d); }
+    cudaFree(w_d);
+    cudaFree(m_d);
+  };
+#define MIX_CUDA(expr)                                                             \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                   \
+      cleanup();                                                                   \
+      return CMX_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+  MIX_CUDA(cudaMalloc((void**)&w_d, 2 * (size_t)nA * sizeof(float)));
+  MIX_CUDA(cudaMalloc((void**)&m_d, (size_t)nA * sizeof(int)));
+  if (io_on_device) {
+    P_d = const_cast<float*>(P);
+    S_d = const_cast<float*>(S);
+    out_d = out;
+    f_d = flags;
+  } else {
+    MIX_CUDA(cudaMalloc((void**)&P_d, in_bytes));
+    MIX_CUDA(cudaMalloc((void**)&S_d, in_bytes));
+    MIX_CUDA(cudaMalloc((void**)&out_d, out_elems * sizeof(float)));
+    MIX_CUDA(cudaMalloc((void**)&f_d, (size_t)nA * nq));
+    MIX_CUDA(cudaMemcpyAsync(P_d, P, in_bytes, cudaMemcpyHostToDevice, st));
+    MIX_CUDA(cudaMemcpyAsync(S_d, S, in_bytes, cudaMemcpyHostToDevice, st));
+  }
+  rc = mix_on_device(P_d, S_d, nq, d, alphas, nA, out_d, f_d, w_d, m_d, st);
+  if (rc != CMX_OK) { cleanup(); return rc; }
+  if (!io_on_device) {
+    MIX_CUDA(cudaMemcpyAsync(out, out_d, out_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (flags) MIX_CUDA(cudaMemcpyAsync(flags, f_d, (size_t)nA * nq, cudaMemcpyDeviceToHost, st));
+  }
+  MIX_CUDA(cudaStreamSynchronize(st));
+#undef MIX_CUDA
+  cleanup();
+  return CMX_OK;
+}
+
+int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int64_t nq, const double* alphas, int nA, int k,
+                     float* D, int64_t* I, uint8_t* flags, int io_on_device, int64_t id_base, int path, void* stream) {
+  CMX_CHECK(ix != nullptr, "null index");
+  CMX_CHECK(nq >= 0 && nA >= 0, "bad shape");
+  CMX_CHECK(k >= 1 && k <= CMX_MAX_K, "k=%d out of range [1, %d]", k, CMX_MAX_K);
+  CMX_CHECK(path >= 0 && path <= 2, "bad path selector %d", path);
+  if (nq == 0 || nA == 0) return CMX_OK;
+  CMX_CHECK(P && S && alphas && D && I, "null buffer");
+  DevGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nqt = nq * (int64_t)nA;
+  stats_begin(ix, nqt);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_profiling) {
+    CMX_TRY(ensure_events(ix));
+    e0 = ix->ev[4 * kMaxSlabEvents - 1];
+    e1 = ix->ev[4 * kMaxSlabEvents - 2];
+    CMX_CUDA(cudaEventRecord(e0, st));
+  }
+  const float *P_d = P, *S_d = S;
+  float* D_d = D;
+  int64_t* I_d = I;
+  CMX_TRY(ensure_buf(&ix->q_dev, &ix->q_cap, nqt * (int64_t)ix->d));
+  CMX_TRY(ensure_buf(&ix->flags_dev, &ix->flags_cap, nqt));
+  CMX_TRY(ensure_buf(&ix->w_dev, &ix->w_cap, 2 * (int64_t)nA));
+  CMX_TRY(ensure_buf(&ix->mode_dev, &ix->mode_cap, (int64_t)nA));
+  if (!io_on_device) {
+    CMX_TRY(ensure_buf(&ix->p_dev, &ix->p_cap, nq * (int64_t)ix->d));
+    CMX_TRY(ensure_buf(&ix->s_dev, &ix->s_cap, nq * (int64_t)ix->d));
+    CMX_TRY(ensure_buf(&ix->D_dev, &ix->D_cap, nqt * (int64_t)k));
+    CMX_TRY(ensure_buf(&ix->I_dev, &ix->I_cap, nqt * (int64_t)k));
+    CMX_CUDA(cudaMemcpyAsync(ix->p_dev, P, (size_t)nq * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
+    CMX_CUDA(cudaMemcpyAsync(ix->s_dev, S, (size_t)nq * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
+    P_d = ix->p_dev;
+    S_d = ix->s_dev;
+    D_d = ix->D_dev;
+    I_d = ix->I_dev;
+  }
+  uint8_t* f_d = (io_on_device && flags) ? flags : ix->flags_dev;
+  CMX_TRY(mix_on_device(P_d, S_d, nq, ix->d, alphas, nA, ix->q_dev, f_d, ix->w_dev, ix->mode_dev, st));
+  CMX_TRY(search_device(ix, ix->q_dev, nqt, k, D_d, I_d, id_base, path, st));
+  if (!io_on_device) {
+    CMX_CUDA(cudaMemcpyAsync(D, D_d, (size_t)nqt * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CMX_CUDA(cudaMemcpyAsync(I, I_d, (size_t)nqt * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (flags) CMX_CUDA(cudaMemcpyAsync(flags, f_d, (size_t)nqt, cudaMemcpyDeviceToHost, st));
+  }
+  if (g_profiling) CMX_CUDA(cudaEventRecord(e1, st));
+  CMX_CUDA(cudaStreamSynchronize(st));
+  if (g_profiling) cudaEventElapsedTime(&ix->stats.total_ms, e0, e1);
+  stats_end(ix);
+  return CMX_OK;
+}
+
+int cmx_merge_topk(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k, float* D, int64_t* I,
+                   int io_on_device, int device, void* stream) {
+  CMX_CHECK(nparts >= 1 && nq >= 0, "bad shape");
+  CMX_CHECK(k >= 1 && k <= CMX_MAX_K, "k=%d out of range [1, %d]", k, CMX_MAX_K);
+  if (nq == 0) return CMX_OK;
+  CMX_CHECK(D_parts && I_parts && D && I, "null buffer");
+  int ndev = 0;
+  CMX_TRY(cmx_device_count(&ndev));
+  CMX_CHECK(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+  DevGuard g(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (io_on_device) {
+    CMX_TRY(launch_merge(D_parts, I_parts, nparts, nq, k, D, I, st));
+    CMX_CUDA(cudaStreamSynchronize(st));
+    return CMX_OK;
+  }
+  const size_t pe = (size_t)nparts * nq * k, oe = (size_t)nq * k;
+  float *Dp = nullptr, *Do = nullptr;
+  int64_t *Ip = nullptr, *Io = nullptr;
+  int rc = CMX_OK;
+  cudaError_t e = cudaMalloc((void**)&Dp, pe * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&Ip, pe * sizeof(int64_t));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&Do, oe * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&Io, oe * sizeof(int64_t));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(Dp, D_parts, pe * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(Ip, I_parts, pe * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    rc = launch_merge(Dp, Ip, nparts, nq, k, Do, Io, st);
+    if (rc == CMX_OK) {
+      e = cudaMemcpyAsync(D, Do, oe * sizeof(float), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(I, Io, oe * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+  }
+  cudaFree(Dp); cudaFree(Ip); cudaFree(Do); cudaFree(Io);
+  if (e != cudaSuccess) { set_error("merge: %s", cudaGetErrorString(e)); return CMX_ERR_CUDA; }
+  return rc;
+}
+
+/* test hook (not in cmx.h): tensor tile width 256 / 128 */
+CMX_API int cmx_debug_set_tensor_tile(int bn) { set_tensor_tile(bn); return CMX_OK; }
+
+}  // extern "C"

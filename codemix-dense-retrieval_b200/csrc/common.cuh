@@ -1,0 +1,123 @@
+// Shared helpers for libcmx (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/cmx.h"
+
+namespace cmx {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+extern int g_profiling;
+
+#define CMX_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      cmx::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                     __LINE__);                                                          \
+      return (_e == cudaErrorMemoryAllocation) ? CMX_ERR_NOMEM : CMX_ERR_CUDA;           \
+    }                                                                                    \
+  } while (0)
+
+#define CMX_CHECK(cond, ...)        \
+  do {                              \
+    if (!(cond)) {                  \
+      cmx::set_error(__VA_ARGS__);  \
+      return CMX_ERR_INVALID;       \
+    }                               \
+  } while (0)
+
+#define CMX_TRY(expr)          \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != CMX_OK) return _rc; \
+  } while (0)
+
+// after every kernel launch
+#define CMX_LAUNCHED()                       \
+  do {                                       \
+    cmx::g_launches.fetch_add(1);            \
+    CMX_CUDA(cudaGetLastError());            \
+  } while (0)
+
+// ---- candidate keys ---------------------------------------------------------
+// A candidate is one 64-bit key: high word = score mapped to an unsigned that
+// orders like the float, low word = ~row, so that a DESCENDING sort of keys
+// yields score descending, row ascending.  key 0 is below every real candidate.
+__host__ __device__ __forceinline__ uint32_t f32_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_f32(uint32_t o) {
+  uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  union { float f; uint32_t u; } c; c.u = b; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
+  return ((uint64_t)f32_to_ordered(score) << 32) | (uint64_t)(0xffffffffu - row);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t k) { return ordered_to_f32((uint32_t)(k >> 32)); }
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return 0xffffffffu - (uint32_t)(k & 0xffffffffu); }
+
+#define CMX_NEG_PAD (-3.402823466e+38f) /* FAISS pads IP results with lowest float */
+
+// ---- search workspace (device) ----------------------------------------------
+struct SearchWs {
+  float* tau = nullptr;        // [nq_pad] running k-th best score per query (filter threshold)
+  uint32_t* cnt = nullptr;     // [nq_pad] candidates appended per query (may exceed cap)
+  uint64_t* cand = nullptr;    // [nq_pad, cap] candidate keys
+  uint32_t* overflow = nullptr;// [1] set when some query's buffer overflowed
+  int cap = 0;
+  int64_t nq_cap = 0;
+};
+
+// ---- kernels (launchers return CMX codes) -------------------------------------
+int launch_mix_normalize(const float* P, const float* S, int64_t nq, int d, const float* w1,
+                         const float* w2, const int* mode, int nA, float* out, uint8_t* flags,
+                         cudaStream_t st);
+
+int launch_absmax(const float* x, int64_t n, uint32_t* absmax_bits, cudaStream_t st);
+// hi = f16(x*scale), lo = f16(x*scale - hi); planes have leading dim d_pad (zero padded)
+int launch_split_planes(const float* x, int64_t rows, int d, int d_pad, const float* scale_dev,
+                        float scale_host, __half* hi, __half* lo, cudaStream_t st);
+// scale_out[0] = 2^e with absmax*2^e in [2^12,2^13); scale_out[1] = 1/scale
+int launch_scale_from_absmax(const uint32_t* absmax_bits, float* scale_out, cudaStream_t st);
+float host_scale_for_absmax_bits(uint32_t bits);
+
+int launch_stream_score(const float* X, int64_t row0, int64_t nrows, int d, const float* Q,
+                        int nq, const SearchWs& ws, int64_t q0, int dense, int64_t dense_row0,
+                        cudaStream_t st, int sm_count);
+
+int tensor_path_available();
+void set_tensor_tile(int bn);  // 256 (default) or 128 corpus rows per tile
+int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
+                        int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,
+                        int64_t nq, int64_t nq_pad, const float* q_inv_scale_dev, float b_inv_scale,
+                        const SearchWs& ws, int dense, int64_t dense_row0, cudaStream_t st,
+                        int sm_count);
+
+int launch_ws_init(const SearchWs& ws, int64_t nq, int64_t nq_pad, cudaStream_t st);
+int launch_set_counts(const SearchWs& ws, int64_t nq, uint32_t value, cudaStream_t st);
+// sort candidates, keep top-k, refresh tau; final=1 also writes D/I (+id_base, padded)
+int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float* D, int64_t* I,
+                   int64_t id_base, cudaStream_t st);
+int launch_merge(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,
+                 float* D, int64_t* I, cudaStream_t st);
+
+}  // namespace cmx

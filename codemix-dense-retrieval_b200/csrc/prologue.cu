@@ -1,0 +1,223 @@
+// Vector-mix prologue and fp16 hi/lo operand split (sm_100a).
+//
+// mix_normalize_kernel restates safe_mix (reference
+// onepass_dense_mix_run_custom_lang.py:342-377) for a whole [nA, nq] batch in one
+// launch: one warp per output row, HBM-bound (12*d bytes per row).
+#include "common.cuh"
+
+namespace cmx {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ bool is_finite_f(float v) {
+  return (__float_as_uint(v) & 0x7f800000u) != 0x7f800000u;
+}
+
+// mode[a]: bits 0-1: 0 = mix, 1 = copy primary, 2 = copy secondary;
+//          bits 4-5: fallback row on non-finite output (1 = primary, 2 = secondary)
+__global__ void __launch_bounds__(256)
+mix_normalize_kernel(const float* __restrict__ P, const float* __restrict__ S, int64_t nq, int d,
+                     const float* __restrict__ w1s, const float* __restrict__ w2s,
+                     const int* __restrict__ modes, int nA, float* __restrict__ out,
+                     uint8_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (int64_t)nA * nq) return;
+  const int a = (int)(row / nq);
+  const int64_t q = row - (int64_t)a * nq;
+  const float* p = P + q * d;
+  const float* s = S + q * d;
+  float* o = out + row * d;
+  const int mode = modes[a];
+  const int sel = mode & 3;
+  uint8_t flag = 0;
+  const bool vec = (d & 3) == 0;
+
+  if (sel == 0) {
+    const float w1 = w1s[a], w2 = w2s[a];
+    float ss = 0.f;
+    if (vec) {
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+      for (int i = lane; i < (d >> 2); i += 32) {
+        float4 a4 = p4[i], b4 = s4[i];
+        float m0 = __fadd_rn(__fmul_rn(w1, a4.x), __fmul_rn(w2, b4.x));
+        float m1 = __fadd_rn(__fmul_rn(w1, a4.y), __fmul_rn(w2, b4.y));
+        float m2 = __fadd_rn(__fmul_rn(w1, a4.z), __fmul_rn(w2, b4.z));
+        float m3 = __fadd_rn(__fmul_rn(w1, a4.w), __fmul_rn(w2, b4.w));
+        ss = fmaf(m0, m0, ss); ss = fmaf(m1, m1, ss); ss = fmaf(m2, m2, ss); ss = fmaf(m3, m3, ss);
+      }
+    } else {
+      for (int i = lane; i < d; i += 32) {
+        float m = __fadd_rn(__fmul_rn(w1, p[i]), __fmul_rn(w2, s[i]));
+        ss = fmaf(m, m, ss);
+      }
+    }
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    const bool denom_nan = (ss != ss);
+    bool bad = denom_nan;
+    if (vec) {
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+      float4* o4 = reinterpret_cast<float4*>(o);
+      for (int i = lane; i < (d >> 2); i += 32) {
+        float4 a4 = p4[i], b4 = s4[i], r;
+        r.x = __fdiv_rn(__fadd_rn(__fmul_rn(w1, a4.x), __fmul_rn(w2, b4.x)), denom);
+        r.y = __fdiv_rn(__fadd_rn(__fmul_rn(w1, a4.y), __fmul_rn(w2, b4.y)), denom);
+        r.z = __fdiv_rn(__fadd_rn(__fmul_rn(w1, a4.z), __fmul_rn(w2, b4.z)), denom);
+        r.w = __fdiv_rn(__fadd_rn(__fmul_rn(w1, a4.w), __fmul_rn(w2, b4.w)), denom);
+        bad |= !(is_finite_f(r.x) && is_finite_f(r.y) && is_finite_f(r.z) && is_finite_f(r.w));
+        o4[i] = r;
+      }
+    } else {
+      for (int i = lane; i < d; i += 32) {
+        float r = __fdiv_rn(__fadd_rn(__fmul_rn(w1, p[i]), __fmul_rn(w2, s[i])), denom);
+        bad |= !is_finite_f(r);
+        o[i] = r;
+      }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (bad) {
+      const int fb = (mode >> 4) & 3;
+      const float* src = (fb == 2) ? s : p;
+      __syncwarp();
+      for (int i = lane; i < d; i += 32) o[i] = src[i];
+      flag = (uint8_t)fb;
+    }
+  } else {
+    const float* src = (sel == 2) ? s : p;
+    if (vec) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* o4 = reinterpret_cast<float4*>(o);
+      for (int i = lane; i < (d >> 2); i += 32) o4[i] = s4[i];
+    } else {
+      for (int i = lane; i < d; i += 32) o[i] = src[i];
+    }
+  }
+  if (flags != nullptr && lane == 0) flags[row] = flag;
+}
+
+int launch_mix_normalize(const float* P, const float* S, int64_t nq, int d, const float* w1,
+                         const float* w2, const int* mode, int nA, float* out, uint8_t* flags,
+                         cudaStream_t st) {
+  const int64_t rows = (int64_t)nA * nq;
+  if (rows == 0) return CMX_OK;
+  const int warps = 8;
+  const int64_t blocks = (rows + warps - 1) / warps;
+  mix_normalize_kernel<<<(unsigned)blocks, warps * 32, 0, st>>>(P, S, nq, d, w1, w2, mode, nA, out, flags);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+// ---- absmax over finite values ------------------------------------------------
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ out_bits) {
+  uint32_t m = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t b = __float_as_uint(x[i]) & 0x7fffffffu;
+    if ((b & 0x7f800000u) != 0x7f800000u) m = max(m, b);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(out_bits, m);
+}
+
+int launch_absmax(const float* x, int64_t n, uint32_t* absmax_bits, cudaStream_t st) {
+  if (n == 0) return CMX_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, absmax_bits);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+// scale = 2^(12 - floor(log2(absmax))) so that absmax*scale lies in [2^12, 2^13):
+// 8x head-room below the fp16 maximum, and the lo parts of typical elements stay
+// fp16-normal.  scale_out = {scale, 1/scale}
+__host__ __device__ inline float scale_for_absmax_bits(uint32_t bits) {
+  int e = (int)((bits >> 23) & 0xffu);
+  if (bits == 0u || e == 0) return 1.0f;  // all-zero (or denormal-only) data
+  int se = 12 - (e - 127);
+  if (se > 100) se = 100;
+  if (se < -100) se = -100;
+  uint32_t sb = (uint32_t)(se + 127) << 23;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(sb);
+#else
+  union { float f; uint32_t u; } c; c.u = sb; return c.f;
+#endif
+}
+
+__global__ void scale_from_absmax_kernel(const uint32_t* __restrict__ bits, float* __restrict__ out) {
+  float s = scale_for_absmax_bits(bits[0]);
+  out[0] = s;
+  out[1] = 1.0f / s;
+}
+
+int launch_scale_from_absmax(const uint32_t* absmax_bits, float* scale_out, cudaStream_t st) {
+  scale_from_absmax_kernel<<<1, 1, 0, st>>>(absmax_bits, scale_out);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+float host_scale_for_absmax_bits(uint32_t bits) { return scale_for_absmax_bits(bits); }
+
+// ---- fp32 -> fp16 hi/lo planes --------------------------------------------------
+// x*scale = hi + lo + O(2^-22 |x*scale|) with hi, lo fp16; scale is a power of two.
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ x, int64_t rows, int d, int d_pad,
+                    const float* __restrict__ scale_dev, float scale_host,
+                    __half* __restrict__ hi, __half* __restrict__ lo) {
+  const float scale = scale_dev ? scale_dev[0] : scale_host;
+  const int groups = d_pad >> 3;  // 8 elements per thread
+  const int64_t total = rows * (int64_t)groups;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t r = t / groups;
+    const int c0 = (int)(t - r * groups) << 3;
+    float v[8];
+    const float* src = x + r * d + c0;
+    if ((d & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + 4 * j < d) f = *reinterpret_cast<const float4*>(src + 4 * j);
+        v[4 * j + 0] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < d) ? src[j] : 0.f;
+    }
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float sv = v[j] * scale;
+      __half hh = __float2half_rn(sv);
+      float res = sv - __half2float(hh);
+      // inf/NaN inputs: keep them in hi, zero in lo (inf - inf would poison lo with NaN anyway)
+      h[j] = hh;
+      l[j] = __float2half_rn(res);
+    }
+    *reinterpret_cast<uint4*>(hi + r * d_pad + c0) = *reinterpret_cast<uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + r * d_pad + c0) = *reinterpret_cast<uint4*>(l);
+  }
+}
+
+int launch_split_planes(const float* x, int64_t rows, int d, int d_pad, const float* scale_dev,
+                        float scale_host, __half* hi, __half* lo, cudaStream_t st) {
+  if (rows == 0) return CMX_OK;
+  const int64_t total = rows * (int64_t)(d_pad >> 3);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  split_planes_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, rows, d, d_pad, scale_dev, scale_host, hi, lo);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+}  // namespace cmx

@@ -1,0 +1,383 @@
+// Tensor-core scorer: Q x Corpus^T with a fused threshold-filter epilogue (sm_100a).
+//
+// Replaces the SGEMM + blockSelect pair behind index.search for batched queries
+// (reference call sites onepass_dense_mix_run_custom_lang.py:878,
+// onepass_bilingual_mix_hub_custom_lang.py:950).
+//
+// Arithmetic: split precision with fp32 accumulation.  Every operand element x is
+// stored as two fp16 numbers hi = f16(x*2^e), lo = f16(x*2^e - hi) (prologue.cu), so
+// x*2^e = hi + lo up to 2^-22 relative; a score is accumulated by three tcgen05
+// kind::f16 MMAs per k-step into one fp32 TMEM accumulator
+//        D += Qlo*Bhi ;  D += Qhi*Blo ;  D += Qhi*Bhi
+// (products of fp16 pairs are exact in fp32; only lo*lo ~ 2^-22 is dropped) and
+// rescaled by the exact power of two 2^-(eq+eb) in the epilogue.
+//
+// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0    TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of Qhi/Qlo
+//             [128 x 64] and Bhi/Blo [BN x 64] into a ring of smem stages
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16)
+//   warps 2-5 epilogue: tcgen05.ld the 128 x BN fp32 accumulator (one query row per
+//             thread), compare with the row's threshold tau and append survivors
+//             (score,row keys) to the query's candidate buffer -- the score matrix
+//             never leaves the SM.
+// Accumulators are double-buffered in TMEM (2 x BN columns) so the epilogue of tile
+// i overlaps the MMAs of tile i+1.  Tiles are ordered m-fastest so that CTAs running
+// concurrently share the same corpus tile through L2: each corpus byte is read from
+// HBM once per pass.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace cmx {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;  // fp16 elements = 128 bytes = one swizzle-128B row
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB per Q plane tile
+
+// ---- PTX wrappers -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 "version 1"):
+// start address >> 4 | LBO (unused for swizzled K-major) | SBO = 1024 B (8 rows x
+// 128 B) | version = 1 | layout = SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct TcParams {
+  int64_t row0;        // first corpus row of the slab (plane row index)
+  int64_t nrows;       // rows in the slab
+  int kblocks;         // d_pad / 64
+  int mtiles;          // ceil(nq / 128)
+  int64_t ntiles;      // mtiles * ceil(nrows / BN)
+  int64_t nq;
+  const float* q_inv_scale;  // device: 1 / query scale
+  float b_inv_scale;         // 1 / corpus scale
+  const float* tau;
+  uint32_t* cnt;
+  uint64_t* cand;
+  int cap;
+  int dense;
+  int64_t dense_row0;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant__ CUtensorMap tmQlo,
+                const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                const TcParams p) {
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SW128 needs 1024B alignment
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmQhi); tma_prefetch_desc(&tmQlo);
+    tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int mtiles = p.mtiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        const int m = (int)(t % mtiles);
+        const int64_t n = t / mtiles;
+        const int32_t qrow = m * TC_BM;
+        const int32_t brow = (int32_t)(p.row0 + n * BN);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(sbase, &tmQhi, full_bar(stage), kb * TC_BK, qrow);
+          tma_load_2d(sbase + TC_A_BYTES, &tmQlo, full_bar(stage), kb * TC_BK, qrow);
+          tma_load_2d(sbase + 2 * TC_A_BYTES, &tmBhi, full_bar(stage), kb * TC_BK, brow);
+          tma_load_2d(sbase + 2 * TC_A_BYTES + B_BYTES, &tmBlo, full_bar(stage), kb * TC_BK, brow);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+          const uint64_t qhi = make_smem_desc(sbase);
+          const uint64_t qlo = make_smem_desc(sbase + TC_A_BYTES);
+          const uint64_t bhi = make_smem_desc(sbase + 2 * TC_A_BYTES);
+          const uint64_t blo = make_smem_desc(sbase + 2 * TC_A_BYTES + B_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 32) >> 4);  // 16 fp16 = 32 bytes per k-step
+            tc_mma_f16(d_tmem, qlo + koff, bhi + koff, IDESC, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_f16(d_tmem, qhi + koff, blo + koff, IDESC, 1u);
+            tc_mma_f16(d_tmem, qhi + koff, bhi + koff, IDESC, 1u);
+          }
+          tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue: threshold filter + append =====================
+    const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may touch
+    const float inv = p.q_inv_scale[0] * p.b_inv_scale;
+    const float fwd = 1.0f / inv;  // power of two
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+      const int m = (int)(t % mtiles);
+      const int64_t n = t / mtiles;
+      const int64_t q = (int64_t)m * TC_BM + lane_base + lane;
+      const int64_t tile_row0 = p.row0 + n * BN;
+      int64_t cols_valid = p.row0 + p.nrows - tile_row0;
+      if (cols_valid > BN) cols_valid = BN;
+      const bool qvalid = q < p.nq;
+      // compare raw accumulators against tau expressed in accumulator units
+      const float tau_raw = qvalid ? p.tau[q] * fwd : __int_as_float(0x7f800000);
+      uint64_t* qcand = p.cand + q * (int64_t)p.cap;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN + c * 32);
+        tmem_ld_x32(taddr, v);
+        tmem_ld_wait();
+        const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
+        if (p.dense) {
+          if (qvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < jmax) {
+                const float s = __uint_as_float(v[j]) * inv;
+                const int64_t grow = tile_row0 + c * 32 + j;
+                qcand[grow - p.dense_row0] = (s > CMX_NEG_PAD) ? make_key(s, (uint32_t)grow) : 0ull;
+              }
+            }
+          }
+        } else {
+          float mx = __int_as_float(0xff800000);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (j < jmax) ? __uint_as_float(v[j]) : mx);
+          if (mx > tau_raw) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float raw = __uint_as_float(v[j]);
+              if (j < jmax && raw > tau_raw) {
+                const uint32_t pos = atomicAdd(&p.cnt[q], 1u);
+                if (pos < (uint32_t)p.cap)
+                  qcand[pos] = make_key(raw * inv, (uint32_t)(tile_row0 + c * 32 + j));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static int make_plane_map(CUtensorMap* tm, const __half* base, int64_t rows, int d_pad, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return CMX_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)d_pad * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return CMX_ERR_CUDA; }
+  return CMX_OK;
+}
+
+int tensor_path_available() { return get_encode() != nullptr; }
+
+static int g_tc_bn = 256;  // tile width in corpus rows: 256 (2 stages) or 128 (3 stages)
+void set_tensor_tile(int bn) { g_tc_bn = (bn == 128) ? 128 : 256; }
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const CUtensorMap& tb_hi,
+                     const CUtensorMap& tb_lo, const TcParams& p, cudaStream_t st, int sm_count) {
+  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * BN * TC_BK * 2;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  CMX_CUDA(cudaFuncSetAttribute(tc_score_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = p.ntiles < sm_count ? p.ntiles : sm_count;
+  if (grid < 1) return CMX_OK;
+  tc_score_kernel<BN, STAGES><<<(unsigned)grid, TC_THREADS, smem, st>>>(tq_hi, tq_lo, tb_hi, tb_lo, p);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
+                        int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,
+                        int64_t nq, int64_t nq_pad, const float* q_inv_scale_dev, float b_inv_scale,
+                        const SearchWs& ws, int dense, int64_t dense_row0, cudaStream_t st,
+                        int sm_count) {
+  if (nrows <= 0 || nq <= 0) return CMX_OK;
+  CMX_CHECK(d_pad % TC_BK == 0, "tensor path: padded dim must be a multiple of %d", TC_BK);
+  CMX_CHECK(plane_rows < (int64_t)0x7fffffff, "tensor path: more than 2^31 rows per shard");
+  const int bn = g_tc_bn;
+  CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;
+  CMX_TRY(make_plane_map(&tq_hi, Qhi, nq_pad, d_pad, TC_BM));
+  CMX_TRY(make_plane_map(&tq_lo, Qlo, nq_pad, d_pad, TC_BM));
+  CMX_TRY(make_plane_map(&tb_hi, Bhi, plane_rows, d_pad, bn));
+  CMX_TRY(make_plane_map(&tb_lo, Blo, plane_rows, d_pad, bn));
+  TcParams p;
+  p.row0 = row0;
+  p.nrows = nrows;
+  p.kblocks = d_pad / TC_BK;
+  p.mtiles = (int)((nq + TC_BM - 1) / TC_BM);
+  p.ntiles = (int64_t)p.mtiles * ((nrows + bn - 1) / bn);
+  p.nq = nq;
+  p.q_inv_scale = q_inv_scale_dev;
+  p.b_inv_scale = b_inv_scale;
+  p.tau = ws.tau;
+  p.cnt = ws.cnt;
+  p.cand = ws.cand;
+  p.cap = ws.cap;
+  p.dense = dense;
+  p.dense_row0 = dense_row0;
+  if (bn == 256) return launch_tc<256, 2>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
+  return launch_tc<128, 3>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
+}
+
+}  // namespace cmx

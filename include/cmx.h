@@ -1,0 +1,152 @@
+/*
+ * cmx.h -- C ABI of libcmx.so: B200 (sm_100a) vector-mix + flat inner-product
+ * top-k search.  This is the drop-in boundary for the search path of
+ * cmHuang777/codemix-dense-retrieval: every entry point below replaces one call
+ * the reference makes into faiss / torch (reference file:line cited per entry).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary;
+ *   - every function returns 0 on success and a non-zero code on error, with a
+ *     thread-local message available from cmx_last_error(); nothing aborts the
+ *     process (the reference lets faiss raise RuntimeError: the Python shim maps
+ *     non-zero -> RuntimeError(cmx_last_error()));
+ *   - `*_on_device` = 0: the pointer is host memory (pageable or pinned),
+ *                     1: the pointer is device memory on the index's device;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default
+ *     stream).  Calls are synchronous: results are valid on return;
+ *   - an index owns its device storage; add() copies the caller's rows; no
+ *     caller pointer is retained after a call returns;
+ *   - one index lives on one device ("shard").  Multi-GPU = one shard per
+ *     device/rank plus cmx_merge_topk.
+ *
+ * There is NO CPU fallback anywhere behind this header: if no CUDA device is
+ * usable every compute entry point fails with an error.
+ */
+#ifndef CMX_H_
+#define CMX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CMX_API __attribute__((visibility("default")))
+#else
+#define CMX_API
+#endif
+
+typedef struct cmx_index cmx_index;
+
+/* error codes */
+#define CMX_OK 0
+#define CMX_ERR_INVALID 1   /* bad argument (shape, k, null pointer ...)   */
+#define CMX_ERR_CUDA 2      /* CUDA runtime / driver error                  */
+#define CMX_ERR_NOMEM 3     /* device allocation failed                     */
+#define CMX_ERR_INTERNAL 4
+
+/* scoring path selector for search */
+#define CMX_PATH_AUTO 0     /* nq <= 8: stream, else tensor                 */
+#define CMX_PATH_STREAM 1   /* CUDA-core fp32 streaming scorer (HBM-bound)  */
+#define CMX_PATH_TENSOR 2   /* tcgen05 fp16-split (hi/lo) tensor-core scorer */
+
+/* FAISS-GPU's own cap on k is 2048; kept here. */
+#define CMX_MAX_K 2048
+
+CMX_API const char* cmx_last_error(void);
+CMX_API int cmx_version(void);
+/* number of visible CUDA devices (0 and an error string when none). */
+CMX_API int cmx_device_count(int* out);
+/* cumulative number of kernels launched by this library in this process. */
+CMX_API uint64_t cmx_launch_count(void);
+
+/* ---- index lifecycle -------------------------------------------------------
+ * replaces: faiss.IndexFlatIP(dim) + faiss.index_cpu_to_gpu(res, gpu_id, index)
+ *   onepass_dense_mix_run_custom_lang.py:604,658-664,726-730
+ *   onepass_bilingual_mix_hub_custom_lang.py:558,931-936
+ *   encode_multilingual_corpus.py:367-373
+ */
+CMX_API int cmx_index_create(int d, int device, cmx_index** out);
+CMX_API int cmx_index_free(cmx_index* ix);
+/* pre-size storage for n rows (avoids re-allocation while adding). */
+CMX_API int cmx_index_reserve(cmx_index* ix, int64_t n);
+/* replaces: index.add(x) / index.add_with_ids(x, ids) (ids stay host-side in the
+ * Python IndexIDMap)  onepass_dense_mix_run_custom_lang.py:719,
+ * onepass_bilingual_mix_hub_custom_lang.py:646,672, encode_multilingual_corpus.py:440 */
+CMX_API int cmx_index_add(cmx_index* ix, const float* x, int64_t n, int x_on_device);
+CMX_API int cmx_index_reset(cmx_index* ix);
+CMX_API int cmx_index_ntotal(const cmx_index* ix, int64_t* out);
+CMX_API int cmx_index_dim(const cmx_index* ix, int* out);
+CMX_API int cmx_index_device(const cmx_index* ix, int* out);
+/* replaces: base_index.reconstruct(i[, out])  onepass_dense_mix_run_custom_lang.py:268-269,
+ * onepass_bilingual_mix_hub_custom_lang.py:644.  Copies rows [i0, i0+n). */
+CMX_API int cmx_index_reconstruct(const cmx_index* ix, int64_t i0, int64_t n, float* out, int out_on_device);
+/* device pointer of the fp32 row store (rows [0, ntotal), leading dim = d);
+ * valid until the next add/reserve/reset/free.  For zero-copy device concat
+ * (bilingual combined-index build, onepass_bilingual_mix_hub_custom_lang.py:606-702). */
+CMX_API int cmx_index_data(const cmx_index* ix, const float** out);
+
+/* ---- search ----------------------------------------------------------------
+ * replaces: D, I = index.search(q_chunk, k)
+ *   onepass_dense_mix_run_custom_lang.py:878 (k=100)
+ *   onepass_bilingual_mix_hub_custom_lang.py:950 (k=--topk)
+ *   onepass_dense_run.py:427,460 (nq=1)
+ * q [nq,d] fp32 row-major; D [nq,k] fp32 sorted descending; I [nq,k] int64 =
+ * id_base + row number, ties by ascending row; tail padded with I=-1,
+ * D=-FLT_MAX when k > ntotal (FAISS semantics).  1 <= k <= CMX_MAX_K. */
+CMX_API int cmx_index_search(cmx_index* ix, const float* q, int64_t nq, int k, float* D, int64_t* I,
+                     int io_on_device, int64_t id_base, int path, void* stream);
+
+/* ---- vector-mix prologue ---------------------------------------------------
+ * replaces: safe_mix(...) called per query per alpha
+ *   onepass_dense_mix_run_custom_lang.py:342-377,853-867
+ *   onepass_bilingual_mix_hub_custom_lang.py:390-424,901-919
+ * out [nA,nq,d]: |alpha|<=1e-8 -> P row; |alpha-1|<=1e-8 -> S row; else
+ * normalize(fl32(1-alpha)*P + fl32(alpha)*S) with each mul/add rounded (no FMA),
+ * x / max(||x||,1e-12); non-finite result -> S row if |alpha|>0.5 else P row.
+ * flags [nA,nq] (may be NULL): 0 ok, 1 fell back to P, 2 fell back to S. */
+CMX_API int cmx_mix_normalize(const float* P, const float* S, int64_t nq, int d, const double* alphas,
+                      int nA, float* out, uint8_t* flags, int io_on_device, int device,
+                      void* stream);
+
+/* ---- fused prologue + search over a batch of alphas -------------------------
+ * replaces the body of the alpha loop: onepass_dense_mix_run_custom_lang.py:846-886,
+ * onepass_bilingual_mix_hub_custom_lang.py:901-919 + 942-952.
+ * D [nA,nq,k], I [nA,nq,k], flags [nA,nq] (may be NULL). */
+CMX_API int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int64_t nq,
+                     const double* alphas, int nA, int k, float* D, int64_t* I, uint8_t* flags,
+                     int io_on_device, int64_t id_base, int path, void* stream);
+
+/* ---- k-way merge of per-shard results (multi-GPU) ---------------------------
+ * new capability (BASELINE north_star (4)); the reference never shards.
+ * D_parts [nparts,nq,k], I_parts [nparts,nq,k] -> D [nq,k], I [nq,k]; order:
+ * score desc, then part number, then position inside the part. */
+CMX_API int cmx_merge_topk(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,
+                   float* D, int64_t* I, int io_on_device, int device, void* stream);
+
+/* ---- instrumentation --------------------------------------------------------*/
+typedef struct cmx_search_stats {
+  int32_t path;            /* CMX_PATH_STREAM / CMX_PATH_TENSOR actually used       */
+  int32_t slabs;           /* corpus slabs (score launches) of the last search      */
+  int32_t reruns;          /* 1 if the candidate buffers overflowed and the search
+                              was repeated with worst-case-safe slabs               */
+  int32_t launches;        /* kernels launched by the last search                   */
+  int64_t nq, ntotal;      /* shape of the last search                              */
+  float score_ms;          /* CUDA-event time inside the scoring kernels (0 unless
+                              cmx_set_profiling(1))                                 */
+  float select_ms;         /* ... inside the compaction / finalize kernels          */
+  float total_ms;          /* ... whole device part of the search                   */
+  int32_t score_launches;
+  int32_t select_launches;
+} cmx_search_stats;
+CMX_API int cmx_index_last_stats(const cmx_index* ix, cmx_search_stats* out);
+/* 1: bracket kernel groups with CUDA events on the launching stream. */
+CMX_API int cmx_set_profiling(int on);
+/* tuning knob (tests): candidate-buffer capacity per query (0 = automatic). */
+CMX_API int cmx_index_set_cand_capacity(cmx_index* ix, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMX_H_ */

@@ -1,0 +1,433 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(ctypes -> libcmx.so), against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE north_star): scores within 1e-5 relative (+1e-6 absolute floor for
+near-zero scores) of the fp32 oracle; ids equal rank by rank except inside score ties
+within that tolerance; the mix is bit-exact and the normalise within 2 ulp.
+"""
+import json
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _unit(rng, n, d):
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+def _aniso(rng, n, d, c=1.5):
+    u = np.random.default_rng(7).standard_normal(d).astype(np.float32)
+    u /= np.linalg.norm(u)
+    x = rng.standard_normal((n, d)).astype(np.float32) + c * np.sqrt(d) * u
+    return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+
+
+def _shard(X, device=0):
+    from cmx.engine import Shard
+
+    sh = Shard(X.shape[1], device)
+    if X.shape[0]:
+        sh.add(X)
+    return sh
+
+
+def _check(D, I, X, Q, k, **kw):
+    Dr, Ir = oracle.flat_ip_search(X, Q, k)
+    rep = oracle.compare_topk(D, I, Dr, Ir, rtol=RTOL, atol=ATOL)
+    assert rep["ok"], rep
+    return rep
+
+
+# ---------------------------------------------------------------- prologue
+def test_mix_golden_bit_exact(golden_dir):
+    from cmx.engine import mix_normalize
+
+    g = np.load(golden_dir / "mix_golden.npz")
+    alphas = g["alphas"].tolist()
+    out, flags = mix_normalize(g["P"], g["S"], alphas, want_flags=True)
+    ref = g["Q"]
+    oq, of = oracle.mix_normalize(g["P"], g["S"], alphas)
+    assert np.array_equal(flags, of)
+    for ai, a in enumerate(alphas):
+        endpoint = abs(a) <= 1e-8 or abs(a - 1.0) <= 1e-8
+        for qi in range(ref.shape[1]):
+            got, want = out[ai, qi], ref[ai, qi]
+            if endpoint or flags[ai, qi]:
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (a, qi)
+            else:
+                ulp = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+                assert ulp.max() <= 2, (a, qi, int(ulp.max()))
+
+
+def test_mix_random_vs_oracle_and_device_io():
+    import torch
+    from cmx.engine import mix_normalize
+
+    rng = np.random.default_rng(10)
+    P, S = _unit(rng, 700, 1024), _unit(rng, 700, 1024)
+    alphas = [0, 0.1, 0.3, 0.5, 0.7, 0.9, 1]
+    out = mix_normalize(P, S, alphas)
+    ref, _ = oracle.mix_normalize(P, S, alphas)
+    ulp = np.abs(out.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 2
+    assert np.array_equal(out[0], P) and np.array_equal(out[-1], S)
+    # unnormalised mix must be bit exact: undo nothing, check through an odd dim (scalar path)
+    P2, S2 = _unit(rng, 33, 70), _unit(rng, 33, 70)
+    o2 = mix_normalize(P2, S2, [0.25])
+    r2, _ = oracle.mix_normalize(P2, S2, [0.25])
+    assert np.abs(o2.view(np.int32).astype(np.int64) - r2.view(np.int32).astype(np.int64)).max() <= 2
+    # device-resident io gives the same bits as host io
+    od = mix_normalize(torch.from_numpy(P).cuda(), torch.from_numpy(S).cuda(), alphas)
+    assert np.array_equal(od.cpu().numpy().view(np.uint32), out.view(np.uint32))
+
+
+# ---------------------------------------------------------------- stream path
+@pytest.mark.parametrize("nq", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("k", [1, 10, 100])
+def test_stream_search_parity(nq, k):
+    rng = np.random.default_rng(100 + nq + k)
+    X, Q = _unit(rng, 20011, 128), _unit(rng, nq, 128)
+    sh = _shard(X)
+    D, I = sh.search(Q, k, path="stream")
+    _check(D, I, X, Q, k)
+    assert sh.last_stats()["path"] == 1
+
+
+def test_stream_many_queries_and_k1000():
+    rng = np.random.default_rng(11)
+    X, Q = _aniso(rng, 50000, 256), _aniso(rng, 21, 256)
+    sh = _shard(X)
+    D, I = sh.search(Q, 1000, path="stream")
+    _check(D, I, X, Q, 1000)
+    assert np.all(np.diff(D, axis=1) <= 0)
+
+
+# ---------------------------------------------------------------- tensor path
+@pytest.mark.parametrize("d", [64, 256, 1024])
+@pytest.mark.parametrize("k", [10, 100, 1000])
+def test_tensor_search_parity(d, k):
+    rng = np.random.default_rng(200 + d + k)
+    X, Q = _unit(rng, 30077, d), _unit(rng, 301, d)
+    sh = _shard(X)
+    D, I = sh.search(Q, k, path="tensor")
+    rep = _check(D, I, X, Q, k)
+    assert sh.last_stats()["path"] == 2
+    assert rep["max_rel_err"] < RTOL
+
+
+def test_tensor_anisotropic_realistic_scores():
+    rng = np.random.default_rng(12)
+    X, Q = _aniso(rng, 40000, 1024), _aniso(rng, 200, 1024)
+    sh = _shard(X)
+    D, I = sh.search(Q, 100, path="tensor")
+    rep = _check(D, I, X, Q, 100)
+    assert D[:, 0].min() > 0.5  # scores in the range real BGE-M3 cosines live in
+    Dt, It = oracle.flat_ip_search_f64(X, Q, 100)
+    assert oracle.compare_topk(D, I, Dt, It, rtol=RTOL, atol=ATOL)["ok"]
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+def test_tensor_tile_variants(bn):
+    from cmx import _lib
+
+    rng = np.random.default_rng(13)
+    X, Q = _unit(rng, 9000, 192), _unit(rng, 130, 192)
+    _lib.check(_lib.lib().cmx_debug_set_tensor_tile(bn))
+    try:
+        sh = _shard(X)
+        D, I = sh.search(Q, 50, path="tensor")
+        _check(D, I, X, Q, 50)
+    finally:
+        _lib.check(_lib.lib().cmx_debug_set_tensor_tile(256))
+
+
+@pytest.mark.parametrize("d", [96, 100, 768])
+def test_tensor_ragged_dims(d):
+    """d not a multiple of 64 -> zero-padded operand planes; N, nq not tile multiples."""
+    rng = np.random.default_rng(14 + d)
+    X, Q = _unit(rng, 5003, d), _unit(rng, 129, d)
+    sh = _shard(X)
+    D, I = sh.search(Q, 20, path="tensor")
+    _check(D, I, X, Q, 20)
+    D2, I2 = sh.search(Q[:5], 20, path="stream")
+    assert oracle.compare_topk(D2, I2, D[:5], I[:5], rtol=RTOL, atol=ATOL)["ok"]
+
+
+def test_tensor_unnormalised_wide_range():
+    """Raw (non unit-norm) vectors with a wide dynamic range: the power-of-two operand
+    scaling keeps the split exact enough."""
+    rng = np.random.default_rng(15)
+    X = (rng.standard_normal((20000, 128)) * np.exp(rng.uniform(-3, 3, (20000, 1)))).astype(np.float32)
+    Q = (rng.standard_normal((64, 128)) * 37.0).astype(np.float32)
+    sh = _shard(X)
+    D, I = sh.search(Q, 30, path="tensor")
+    Dt, It = oracle.flat_ip_search_f64(X, Q, 30)
+    assert oracle.compare_topk(D, I, Dt, It, rtol=RTOL, atol=ATOL)["ok"]
+
+
+# ---------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("path", ["stream", "tensor"])
+def test_k_larger_than_ntotal_pads(path):
+    rng = np.random.default_rng(16)
+    X, Q = _unit(rng, 7, 64), _unit(rng, 3, 64)
+    D, I = _shard(X).search(Q, 12, path=path)
+    Dr, Ir = oracle.flat_ip_search(X, Q, 12)
+    assert np.array_equal(I[:, 7:], Ir[:, 7:]) and (I[:, 7:] == -1).all()
+    assert (D[:, 7:] == np.finfo(np.float32).min).all()
+    assert oracle.compare_topk(D, I, Dr, Ir, rtol=RTOL, atol=ATOL)["ok"]
+
+
+def test_empty_index_and_empty_queries():
+    from cmx.engine import Shard
+
+    sh = Shard(32, 0)
+    D, I = sh.search(np.zeros((2, 32), np.float32), 5)
+    assert (I == -1).all() and (D == np.finfo(np.float32).min).all()
+    sh.add(np.ones((3, 32), np.float32))
+    D, I = sh.search(np.zeros((0, 32), np.float32), 5)
+    assert D.shape == (0, 5) and I.shape == (0, 5)
+
+
+@pytest.mark.parametrize("path", ["stream", "tensor"])
+def test_duplicate_rows_tie_order(path):
+    """Exact ties come out in ascending row order (deterministic; one of FAISS' legal orders)."""
+    rng = np.random.default_rng(17)
+    X = _unit(rng, 3000, 64)
+    X[1000:2000] = X[0:1000]  # every row twice
+    Q = _unit(rng, 6, 64)
+    D, I = _shard(X).search(Q, 40, path=path)
+    Dr, Ir = oracle.flat_ip_search(X, Q, 40)
+    assert oracle.compare_topk(D, I, Dr, Ir, rtol=RTOL, atol=ATOL)["ok"]
+    pairs = 0
+    for r in range(6):
+        row = I[r].tolist()
+        for pos, a in enumerate(row):
+            if a < 1000 and (a + 1000) in row:
+                # the copy scores bit-identically and must follow its original immediately
+                assert row[pos + 1] == a + 1000 and D[r, pos] == D[r, pos + 1], (r, a)
+                pairs += 1
+    assert pairs > 0
+
+
+@pytest.mark.parametrize("path", ["stream", "tensor"])
+def test_zero_and_nan_queries(path):
+    rng = np.random.default_rng(18)
+    X = _unit(rng, 900, 64)
+    Q = _unit(rng, 4, 64)
+    Q[1] = 0.0  # P = -S at alpha = 0.5: all scores tie at 0 -> first k rows
+    Q[2, 5] = np.nan  # never enters a FAISS heap -> all -1
+    D, I = _shard(X).search(Q, 10, path=path)
+    assert I[1].tolist() == list(range(10)) and (D[1] == 0).all()
+    assert (I[2] == -1).all() and (D[2] == np.finfo(np.float32).min).all()
+    Dr, Ir = oracle.flat_ip_search(X, Q[[0, 3]], 10)
+    assert oracle.compare_topk(D[[0, 3]], I[[0, 3]], Dr, Ir, rtol=RTOL, atol=ATOL)["ok"]
+
+
+@pytest.mark.parametrize("path", ["stream", "tensor"])
+def test_adversarial_order_triggers_safe_rerun(path):
+    """Rows sorted by ascending score for one query: every row beats the stale threshold,
+    the candidate buffer overflows, the search is redone with worst-case-safe slabs."""
+    rng = np.random.default_rng(19)
+    d = 64
+    q = _unit(rng, 1, d)
+    X = _unit(rng, 12000, d)
+    X = X[np.argsort(X @ q[0])]  # ascending score for q
+    Q = np.concatenate([q, _unit(rng, 9, d)], axis=0)
+    sh = _shard(X)
+    sh.set_cand_capacity(256)
+    D, I = sh.search(Q, 100, path=path)
+    st = sh.last_stats()
+    assert st["reruns"] == 1, st
+    _check(D, I, X, Q, 100)
+
+
+def test_incremental_add_and_reconstruct():
+    rng = np.random.default_rng(20)
+    X, Q = _unit(rng, 5000, 128), _unit(rng, 40, 128)
+    from cmx.engine import Shard
+
+    sh = Shard(128, 0)
+    for a, b in ((0, 1), (1, 700), (700, 701), (701, 5000)):  # forces store growth
+        sh.add(X[a:b])
+    assert sh.ntotal == 5000
+    assert np.array_equal(sh.reconstruct_n(0, 5000), X)
+    D, I = sh.search(Q, 25, path="tensor")
+    _check(D, I, X, Q, 25)
+    sh.add(X[:300] * np.float32(64.0))  # larger magnitude -> operand planes are re-scaled
+    X2 = np.concatenate([X, X[:300] * np.float32(64.0)])
+    D, I = sh.search(Q, 25, path="tensor")
+    _check(D, I, X2, Q, 25)
+    D, I = sh.search(Q[:3], 25, path="stream")
+    _check(D, I, X2, Q[:3], 25)
+
+
+def test_device_tensors_zero_copy():
+    import torch
+
+    rng = np.random.default_rng(21)
+    X, Q = _unit(rng, 8000, 128), _unit(rng, 150, 128)
+    from cmx.engine import Shard
+
+    sh = Shard(128, 0)
+    sh.add(torch.from_numpy(X).cuda())
+    Dd, Id = sh.search(torch.from_numpy(Q).cuda(), 30)
+    assert Dd.is_cuda and Id.dtype == torch.int64
+    Dh, Ih = sh.search(Q, 30)
+    assert np.array_equal(Dd.cpu().numpy(), Dh) and np.array_equal(Id.cpu().numpy(), Ih)
+    _check(Dh, Ih, X, Q, 30)
+
+
+# ---------------------------------------------------------------- fused + merge + shim
+def test_search_mixed_equals_mix_then_search():
+    from cmx.engine import mix_normalize
+
+    rng = np.random.default_rng(22)
+    X = _aniso(rng, 25000, 256)
+    P = _aniso(rng, 140, 256)
+    S = _aniso(rng, 140, 256)
+    alphas = [0, 0.1, 0.5, 1]
+    sh = _shard(X)
+    D, I, flags = sh.search_mixed(P, S, alphas, 100, want_flags=True)
+    assert D.shape == (4, 140, 100) and not flags.any()
+    Qm = mix_normalize(P, S, alphas)
+    for ai in range(4):
+        D1, I1 = sh.search(Qm[ai], 100)
+        assert np.array_equal(D[ai], D1) and np.array_equal(I[ai], I1)
+    Qo, _ = oracle.mix_normalize(P, S, alphas)
+    for ai in range(4):
+        _check(D[ai], I[ai], X, Qo[ai], 100)
+
+
+def test_merge_and_sharded_equal_single():
+    from cmx.engine import merge_topk
+    import cmx.faiss as faiss
+
+    rng = np.random.default_rng(23)
+    X, Q = _unit(rng, 21000, 128), _unit(rng, 77, 128)
+    X[15000:15500] = X[100:600]  # ties across shard boundaries
+    k = 64
+    D1, I1 = _shard(X).search(Q, k, path="tensor")
+    bounds = faiss.IndexShardsIP.split(X.shape[0], 3)
+    parts = [_shard(X[a:b]).search(Q, k, id_base=a, path="tensor") for a, b in zip(bounds[:-1], bounds[1:])]
+    Dp, Ip = np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts])
+    Dm, Im = merge_topk(Dp, Ip)
+    assert np.array_equal(Im, I1) and np.array_equal(Dm, D1)
+    Do, Io = oracle.merge_topk(Dp, Ip, k)
+    assert np.array_equal(Im, Io) and np.array_equal(Dm, Do)
+    # the single-process multi-GPU index (here: all shards on GPU 0) gives the same answer
+    cpu = faiss.IndexFlatIP(128)
+    cpu.add(X)
+    sharded = faiss.index_cpu_to_gpus_list(cpu, gpus=[0, 0, 0])
+    sharded.path = "tensor"
+    Ds, Is = sharded.search(Q, k)
+    assert np.array_equal(Is, I1) and np.array_equal(Ds, D1)
+
+
+def test_faiss_shim_dropin_flow(tmp_path):
+    """The call sequence of onepass_dense_mix_run_custom_lang.py on a synthetic cached index."""
+    import cmx.faiss as faiss
+
+    rng = np.random.default_rng(24)
+    X, Q = _unit(rng, 6000, 64), _unit(rng, 50, 64)
+    ids = np.arange(6000, dtype=np.int64)[::-1].copy() + 10_000
+    cpu = faiss.IndexIDMap(faiss.IndexFlatIP(64))
+    cpu.add_with_ids(X, ids)
+    faiss.write_index(cpu, str(tmp_path / "index.faiss"))
+    cached = faiss.read_index(str(tmp_path / "index.faiss"))
+    base = faiss.downcast_index(cached.index)
+    base.reconstruct(0, np.empty((64,), np.float32))
+    res = faiss.StandardGpuResources()
+    gpu = faiss.index_cpu_to_gpu(res, 0, cached)
+    D, I = gpu.search(Q, 100)
+    Dr, Ir = oracle.flat_ip_search(X, Q, 100, ids=ids)
+    assert oracle.compare_topk(D, I, Dr, Ir, rtol=RTOL, atol=ATOL)["ok"]
+    # the CPU index stays valid and independent; searching it runs on the GPU as well
+    cached.add_with_ids(X[:10], np.arange(10))
+    assert cached.ntotal == 6010 and gpu.ntotal == 6000
+    D2, I2 = cached.search(Q[:4], 5)
+    assert D2.shape == (4, 5)
+    with pytest.raises(AssertionError):
+        gpu.search(np.zeros((1, 65), np.float32), 3)
+    with pytest.raises(RuntimeError):
+        gpu.search(Q, 5000)  # k above the engine cap -> RuntimeError like faiss-gpu
+    back = faiss.index_gpu_to_cpu(gpu)
+    assert back.ntotal == 6000 and np.array_equal(back.index.reconstruct_n(0, 6000), X)
+
+
+def test_run_alpha_sweep_files(tmp_path):
+    import cmx.faiss as faiss
+    from cmx import runloop
+
+    rng = np.random.default_rng(25)
+    X = _aniso(rng, 9000, 128)
+    P, S = _aniso(rng, 60, 128), _aniso(rng, 60, 128)
+    qids = [str(1000 + 3 * i) for i in range(60)]
+    lookup = {i: f"d{i * 11}" for i in range(9000)}
+    idx = faiss.IndexIDMap(faiss.GpuIndexFlatIP(128))
+    idx.add_with_ids(X, np.arange(9000))
+    alphas = [0.0, 0.25, 0.5, 1.0]
+    files = runloop.run_alpha_sweep(idx, lookup, qids, P, S, alphas, tmp_path / "mono", k=100, alpha_batch=2)
+    assert [f.name for f in files] == ["cm-alpha-0.trec", "cm-alpha-0.25.trec", "cm-alpha-0.5.trec", "cm-alpha-1.trec"]
+    Qo, _ = oracle.mix_normalize(P, S, alphas)
+    for ai, f in enumerate(files):
+        D, I = idx.search(Qo[ai], 100)
+        _check(D, I, X, Qo[ai], 100)
+        # byte-identical to what the reference loop writes for this (D, I)
+        assert f.read_text() == "\n".join(oracle.mono_trec_lines(qids, D, I, lookup))
+    # bilingual: two derived ids per base document
+    id2doc = [f"{i // 2}#{'en' if i % 2 == 0 else 'zh'}" for i in range(9000)]
+    files = runloop.run_alpha_sweep_bilingual(idx, id2doc, qids, P, S, [0.5], tmp_path / "bi", topk=500,
+                                              tag="bilingual-mix-en-zh")
+    D, I = idx.search(Qo[2], 500)
+    raw = oracle.bilingual_raw_lines(qids, D, I, id2doc, "bilingual-mix-en-zh")
+    assert (tmp_path / "bi" / "cm-alpha-0.5_raw.trec").read_text() == "".join(raw)
+    assert files[0].read_text() == oracle.collapse_run_max_text(raw)
+    meta = json.loads((tmp_path / "bi" / "cm-alpha-0.5_meta.json").read_text())
+    assert meta["topk"] == 500 and meta["alpha"] == "0.5"
+
+
+# ---------------------------------------------------------------- larger-size properties
+def test_large_properties_tensor_vs_stream_and_recompute():
+    """1M x 1024 on device: size-independent properties + agreement of the two paths."""
+    import torch
+    from cmx.engine import Shard
+
+    d, N, nq, k = 1024, 1_000_000, 512, 1000
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    sh = Shard(d, 0)
+    sh.reserve(N)
+    chunks = []
+    for c in range(0, N, 1 << 18):
+        x = torch.randn((min(1 << 18, N - c), d), generator=g, device="cuda")
+        x = torch.nn.functional.normalize(x, dim=1)
+        sh.add(x)
+        chunks.append(x)
+    X = torch.cat(chunks)
+    del chunks
+    Q = torch.nn.functional.normalize(torch.randn((nq, d), generator=g, device="cuda"), dim=1)
+    D, I = sh.search(Q, k, path="tensor")
+    assert sh.last_stats()["reruns"] == 0
+    assert bool((D[:, 1:] <= D[:, :-1]).all())  # sorted descending
+    assert int(I.min()) >= 0 and int(I.max()) < N
+    srt = torch.sort(I, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())  # no duplicate ids in a row
+    # recompute the returned scores in fp64 on the device
+    rec = torch.einsum("qkd,qd->qk", X[I[:64]].double(), Q[:64].double())
+    assert float(((rec - D[:64].double()).abs() / rec.abs().clamp_min(1e-30)).max()) < RTOL
+    # completeness: nothing outside the list beats the k-th score by more than the tolerance
+    full = Q[:8].double() @ X.double().T
+    kth = D[:8, -1].double()
+    above = (full > (kth * (1 + RTOL) + ATOL)[:, None]).sum(dim=1)
+    assert bool((above <= k).all()) and bool((above >= k - 5).all())
+    # the fp32 streaming path agrees with the tensor path
+    Ds, Is = sh.search(Q[:8], k, path="stream")
+    rep = oracle.compare_topk(Ds.cpu().numpy(), Is.cpu().numpy(), D[:8].cpu().numpy(), I[:8].cpu().numpy(),
+                              rtol=RTOL, atol=ATOL)
+    assert rep["ok"], rep

@@ -1,0 +1,193 @@
+"""Host-side logic (no GPU): labels, vectorised TREC text, collapse, file formats,
+and that libcmx.so loads and exports every symbol include/cmx.h declares."""
+import ctypes
+import json
+import pathlib
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from cmx import runloop
+from cmx import io as cio
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def test_labels_match_golden(golden_dir):
+    g = json.loads((golden_dir / "text_golden.json").read_text())
+    assert [runloop.format_alpha(a) for a in g["format_alpha"]["in"]] == g["format_alpha"]["out"]
+    for s, want in zip(g["parse_alpha_list"]["in"], g["parse_alpha_list"]["out"]):
+        try:
+            got = runloop.parse_alpha_list(s)
+        except SystemExit as exc:
+            got = {"SystemExit": str(exc)}
+        assert got == want
+
+
+def test_format_scores_matches_python(golden_dir):
+    g = json.loads((golden_dir / "text_golden.json").read_text())
+    sc = np.array([np.frombuffer(bytes.fromhex(h), dtype=np.float32)[0] for h in g["trec_scores_f32_hex"]])
+    rng = np.random.default_rng(5)
+    more = np.concatenate([sc, rng.uniform(-1, 1, 20000).astype(np.float32),
+                           (rng.integers(0, 20000, 5000) / 20000.0 + 0.000025).astype(np.float32),
+                           np.array([np.nan, np.inf, -np.inf, 1e12, -2.5e15], np.float32)])
+    for dec in (4, 6):
+        got = runloop.format_scores(more, dec).tolist()
+        want = [f"{float(v):.{dec}f}" for v in more]
+        assert got == want
+
+
+def _fake_results(rng, nq, k, nrows):
+    D = -np.sort(-rng.uniform(-0.2, 0.9, (nq, k)).astype(np.float32), axis=1)
+    I = rng.integers(0, nrows, (nq, k)).astype(np.int64)
+    return D, I
+
+
+def test_mono_text_equals_oracle_lines():
+    rng = np.random.default_rng(6)
+    D, I = _fake_results(rng, 13, 50, 400)
+    I[3, 40:] = -1
+    D[3, 40:] = np.finfo(np.float32).min
+    I[5, 7] = 399  # not in lookup -> str(id)
+    lookup = {i: f"doc{i * 7}" for i in range(399)}
+    qids = [str(100 + i) for i in range(13)]
+    want = "\n".join(oracle.mono_trec_lines(qids, D, I, lookup))
+    assert runloop.mono_trec_text(qids, D, I, runloop.DocTable(lookup)) == want
+
+
+def test_bilingual_raw_and_collapse_equal_oracle():
+    rng = np.random.default_rng(7)
+    nq, k, nrows = 9, 60, 80
+    D, I = _fake_results(rng, nq, k, nrows)
+    D[:, 10] = D[:, 9]  # exact ties
+    D[:, 21] = D[:, 20] - np.float32(3e-8)  # ties after 6-decimal rounding
+    I[2, 5] = -1
+    I[4, 8] = nrows + 3  # out of range -> skipped, rank kept
+    id2doc = [f"{i // 2}#{'en' if i % 2 == 0 else 'zh'}" for i in range(nrows)]
+    qids = [f"q{i}" for i in range(nq)]
+    tag = "bilingual-mix-en-zh"
+    raw_lines = oracle.bilingual_raw_lines(qids, D, I, id2doc, tag)
+    assert runloop.bilingual_raw_text(qids, D, I, id2doc, tag) == "".join(raw_lines)
+    want = oracle.collapse_run_max_text(raw_lines)
+    assert runloop.collapse_by_base(qids, D, I, id2doc) == want
+
+
+def test_collapse_text_form_matches_golden(golden_dir, tmp_path):
+    g = json.loads((golden_dir / "text_golden.json").read_text())
+    pin, pout = tmp_path / "x_raw.trec", tmp_path / "x.trec"
+    pin.write_text("".join(g["collapse"]["raw"]))
+    runloop.collapse_run_max(pin, pout)
+    assert pout.read_text() == g["collapse"]["out"]
+
+
+def test_query_cache_roundtrip(tmp_path):
+    rng = np.random.default_rng(8)
+    qids = [str(i) for i in (5, 3, 11)]
+    vecs = rng.standard_normal((3, 8)).astype(np.float32)
+    cio.save_query_cache(tmp_path, "en", qids, vecs)
+    assert np.array_equal(cio.load_query_cache(tmp_path, "en", qids), vecs)
+    assert cio.load_query_cache(tmp_path, "en", qids[::-1]) is None  # order matters
+    assert cio.load_query_cache(tmp_path, "zh", qids) is None
+    cio.save_query_cache(tmp_path, "zh", qids, {q: v for q, v in zip(qids, vecs)})
+    assert np.array_equal(cio.load_query_cache(tmp_path, "zh", qids), vecs)
+
+
+def test_docid_map_roundtrip(tmp_path):
+    p = tmp_path / "docid_map.tsv"
+    cio.write_docid_map(p, [0, 1, 2], ["7#en", "9#en", "4#en"], ["7", "9", "4"], "en")
+    with open(p, "a") as fh:
+        fh.write("bad\tline\n")
+        fh.write("x\ty\tz\tw\n")
+    lookup, kept, derived = cio.read_docid_map(p)
+    assert lookup == {0: "7", 1: "9", 2: "4"} and kept == ["7", "9", "4"] and derived == ["7#en", "9#en", "4#en"]
+
+
+def test_index_file_roundtrip(tmp_path):
+    import cmx.faiss as faiss
+
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((37, 12)).astype(np.float32)
+    ids = rng.permutation(1000)[:37].astype(np.int64)
+    idx = faiss.IndexIDMap(faiss.IndexFlatIP(12))
+    idx.add_with_ids(x, ids)
+    faiss.write_index(idx, tmp_path / "index.faiss")
+    raw = (tmp_path / "index.faiss").read_bytes()
+    assert raw[:4] == b"IxMp" and raw[4 + 33: 4 + 37] == b"IxFI"
+    assert len(raw) == 2 * (4 + 33) + 8 + 37 * 12 * 4 + 8 + 37 * 8
+    back = faiss.read_index(str(tmp_path / "index.faiss"))
+    assert back.d == 12 and back.ntotal == 37
+    assert np.array_equal(back.id_map, ids)
+    base = faiss.downcast_index(back.index)
+    tmp = np.empty((12,), np.float32)
+    base.reconstruct(0, tmp)
+    assert np.array_equal(tmp, x[0])
+    assert np.array_equal(base.reconstruct_n(0, 37), x)
+    with pytest.raises(RuntimeError):
+        back.reconstruct(0)
+    flat = faiss.IndexFlatIP(12)
+    flat.add(x)
+    faiss.write_index(flat, tmp_path / "flat.faiss")
+    assert np.array_equal(faiss.read_index(tmp_path / "flat.faiss").reconstruct_n(0, 37), x)
+    (tmp_path / "bad.faiss").write_bytes(b"IxXX" + raw[4:])
+    with pytest.raises(RuntimeError):
+        faiss.read_index(tmp_path / "bad.faiss")
+    (tmp_path / "trunc.faiss").write_bytes(raw[:200])
+    with pytest.raises(RuntimeError):
+        faiss.read_index(tmp_path / "trunc.faiss")
+
+
+def test_faiss_shim_host_semantics():
+    import cmx.faiss as faiss
+
+    assert hasattr(faiss, "StandardGpuResources")  # the reference's feature probe
+    idx = faiss.IndexIDMap(faiss.IndexFlatIP(4))
+    with pytest.raises(AssertionError):
+        idx.add_with_ids(np.zeros((2, 5), np.float32), np.arange(2))
+    with pytest.raises(AssertionError):
+        idx.add_with_ids(np.zeros((2, 4), np.float32), np.arange(3))
+    x = np.arange(8, dtype=np.float64).reshape(2, 4)  # coerced to float32, copied
+    idx.add_with_ids(x, [10, 20])
+    x[:] = -1
+    assert idx.ntotal == 2 and idx.index.reconstruct(1).tolist() == [4.0, 5.0, 6.0, 7.0]
+    with pytest.raises(RuntimeError):
+        idx.index.reconstruct(2)
+    with pytest.raises(RuntimeError):
+        faiss.IndexIDMap(idx.index)
+    assert faiss.IndexShardsIP.split(10, 4) == [0, 2, 5, 7, 10]
+
+
+def test_library_exports_every_declared_symbol():
+    from cmx import _lib
+
+    header = (ROOT / "include" / "cmx.h").read_text()
+    declared = sorted(set(re.findall(r"CMX_API\s+[\w\s\*]+?\b(cmx_\w+)\s*\(", header)))
+    assert len(declared) >= 20, declared
+    assert _lib.LIB_PATH.exists(), "libcmx.so not built (python codemix-dense-retrieval_b200/build.py)"
+    L = ctypes.CDLL(str(_lib.LIB_PATH))
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    _lib.lib()  # prototypes bind
+    assert L.cmx_version() >= 100
+
+
+def test_no_gpu_fails_loudly():
+    """Without a CUDA device the product path must raise, never fall back to the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import cmx.faiss as faiss
+    from cmx import engine
+
+    with pytest.raises(RuntimeError):
+        faiss.StandardGpuResources()
+    with pytest.raises(RuntimeError):
+        engine.Shard(8, 0)
+    idx = faiss.IndexFlatIP(8)
+    idx.add(np.zeros((3, 8), np.float32))
+    with pytest.raises(RuntimeError):
+        idx.search(np.zeros((1, 8), np.float32), 2)
+    with pytest.raises(RuntimeError):
+        engine.mix_normalize(np.zeros((2, 8), np.float32), np.zeros((2, 8), np.float32), [0.5])
