@@ -104,6 +104,7 @@ int launch_stream_score(const float* X, int64_t row0, int64_t nrows, int d, cons
                         int nq, const SearchWs& ws, int64_t q0, int dense, int64_t dense_row0,
                         cudaStream_t st, int sm_count);
 
+void set_stream_variant(int v);  // tuning experiments
 int tensor_path_available();
 void set_tensor_tile(int bn);  // 256 (default) or 128 corpus rows per tile
 int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,

@@ -1,5 +1,5 @@
-// k-selection: candidate-buffer compaction (bitonic sort in shared memory),
-// final (D, I) emission and the k-way merge of per-shard results.
+// k-selection: candidate-buffer compaction (radix select + small bitonic sort in shared
+// memory), final (D, I) emission and the k-way merge of per-shard results.
 //
 // Replaces FAISS's blockSelect / heap pass behind index.search
 // (reference call sites onepass_dense_mix_run_custom_lang.py:878,
@@ -7,9 +7,16 @@
 // materialise the score matrix: they append (score,row) keys that beat the
 // query's running threshold tau to a per-query buffer; this file turns the
 // buffers into exact, deterministically ordered top-k lists.
+//
+// Keys are distinct 64-bit integers (score-ordered high word, ~row low word), so the
+// k-th largest key is found exactly by an MSB-first radix select (8-bit digits, shared
+// memory histogram, digits above the first bit where min and max differ are skipped);
+// only the k survivors are ever sorted, and only in the final pass.
 #include "common.cuh"
 
 namespace cmx {
+
+constexpr int kSelThreads = 512;
 
 __global__ void ws_init_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, int64_t nq, int64_t nq_pad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,38 +71,149 @@ __device__ __forceinline__ int next_pow2(int n) {
   return p;
 }
 
-// One CTA per query.  Sorts the query's candidates, keeps the best k at the front
-// of its buffer and sets tau to the k-th best score.  Because later corpus slabs
-// only hold larger row numbers, "score > tau" (strict) is then an exact filter
-// under the (score desc, row asc) order.
-__global__ void __launch_bounds__(512)
+struct SelectShared {
+  uint32_t hist[256];
+  uint64_t red_min[32];
+  uint64_t red_max[32];
+  uint64_t kmin, kmax;
+  uint32_t bin, above, count;
+};
+
+// Exact k-th largest of the n DISTINCT keys in smem (1 <= k < n).  All threads of the
+// CTA must call; returns the same value to every thread.
+__device__ uint64_t block_kth_largest(const uint64_t* keys, int n, int k, SelectShared& sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  uint64_t mn = ~0ull, mx = 0ull;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t v = keys[i];
+    mn = min(mn, v);
+    mx = max(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) { sh.red_min[warp] = mn; sh.red_max[warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    mn = (lane < nwarps) ? sh.red_min[lane] : ~0ull;
+    mx = (lane < nwarps) ? sh.red_max[lane] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { sh.kmin = mn; sh.kmax = mx; }
+  }
+  __syncthreads();
+  const uint64_t kmin = sh.kmin, kmax = sh.kmax;
+  const uint64_t diff = kmin ^ kmax;
+  if (diff == 0ull) return kmax;  // all keys equal: only possible for the null key
+  const int top_byte = (63 - __clzll((long long)diff)) >> 3;
+  // digits above top_byte are common to all keys
+  uint64_t mask = (top_byte == 7) ? 0ull : (~0ull << ((top_byte + 1) * 8));
+  uint64_t prefix = kmax & mask;
+  uint32_t want = (uint32_t)k;  // rank (1 = largest) among the keys matching the prefix
+  for (int shift = top_byte * 8; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh.hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t v = keys[i];
+      if ((v & mask) == prefix) atomicAdd(&sh.hist[(uint32_t)(v >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // lane l owns digits [8l, 8l+8); find the digit where the count from the top crosses `want`
+      uint32_t h[8], s = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { h[j] = sh.hist[lane * 8 + j]; s += h[j]; }
+      uint32_t incl = s;  // inclusive suffix sum over lanes (lane 31 = highest digits)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += t;
+      }
+      uint32_t running = incl - s;  // keys in digits above this lane's range
+#pragma unroll
+      for (int j = 7; j >= 0; --j) {
+        if (running < want && want <= running + h[j]) { sh.bin = lane * 8 + j; sh.above = running; }
+        running += h[j];
+      }
+    }
+    __syncthreads();
+    want -= sh.above;
+    prefix |= (uint64_t)sh.bin << shift;
+    mask |= 0xffull << shift;
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// Appends the survivors to dst (smem or global), order arbitrary, and returns how many:
+// the keys >= kth (exactly k of them, real keys are distinct), or -- when the k-th largest
+// is the null key, i.e. fewer than k real candidates exist -- all non-null keys.
+__device__ int block_partition(const uint64_t* keys, int n, uint64_t kth, uint64_t* dst, SelectShared& sh) {
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) sh.count = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const uint64_t v = (i < n) ? keys[i] : 0ull;
+    const bool keep = (i < n) && ((kth != 0ull) ? (v >= kth) : (v != 0ull));
+    const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+    uint32_t wbase = 0;
+    if (lane == 0 && ballot) wbase = atomicAdd(&sh.count, (uint32_t)__popc(ballot));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (keep) dst[wbase + __popc(ballot & ((1u << lane) - 1u))] = v;
+  }
+  __syncthreads();
+  return (int)sh.count;
+}
+
+// One CTA per query.  Keeps the query's best k candidates at the front of its buffer and
+// sets tau to the k-th best score.  Because later corpus slabs only hold larger row
+// numbers, "score > tau" (strict) is then an exact filter under the (score desc, row
+// asc) order.  final_pass additionally sorts the survivors and writes D / I.
+// dynamic smem: cap keys, then next_pow2(k) keys for the final sort
+__global__ void __launch_bounds__(kSelThreads)
 compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* __restrict__ tau,
                uint32_t* __restrict__ overflow, int cap, int k, int final_pass,
                float* __restrict__ D, int64_t* __restrict__ I, int64_t id_base) {
   extern __shared__ __align__(16) uint64_t keys[];
+  __shared__ SelectShared sh;
   const int64_t q = blockIdx.x;
   const uint32_t n_raw = cnt[q];
   if (n_raw > (uint32_t)cap && threadIdx.x == 0) atomicExch(overflow, 1u);
   const int n = (int)min(n_raw, (uint32_t)cap);
   if (!final_pass && n <= k) return;  // nothing to drop yet; tau stays
   uint64_t* buf = cand + q * (int64_t)cap;
-  const int P = next_pow2(max(n, 2));
-  for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = (i < n) ? buf[i] : 0ull;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = buf[i];
   __syncthreads();
-  bitonic_sort_desc(keys, P);
-  const int kk = min(n, k);
-  for (int i = threadIdx.x; i < kk; i += blockDim.x) buf[i] = keys[i];
-  if (threadIdx.x == 0) {
-    cnt[q] = (uint32_t)kk;
-    if (n >= k && keys[k - 1] != 0ull) tau[q] = key_score(keys[k - 1]);
+  uint64_t* top = keys + cap;  // survivors (final pass only)
+  int kk = n;
+  if (n > k) {
+    const uint64_t kth = block_kth_largest(keys, n, k, sh);
+    kk = block_partition(keys, n, kth, final_pass ? top : buf, sh);
+    if (threadIdx.x == 0) {
+      cnt[q] = (uint32_t)kk;
+      if (kth != 0ull) tau[q] = key_score(kth);
+    }
+  } else if (final_pass) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) top[i] = keys[i];
+    __syncthreads();
   }
   if (final_pass) {
+    const int P = next_pow2(max(kk, 2));
+    for (int i = kk + threadIdx.x; i < P; i += blockDim.x) top[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(top, P);
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
       float s = CMX_NEG_PAD;
       int64_t id = -1;
-      if (i < kk && keys[i] != 0ull) {
-        s = key_score(keys[i]);
-        id = id_base + (int64_t)key_row(keys[i]);
+      if (i < kk && top[i] != 0ull) {
+        s = key_score(top[i]);
+        id = id_base + (int64_t)key_row(top[i]);
       }
       D[q * k + i] = s;
       I[q * k + i] = id;
@@ -103,44 +221,76 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
   }
 }
 
+static int pow2_at_least(int n) {
+  int p = 2;
+  while (p < n) p <<= 1;
+  return p;
+}
+
 int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float* D, int64_t* I,
                    int64_t id_base, cudaStream_t st) {
   if (nq == 0) return CMX_OK;
-  const size_t smem = (size_t)ws.cap * sizeof(uint64_t);
+  const size_t smem = ((size_t)ws.cap + pow2_at_least(k)) * sizeof(uint64_t);
   CMX_CUDA(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  compact_kernel<<<(unsigned)nq, 512, smem, st>>>(ws.cand, ws.cnt, ws.tau, ws.overflow, ws.cap, k,
-                                                  final_pass, D, I, id_base);
+  compact_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(ws.cand, ws.cnt, ws.tau, ws.overflow, ws.cap, k,
+                                                          final_pass, D, I, id_base);
   CMX_LAUNCHED();
   return CMX_OK;
 }
 
 // k-way merge: parts are individually sorted (score desc, row asc) and ordered by
 // ascending row range, so (part, position) is the tie-break that reproduces the
-// single-shard order exactly.
-__global__ void __launch_bounds__(512)
+// single-shard order exactly.  dynamic smem: nparts*k keys, then next_pow2(k) keys
+__global__ void __launch_bounds__(kSelThreads)
 merge_kernel(const float* __restrict__ Dp, const int64_t* __restrict__ Ip, int nparts, int64_t nq,
              int k, float* __restrict__ D, int64_t* __restrict__ I) {
   extern __shared__ __align__(16) uint64_t keys[];
+  __shared__ SelectShared sh;
+  __shared__ uint32_t s_valid;
   const int64_t q = blockIdx.x;
-  const int n = nparts * k;
-  const int P = next_pow2(max(n, 2));
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    uint64_t key = 0ull;
-    if (i < n) {
-      const int g = i / k, pos = i - g * k;
-      const int64_t src = ((int64_t)g * nq + q) * k + pos;
-      if (Ip[src] >= 0) key = make_key(Dp[src], (uint32_t)i);
+  const int n_all = nparts * k;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  // compact the valid (id >= 0) entries of all parts into keys[0..n)
+  {
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < n_all; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      bool valid = false;
+      uint64_t key = 0ull;
+      if (i < n_all) {
+        const int g = i / k, pos = i - g * k;
+        const int64_t src = ((int64_t)g * nq + q) * k + pos;
+        valid = Ip[src] >= 0;
+        if (valid) key = make_key(Dp[src], (uint32_t)i);
+      }
+      const uint32_t ballot = __ballot_sync(0xffffffffu, valid);
+      uint32_t wbase = 0;
+      if (lane == 0 && ballot) wbase = atomicAdd(&s_valid, (uint32_t)__popc(ballot));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (valid) keys[wbase + __popc(ballot & ((1u << lane) - 1u))] = key;
     }
-    keys[i] = key;
   }
   __syncthreads();
-  bitonic_sort_desc(keys, P);
+  const int n = (int)s_valid;
+  uint64_t* top = keys + n_all;
+  int kk = n;
+  if (n > k) {
+    const uint64_t kth = block_kth_largest(keys, n, k, sh);
+    kk = block_partition(keys, n, kth, top, sh);
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) top[i] = keys[i];
+    __syncthreads();
+  }
+  const int P = next_pow2(max(kk, 2));
+  for (int i = kk + threadIdx.x; i < P; i += blockDim.x) top[i] = 0ull;
+  __syncthreads();
+  bitonic_sort_desc(top, P);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     float s = CMX_NEG_PAD;
     int64_t id = -1;
-    const uint64_t key = keys[i];
-    if (i < n && key != 0ull) {
-      const uint32_t src_i = key_row(key);
+    if (i < kk) {
+      const uint32_t src_i = key_row(top[i]);
       const int g = src_i / k, pos = src_i - g * k;
       const int64_t src = ((int64_t)g * nq + q) * k + pos;
       s = Dp[src];
@@ -154,16 +304,13 @@ merge_kernel(const float* __restrict__ Dp, const int64_t* __restrict__ Ip, int n
 int launch_merge(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,
                  float* D, int64_t* I, cudaStream_t st) {
   if (nq == 0) return CMX_OK;
-  int n = nparts * k;
-  int P = 2;
-  while (P < n) P <<= 1;
-  const size_t smem = (size_t)P * sizeof(uint64_t);
+  const size_t smem = ((size_t)nparts * k + pow2_at_least(k)) * sizeof(uint64_t);
   if (smem > 200 * 1024) {
-    set_error("merge: nparts*k = %d too large for one shared-memory sort", n);
+    set_error("merge: nparts*k = %d too large for one shared-memory selection", nparts * k);
     return CMX_ERR_INVALID;
   }
   CMX_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_kernel<<<(unsigned)nq, 512, smem, st>>>(D_parts, I_parts, nparts, nq, k, D, I);
+  merge_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(D_parts, I_parts, nparts, nq, k, D, I);
   CMX_LAUNCHED();
   return CMX_OK;
 }

@@ -25,17 +25,17 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 }
 
 constexpr int kStreamThreads = 256;
-constexpr int kStreamUnroll = 4;
 
-template <int B, int R>
-__global__ void __launch_bounds__(kStreamThreads, 3)
+// B queries per pass, R rows per warp iteration, U 128-bit loads per row in flight,
+// MINB resident CTAs per SM the register budget is sized for
+template <int B, int R, int U, int MINB>
+__global__ void __launch_bounds__(kStreamThreads, MINB)
 stream_score_kernel(const float* __restrict__ X, int64_t row0, int64_t nrows, int d,
                     const float* __restrict__ Q, int nq, const float* __restrict__ tau,
                     uint32_t* __restrict__ cnt, uint64_t* __restrict__ cand, int cap, int dense,
                     int64_t dense_row0) {
   extern __shared__ __align__(16) float Qs[];  // [B][d]
   constexpr int NV = R * B;
-  constexpr int U = kStreamUnroll;
   static_assert(NV <= 32 && (NV & (NV - 1)) == 0, "R*B must be a power of two <= 32");
   const int lane = threadIdx.x & 31;
   const int d4 = d >> 2;
@@ -79,9 +79,10 @@ stream_score_kernel(const float* __restrict__ X, int64_t row0, int64_t nrows, in
       if (rr >= nrows) rr = nrows - 1;  // clamp; result discarded below
       xr[r] = reinterpret_cast<const float4*>(X + (row0 + rr) * (int64_t)d);
     }
-    float acc[NV];
+    // packed fp32 FMA (FFMA2, sm_100): two independent partial sums per (row, query)
+    float2 acc2[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NV; ++i) acc2[i] = make_float2(0.f, 0.f);
 
     for (int j0 = 0; j0 < d4; j0 += 32 * U) {
       float4 x[R][U];
@@ -99,18 +100,20 @@ stream_score_kernel(const float* __restrict__ X, int64_t row0, int64_t nrows, in
 #pragma unroll
         for (int qi = 0; qi < B; ++qi) {
           const float4 q4 = Qs4[qi * d4 + jj];
+          const float2 qa = make_float2(q4.x, q4.y), qb = make_float2(q4.z, q4.w);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            float a = acc[r * B + qi];
-            a = fmaf(x[r][u].x, q4.x, a);
-            a = fmaf(x[r][u].y, q4.y, a);
-            a = fmaf(x[r][u].z, q4.z, a);
-            a = fmaf(x[r][u].w, q4.w, a);
-            acc[r * B + qi] = a;
+            float2 a = acc2[r * B + qi];
+            a = __ffma2_rn(make_float2(x[r][u].x, x[r][u].y), qa, a);
+            a = __ffma2_rn(make_float2(x[r][u].z, x[r][u].w), qb, a);
+            acc2[r * B + qi] = a;
           }
         }
       }
     }
+    float acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = acc2[i].x + acc2[i].y;
 
     // transposing butterfly: NV partial sums x 32 lanes -> one total per lane
     {
@@ -150,19 +153,22 @@ stream_score_kernel(const float* __restrict__ X, int64_t row0, int64_t nrows, in
   }
 }
 
-template <int B, int R>
+static int g_stream_variant = 0;
+void set_stream_variant(int v) { g_stream_variant = v; }
+
+template <int B, int R, int U, int MINB>
 static int launch_one(const float* X, int64_t row0, int64_t nrows, int d, const float* Q, int nq,
                       const SearchWs& ws, int64_t q0, int dense, int64_t dense_row0,
                       cudaStream_t st, int sm_count) {
   const size_t smem = (size_t)B * d * sizeof(float);
-  CMX_CUDA(cudaFuncSetAttribute(stream_score_kernel<B, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CMX_CUDA(cudaFuncSetAttribute(stream_score_kernel<B, R, U, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t groups = (nrows + R - 1) / R;
   const int warps_per_block = kStreamThreads / 32;
   int64_t blocks = (groups + warps_per_block - 1) / warps_per_block;
-  const int64_t max_blocks = (int64_t)sm_count * 3;
+  const int64_t max_blocks = (int64_t)sm_count * MINB;
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
-  stream_score_kernel<B, R><<<(unsigned)blocks, kStreamThreads, smem, st>>>(
+  stream_score_kernel<B, R, U, MINB><<<(unsigned)blocks, kStreamThreads, smem, st>>>(
       X, row0, nrows, d, Q, nq, ws.tau + q0, ws.cnt + q0, ws.cand + q0 * (int64_t)ws.cap, ws.cap,
       dense, dense_row0);
   CMX_LAUNCHED();
@@ -183,10 +189,13 @@ int launch_stream_score(const float* X, int64_t row0, int64_t nrows, int d, cons
     const int b = (nq - g0 < bmax) ? (nq - g0) : bmax;
     const float* Qg = Q + (int64_t)g0 * d;
     const int64_t qq = q0 + g0;
-    if (b > 4) CMX_TRY((launch_one<8, 2>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
-    else if (b > 2) CMX_TRY((launch_one<4, 4>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
-    else if (b > 1) CMX_TRY((launch_one<2, 4>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
-    else CMX_TRY((launch_one<1, 4>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
+    if (b > 4) {
+      if (g_stream_variant == 1) CMX_TRY((launch_one<8, 2, 2, 3>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
+      else if (g_stream_variant == 2) CMX_TRY((launch_one<8, 2, 4, 2>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
+      else CMX_TRY((launch_one<8, 2, 4, 3>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
+    } else if (b > 2) CMX_TRY((launch_one<4, 2, 4, 3>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
+    else if (b > 1) CMX_TRY((launch_one<2, 4, 4, 3>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
+    else CMX_TRY((launch_one<1, 4, 4, 3>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
   }
   return CMX_OK;
 }
