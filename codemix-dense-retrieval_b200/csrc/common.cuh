@@ -107,6 +107,7 @@ int launch_stream_score(const float* X, int64_t row0, int64_t nrows, int d, cons
 void set_stream_variant(int v);  // tuning experiments
 int tensor_path_available();
 void set_tensor_tile(int bn);  // 256 (default) or 128 corpus rows per tile
+void set_tensor_flags(int f);  // tuning experiments (cache hints)
 int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
                         int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,
                         int64_t nq, int64_t nq_pad, const float* q_inv_scale_dev, float b_inv_scale,

@@ -68,6 +68,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 cache-policy descriptors (the fixed encodings CUTLASS's TMA::CacheHintSm90 uses)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                                 int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void st_stream_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -127,6 +142,7 @@ struct TcParams {
   int cap;
   int dense;
   int64_t dense_row0;
+  int flags;  // bit0: Q tiles evict_last, bit1: corpus tiles evict_first, bit2: streaming (.cs) appends
 };
 
 template <int BN, int STAGES>
@@ -176,6 +192,8 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol_q = (p.flags & 1) ? kL2EvictLast : kL2EvictNormal;
+      const uint64_t pol_b = (p.flags & 2) ? kL2EvictFirst : kL2EvictNormal;
       for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
         const int m = (int)(t % mtiles);
         const int64_t n = t / mtiles;
@@ -185,10 +203,10 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_2d(sbase, &tmQhi, full_bar(stage), kb * TC_BK, qrow);
-          tma_load_2d(sbase + TC_A_BYTES, &tmQlo, full_bar(stage), kb * TC_BK, qrow);
-          tma_load_2d(sbase + 2 * TC_A_BYTES, &tmBhi, full_bar(stage), kb * TC_BK, brow);
-          tma_load_2d(sbase + 2 * TC_A_BYTES + B_BYTES, &tmBlo, full_bar(stage), kb * TC_BK, brow);
+          tma_load_2d_hint(sbase, &tmQhi, full_bar(stage), kb * TC_BK, qrow, pol_q);
+          tma_load_2d_hint(sbase + TC_A_BYTES, &tmQlo, full_bar(stage), kb * TC_BK, qrow, pol_q);
+          tma_load_2d_hint(sbase + 2 * TC_A_BYTES, &tmBhi, full_bar(stage), kb * TC_BK, brow, pol_b);
+          tma_load_2d_hint(sbase + 2 * TC_A_BYTES + B_BYTES, &tmBlo, full_bar(stage), kb * TC_BK, brow, pol_b);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -275,8 +293,11 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
               const float raw = __uint_as_float(v[j]);
               if (j < jmax && raw > tau_raw) {
                 const uint32_t pos = atomicAdd(&p.cnt[q], 1u);
-                if (pos < (uint32_t)p.cap)
-                  qcand[pos] = make_key(raw * inv, (uint32_t)(tile_row0 + c * 32 + j));
+                if (pos < (uint32_t)p.cap) {
+                  const uint64_t key = make_key(raw * inv, (uint32_t)(tile_row0 + c * 32 + j));
+                  if (p.flags & 4) st_stream_u64(qcand + pos, key);
+                  else qcand[pos] = key;
+                }
               }
             }
           }
@@ -332,7 +353,9 @@ static int make_plane_map(CUtensorMap* tm, const __half* base, int64_t rows, int
 int tensor_path_available() { return get_encode() != nullptr; }
 
 static int g_tc_bn = 256;  // tile width in corpus rows: 256 (2 stages) or 128 (3 stages)
+static int g_tc_flags = 0;
 void set_tensor_tile(int bn) { g_tc_bn = (bn == 128) ? 128 : 256; }
+void set_tensor_flags(int f) { g_tc_flags = f; }
 
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const CUtensorMap& tb_hi,
@@ -376,6 +399,7 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   p.cap = ws.cap;
   p.dense = dense;
   p.dense_row0 = dense_row0;
+  p.flags = g_tc_flags;
   if (bn == 256) return launch_tc<256, 2>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
   return launch_tc<128, 3>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
 }

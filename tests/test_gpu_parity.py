@@ -337,6 +337,24 @@ def test_merge_and_sharded_equal_single():
     assert np.array_equal(Is, I1) and np.array_equal(Ds, D1)
 
 
+def test_two_gpu_shards_if_available():
+    """Real multi-GPU (single process): shards on GPU 0 and 1, merged on GPU 0."""
+    import torch
+    import cmx.faiss as faiss
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(26)
+    X, Q = _unit(rng, 30000, 128), _unit(rng, 200, 128)
+    cpu = faiss.IndexFlatIP(128)
+    cpu.add(X)
+    D1, I1 = faiss.index_cpu_to_gpu(faiss.StandardGpuResources(), 0, cpu).search(Q, 100)
+    sharded = faiss.index_cpu_to_all_gpus(cpu, ngpu=2)
+    Ds, Is = sharded.search(Q, 100)
+    assert np.array_equal(Is, I1) and np.array_equal(Ds, D1)
+    _check(Ds, Is, X, Q, 100)
+
+
 def test_faiss_shim_dropin_flow(tmp_path):
     """The call sequence of onepass_dense_mix_run_custom_lang.py on a synthetic cached index."""
     import cmx.faiss as faiss
