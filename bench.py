@@ -178,6 +178,12 @@ def run_reference(a) -> None:
     import numpy as np
     import torch
 
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm must use every host core it may
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except Exception:
+        ncores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncores))
     d, k = a.dim, a.k
     sample_rows = min(a.rows, 1 << 19)
     nq_s = min(a.nq, a.cpu_sample_queries)
@@ -249,15 +255,21 @@ def run_cmx(a) -> None:
     def step_device():
         return index.search_mixed(P, S, [ALPHA], k)
 
+    D_h = torch.empty((1, nq, k), dtype=torch.float32).pin_memory()
+    I_h = torch.empty((1, nq, k), dtype=torch.int64).pin_memory()
+
     def step_e2e():
-        # the user-facing call with HOST buffers: H2D of P,S and D2H of (D,I) inside
-        D, I = index.local.search_mixed(P_h, S_h, [ALPHA], k, id_base=index.row0, path=a.path) if world == 1 else (None, None)
-        if world > 1:
+        # the user-facing call with HOST (pinned) buffers: H2D of P,S and D2H of (D,I) inside
+        if world == 1:
+            index.local.search_mixed(P_h, S_h, [ALPHA], k, id_base=index.row0, path=a.path, out=(D_h, I_h))
+        else:
             Pd = P_h.to(dev, non_blocking=True)
             Sd = S_h.to(dev, non_blocking=True)
             Dd, Id = index.search_mixed(Pd, Sd, [ALPHA], k)
-            D, I = Dd.cpu(), Id.cpu()
-        return D, I
+            D_h.copy_(Dd, non_blocking=True)
+            I_h.copy_(Id, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return D_h, I_h
 
     _lib.set_profiling(True)
     for _ in range(a.warmup):
@@ -346,6 +358,10 @@ def run_cmx(a) -> None:
         rows_s = min(n_local, 1 << 19)
         nq_s = min(nq, a.cpu_sample_queries)
         Xs = index.local.reconstruct_n(0, rows_s)
+        try:
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+        except Exception:
+            pass
         qps, dt, threads = cpu_port_qps(Xs, P_h.numpy(), S_h.numpy(), N, k, nq_s)
         cpu_baseline = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "cpu_count": os.cpu_count(),
                         "sample": f"{nq_s} queries x {rows_s} rows ({dt:.1f} s), extrapolated linearly in rows to {N}"}
