@@ -145,6 +145,90 @@ struct TcParams {
   int flags;  // bit0: Q tiles evict_last, bit1: corpus tiles evict_first, bit2: streaming (.cs) appends
 };
 
+// Dense epilogue (first slab): every column of the calling thread's query row becomes a
+// candidate, written at its own position of the query's buffer.
+template <int BN>
+__device__ __forceinline__ void epilogue_dense_tile(const TcParams& p, uint32_t taddr_row, int64_t q, bool qvalid,
+                                                    float inv, int64_t tile_row0, int64_t cols_valid) {
+  uint64_t* qcand = p.cand + q * (int64_t)p.cap;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld_x32(taddr_row + (uint32_t)(c * 32), v);
+    tmem_ld_wait();
+    const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
+    if (qvalid) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < jmax) {
+          const float s = __uint_as_float(v[j]) * inv;
+          const int64_t grow = tile_row0 + c * 32 + j;
+          qcand[grow - p.dense_row0] = (s > CMX_NEG_PAD) ? make_key(s, (uint32_t)grow) : 0ull;
+        }
+      }
+    }
+  }
+}
+
+// Filter epilogue of one 128 x BN accumulator tile for the calling thread's query row.
+// Pass 1 reads the row from TMEM and records which columns beat the threshold (one bit
+// per column); ONE atomicAdd per thread reserves room for all of them; pass 2 re-reads
+// the chunks that had survivors (warp-uniform decision: tcgen05.ld is .aligned) and
+// stores the keys contiguously.  A warp therefore pays one atomic round trip per tile
+// instead of one per surviving column of any of its lanes.
+template <int BN>
+__device__ __forceinline__ void epilogue_filter_tile(const TcParams& p, uint32_t taddr_row, int64_t q,
+                                                     float tau_raw, float inv, int64_t tile_row0,
+                                                     int64_t cols_valid) {
+  constexpr int NC = BN / 32;
+  uint32_t masks[NC];
+  uint32_t total = 0;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(taddr_row + (uint32_t)(c * 32), v);
+    tmem_ld_wait();
+    const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
+    float mx = __int_as_float(0xff800000);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (j < jmax) ? __uint_as_float(v[j]) : mx);
+    uint32_t m = 0;
+    if (mx > tau_raw) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        m |= (j < jmax && __uint_as_float(v[j]) > tau_raw) ? (1u << j) : 0u;
+    }
+    masks[c] = m;
+    total += __popc(m);
+  }
+  if (!__any_sync(0xffffffffu, total != 0)) return;
+  uint32_t pos = 0;
+  if (total) pos = atomicAdd(&p.cnt[q], total);
+  uint64_t* qcand = p.cand + q * (int64_t)p.cap;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (__any_sync(0xffffffffu, masks[c] != 0)) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld_x32(taddr_row + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+      const uint32_t m = masks[c];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if ((m >> j) & 1u) {
+          if (pos < (uint32_t)p.cap) {
+            const uint64_t key = make_key(__uint_as_float(v[j]) * inv, (uint32_t)(tile_row0 + c * 32 + j));
+            if (p.flags & 4) st_stream_u64(qcand + pos, key);
+            else qcand[pos] = key;
+          }
+          ++pos;
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant__ CUtensorMap tmQlo,
@@ -261,48 +345,11 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       const bool qvalid = q < p.nq;
       // compare raw accumulators against tau expressed in accumulator units
       const float tau_raw = qvalid ? p.tau[q] * fwd : __int_as_float(0x7f800000);
-      uint64_t* qcand = p.cand + q * (int64_t)p.cap;
-
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN + c * 32);
-        tmem_ld_x32(taddr, v);
-        tmem_ld_wait();
-        const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
-        if (p.dense) {
-          if (qvalid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < jmax) {
-                const float s = __uint_as_float(v[j]) * inv;
-                const int64_t grow = tile_row0 + c * 32 + j;
-                qcand[grow - p.dense_row0] = (s > CMX_NEG_PAD) ? make_key(s, (uint32_t)grow) : 0ull;
-              }
-            }
-          }
-        } else {
-          float mx = __int_as_float(0xff800000);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (j < jmax) ? __uint_as_float(v[j]) : mx);
-          if (mx > tau_raw) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float raw = __uint_as_float(v[j]);
-              if (j < jmax && raw > tau_raw) {
-                const uint32_t pos = atomicAdd(&p.cnt[q], 1u);
-                if (pos < (uint32_t)p.cap) {
-                  const uint64_t key = make_key(raw * inv, (uint32_t)(tile_row0 + c * 32 + j));
-                  if (p.flags & 4) st_stream_u64(qcand + pos, key);
-                  else qcand[pos] = key;
-                }
-              }
-            }
-          }
-        }
-      }
+      const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
+      if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid);
+      else epilogue_filter_tile<BN>(p, taddr_row, q, tau_raw, inv, tile_row0, cols_valid);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -315,6 +362,199 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+
+// ---- CTA-pair variant (cta_group::2) ------------------------------------------------
+// Two CTAs of a cluster (an SM pair) cooperate on a 256-query x 256-row tile: each CTA
+// stages its own 128 query rows (hi+lo) and HALF of the corpus tile (128 rows, hi+lo),
+// the leader CTA issues tcgen05.mma.cta_group::2 (M=256) which reads A and B halves
+// from both CTAs' shared memory, and each CTA ends up with its 128 x 256 accumulator in
+// its own TMEM.  Per CTA this halves the corpus-tile bytes moved L2->smem and read by
+// the tensor core (64 KB instead of 96 KB per k-block), which leaves room for a third
+// pipeline stage.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cta(uint32_t saddr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                                 int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant__ CUtensorMap tmQlo,
+                     const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                     const TcParams p) {
+  constexpr int BN = 256;                        // corpus rows per pair tile (TMEM columns)
+  constexpr int HALF_BYTES = 128 * TC_BK * 2;    // 16 KB: 128 rows x 64 fp16
+  constexpr int STAGE_BYTES = 4 * HALF_BYTES;    // Qhi, Qlo, Bhi-half, Blo-half
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // used in the leader
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };           // one per CTA
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };       // one per CTA
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };  // used in the leader
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmQhi); tma_prefetch_desc(&tmQlo);
+    tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers initialised and TMEM allocated before any cross-CTA signal
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int mtiles = p.mtiles;  // pair tiles of 256 queries
+  const int64_t cid = blockIdx.x >> 1;
+  const int64_t ncl = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint64_t pol_q = (p.flags & 1) ? kL2EvictLast : kL2EvictNormal;
+      const uint64_t pol_b = (p.flags & 2) ? kL2EvictFirst : kL2EvictNormal;
+      for (int64_t t = cid; t < p.ntiles; t += ncl) {
+        const int m = (int)(t % mtiles);
+        const int64_t n = t / mtiles;
+        const int32_t qrow = m * 256 + (int32_t)rank * 128;
+        const int32_t brow = (int32_t)(p.row0 + n * BN) + (int32_t)rank * 128;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+          // the leader's barrier collects the bytes of both CTAs
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+          tma_load_2d_pair(sbase, &tmQhi, full_bar(stage), kb * TC_BK, qrow, pol_q);
+          tma_load_2d_pair(sbase + HALF_BYTES, &tmQlo, full_bar(stage), kb * TC_BK, qrow, pol_q);
+          tma_load_2d_pair(sbase + 2 * HALF_BYTES, &tmBhi, full_bar(stage), kb * TC_BK, brow, pol_b);
+          tma_load_2d_pair(sbase + 3 * HALF_BYTES, &tmBlo, full_bar(stage), kb * TC_BK, brow, pol_b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = cid; t < p.ntiles; t += ncl) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+          const uint64_t qhi = make_smem_desc(sbase);
+          const uint64_t qlo = make_smem_desc(sbase + HALF_BYTES);
+          const uint64_t bhi = make_smem_desc(sbase + 2 * HALF_BYTES);
+          const uint64_t blo = make_smem_desc(sbase + 3 * HALF_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 32) >> 4);
+            tc_mma_f16_pair(d_tmem, qlo + koff, bhi + koff, IDESC, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_f16_pair(d_tmem, qhi + koff, blo + koff, IDESC, 1u);
+            tc_mma_f16_pair(d_tmem, qhi + koff, bhi + koff, IDESC, 1u);
+          }
+          tc_commit_pair(empty_bar(stage));  // frees this stage in BOTH CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_pair(tfull_bar(acc));  // accumulators complete in BOTH CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own TMEM) =====================
+    const int lane_base = (warp & 3) * 32;
+    const float inv = p.q_inv_scale[0] * p.b_inv_scale;
+    const float fwd = 1.0f / inv;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = cid; t < p.ntiles; t += ncl) {
+      const int m = (int)(t % mtiles);
+      const int64_t n = t / mtiles;
+      const int64_t q = (int64_t)m * 256 + (int64_t)rank * 128 + lane_base + lane;
+      const int64_t tile_row0 = p.row0 + n * BN;
+      int64_t cols_valid = p.row0 + p.nrows - tile_row0;
+      if (cols_valid > BN) cols_valid = BN;
+      const bool qvalid = q < p.nq;
+      const float tau_raw = qvalid ? p.tau[q] * fwd : __int_as_float(0x7f800000);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
+      if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid);
+      else epilogue_filter_tile<BN>(p, taddr_row, q, tau_raw, inv, tile_row0, cols_valid);
+      tc_fence_before();
+      __syncwarp();
+      // the leader's MMA thread waits for the epilogues of both CTAs (8 warps)
+      if (lane == 0) mbar_arrive_cluster(mapa_cta(tempty_bar(acc), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA frees TMEM / exits while its peer may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -354,6 +594,9 @@ int tensor_path_available() { return get_encode() != nullptr; }
 
 static int g_tc_bn = 256;  // tile width in corpus rows: 256 (2 stages) or 128 (3 stages)
 static int g_tc_flags = 0;
+constexpr int kTcPairDefault = 0;
+static int g_tc_pair = kTcPairDefault;  // 1: CTA-pair kernel (cta_group::2) for nq > 128
+void set_tensor_pair(int on) { g_tc_pair = (on < 0) ? kTcPairDefault : (on ? 1 : 0); }
 void set_tensor_tile(int bn) { g_tc_bn = (bn == 128) ? 128 : 256; }
 void set_tensor_flags(int f) { g_tc_flags = f; }
 
@@ -370,6 +613,19 @@ static int launch_tc(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const C
   return CMX_OK;
 }
 
+static int launch_tc_pair(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const CUtensorMap& tb_hi,
+                          const CUtensorMap& tb_lo, const TcParams& p, cudaStream_t st, int sm_count) {
+  constexpr int STAGES = 3;
+  const size_t smem = (size_t)STAGES * 4 * (128 * TC_BK * 2) + 1024 + 256;
+  CMX_CUDA(cudaFuncSetAttribute(tc_score_pair_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t clusters = sm_count / 2;
+  if (p.ntiles < clusters) clusters = p.ntiles;
+  if (clusters < 1) return CMX_OK;
+  tc_score_pair_kernel<STAGES><<<(unsigned)(2 * clusters), TC_THREADS, smem, st>>>(tq_hi, tq_lo, tb_hi, tb_lo, p);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
 int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
                         int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,
                         int64_t nq, int64_t nq_pad, const float* q_inv_scale_dev, float b_inv_scale,
@@ -378,7 +634,8 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   if (nrows <= 0 || nq <= 0) return CMX_OK;
   CMX_CHECK(d_pad % TC_BK == 0, "tensor path: padded dim must be a multiple of %d", TC_BK);
   CMX_CHECK(plane_rows < (int64_t)0x7fffffff, "tensor path: more than 2^31 rows per shard");
-  const int bn = g_tc_bn;
+  const bool pair = g_tc_pair && nq > 128;
+  const int bn = pair ? 128 : g_tc_bn;  // pair: each CTA loads a 128-row half of the 256-row tile
   CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;
   CMX_TRY(make_plane_map(&tq_hi, Qhi, nq_pad, d_pad, TC_BM));
   CMX_TRY(make_plane_map(&tq_lo, Qlo, nq_pad, d_pad, TC_BM));
@@ -388,8 +645,8 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   p.row0 = row0;
   p.nrows = nrows;
   p.kblocks = d_pad / TC_BK;
-  p.mtiles = (int)((nq + TC_BM - 1) / TC_BM);
-  p.ntiles = (int64_t)p.mtiles * ((nrows + bn - 1) / bn);
+  p.mtiles = pair ? (int)((nq + 255) / 256) : (int)((nq + TC_BM - 1) / TC_BM);
+  p.ntiles = pair ? (int64_t)p.mtiles * ((nrows + 255) / 256) : (int64_t)p.mtiles * ((nrows + bn - 1) / bn);
   p.nq = nq;
   p.q_inv_scale = q_inv_scale_dev;
   p.b_inv_scale = b_inv_scale;
@@ -400,6 +657,7 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   p.dense = dense;
   p.dense_row0 = dense_row0;
   p.flags = g_tc_flags;
+  if (pair) return launch_tc_pair(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
   if (bn == 256) return launch_tc<256, 2>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
   return launch_tc<128, 3>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
 }

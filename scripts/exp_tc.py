@@ -17,9 +17,10 @@ for N in sizes:
     while c * bench.CHUNK < N:
         x = bench.corpus_chunk(c, d, dev)
         sh.add(x[: min(bench.CHUNK, N - c * bench.CHUNK)]); del x; c += 1
-    for bn in (256, 128):
-        _lib.check(_lib.lib().cmx_debug_set_tensor_tile(bn))
-        for flags in ((0, 1, 2, 3, 4, 5, 7) if bn == 256 else (0, 5)):
+    for pair in (0, 1):
+        bn = 256
+        _lib.check(_lib.lib().cmx_debug_set_tensor_pair(pair))
+        for flags in (0, 1):
             _lib.check(_lib.lib().cmx_debug_set_tensor_flags(flags))
             for _ in range(2):
                 sh.search_mixed(P, S, [0.5], 1000, path="tensor")
@@ -29,7 +30,7 @@ for N in sizes:
                 sh.search_mixed(P, S, [0.5], 1000, path="tensor"); st = sh.last_stats()
                 sc += st["score_ms"]; se += st["select_ms"]; tot += st["total_ms"]
             tf = 3 * 2.0 * 6980 * N * d / (sc / reps / 1e3) / 1e12
-            print(json.dumps({"N": N, "bn": bn, "flags": flags, "score_ms": round(sc / reps, 2), "select_ms": round(se / reps, 2),
+            print(json.dumps({"N": N, "pair": pair, "flags": flags, "score_ms": round(sc / reps, 2), "select_ms": round(se / reps, 2),
                               "total_ms": round(tot / reps, 2), "exec_TFLOPs": round(tf, 1)}), flush=True)
     del sh
     torch.cuda.empty_cache()

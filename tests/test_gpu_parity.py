@@ -155,6 +155,24 @@ def test_tensor_tile_variants(bn):
         _lib.check(_lib.lib().cmx_debug_set_tensor_tile(256))
 
 
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("shape", [(30077, 301, 256, 100), (9000, 130, 192, 50), (70001, 700, 1024, 1000), (5003, 257, 96, 20)])
+def test_tensor_single_and_pair_kernels(pair, shape):
+    """Both tensor-core kernels (one CTA per tile / CTA pair with cta_group::2) against the oracle."""
+    from cmx import _lib
+
+    N, nq, d, k = shape
+    rng = np.random.default_rng(300 + N)
+    X, Q = _unit(rng, N, d), _unit(rng, nq, d)
+    _lib.check(_lib.lib().cmx_debug_set_tensor_pair(pair))
+    try:
+        sh = _shard(X)
+        D, I = sh.search(Q, k, path="tensor")
+        _check(D, I, X, Q, k)
+    finally:
+        _lib.check(_lib.lib().cmx_debug_set_tensor_pair(-1))
+
+
 @pytest.mark.parametrize("d", [96, 100, 768])
 def test_tensor_ragged_dims(d):
     """d not a multiple of 64 -> zero-padded operand planes; N, nq not tile multiples."""
