@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--nq", type=int, default=NQ_FULL)
     ap.add_argument("--k", type=int, default=K_FULL)
     ap.add_argument("--path", default="auto", choices=["auto", "stream", "tensor"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "allgather"],
+                    help="multi-GPU merge: fused peer-memory kernel (p2p) or NCCL all_gather + merge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-queries", type=int, default=512)
     return ap.parse_args()
@@ -238,7 +240,7 @@ def run_cmx(a) -> None:
     assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
 
     d, k, nq, N = a.dim, a.k, a.nq, a.rows
-    index = ShardedIndex(d, N, device=local_rank)
+    index = ShardedIndex(d, N, device=local_rank, exchange=a.exchange)
     index.path = a.path
     fill_shard(index, index.row0, index.row1, d, dev)
     assert index.local_complete()
@@ -372,7 +374,7 @@ def run_cmx(a) -> None:
         "dtype": "f16x3-split+f32acc" if used_tensor else "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(a), "rows": N, "dim": d, "queries": nq, "k": k, "alpha": ALPHA,
-                   "parallelism": f"corpus row shards x{world}" if world > 1 else "single GPU",
+                   "parallelism": f"corpus row shards x{world}, exchange={index.exchange_used}" if world > 1 else "single GPU",
                    "cache": "inputs_larger_than_L2 (corpus %.1f GB per GPU)" % (n_local * d * 4 / 1e9),
                    "path": "tensor" if used_tensor else "stream", "slabs": stats["slabs"], "reruns": stats["reruns"]},
         "clocks": clocks,

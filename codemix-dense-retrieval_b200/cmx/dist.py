@@ -11,6 +11,12 @@ Rank r owns the contiguous rows [bounds[r], bounds[r+1]) of the global corpus
   2. ONE exchange: all_gather of the per-shard (D, I) lists (nq*k*12 B per rank),
   3. the k-way merge kernel on every rank (score desc, shard, position) -- so the
      G-way result equals the 1-GPU result exactly, ties included.
+Steps 2+3 are fused when the ranks can map each other's memory (NVLink / NVSwitch,
+torch symmetric memory): every rank writes its lists into a symmetric buffer, and ONE
+kernel per rank (`cmx_merge_topk_peers`) reads all peers' lists in place through peer
+pointers for ITS slice of the queries, merges them and stores the merged rows into
+every rank's output buffer -- no all_gather, no staging copy, and the merge work is
+split G ways.  `exchange="allgather"` keeps the NCCL version (the baseline).
 The local engine and the merge function are injectable so that the host-side
 logic (partition, id bases, exchange layout) is testable on CPU ranks with gloo;
 the defaults are the CUDA engine and the CUDA merge kernel -- there is no CPU
@@ -39,7 +45,8 @@ class ShardedIndex:
     """A flat IP index whose rows are sharded over the ranks of a process group."""
 
     def __init__(self, d: int, ntotal_global: int, device: Optional[int] = None, group=None,
-                 engine_factory: Optional[Callable] = None, merge_fn: Optional[Callable] = None):
+                 engine_factory: Optional[Callable] = None, merge_fn: Optional[Callable] = None,
+                 exchange: str = "auto"):
         self.d = int(d)
         self.group = group
         self.world = dist.get_world_size(group) if dist is not None and dist.is_initialized() else 1
@@ -58,6 +65,12 @@ class ShardedIndex:
         self.local = engine_factory(self.d)
         self._merge = merge_fn
         self.path = "auto"
+        # "p2p": fused peer-memory merge, "allgather": NCCL all_gather + merge, "auto": p2p when possible
+        self.exchange = exchange
+        self.exchange_used = "none" if self.world == 1 else "allgather"
+        self._peer = {}
+        self._device = device
+        self._custom_engine = engine_factory is not None and not hasattr(self.local, "_h")
 
     # ---- storage: each rank adds ITS rows, in global row order ----------------
     def reserve_local(self) -> None:
@@ -87,10 +100,73 @@ class ShardedIndex:
         Dm, Im = self._merge(Dp.view(self.world, nq, k), Ip.view(self.world, nq, k))
         return Dm.reshape(*lead, k), Im.reshape(*lead, k)
 
+    # ---- fused exchange + merge over peer memory -------------------------------------
+    def _peer_buffers(self, nq: int, k: int):
+        """Symmetric (peer-mappable) buffers for the per-shard lists and the merged result."""
+        key = (nq, k)
+        if key in self._peer:
+            return self._peer[key]
+        import torch.distributed._symmetric_memory as symm_mem
+
+        dev = torch.device("cuda", torch.cuda.current_device() if self._device is None else self._device)
+        grp = self.group if self.group is not None else dist.group.WORLD
+        bufs = {}
+        for name, dt in (("D_loc", torch.float32), ("I_loc", torch.int64), ("D_out", torch.float32), ("I_out", torch.int64)):
+            t = symm_mem.empty((nq * k,), dtype=dt, device=dev)
+            hdl = symm_mem.rendezvous(t, grp)
+            bufs[name] = (t, hdl, [int(p) for p in hdl.buffer_ptrs])
+        self._peer = {key: bufs}  # keep one shape alive
+        return bufs
+
+    def _p2p_ok(self, like) -> bool:
+        if self.world == 1 or self.exchange == "allgather" or self._custom_engine:
+            return False
+        if not (torch is not None and isinstance(like, torch.Tensor) and like.is_cuda):
+            return False
+        return True
+
+    def _search_p2p(self, lead_shape, k: int, run_local):
+        import ctypes as C
+
+        from . import _lib
+
+        nq = int(np.prod(lead_shape))
+        bufs = self._peer_buffers(nq, k)
+        D_loc, hdl, D_ptrs = bufs["D_loc"]
+        I_loc, _, I_ptrs = bufs["I_loc"]
+        D_out, _, Do_ptrs = bufs["D_out"]
+        I_out, _, Io_ptrs = bufs["I_out"]
+        run_local((D_loc.view(*lead_shape, k), I_loc.view(*lead_shape, k)))
+        hdl.barrier(channel=0)  # every rank's lists are complete and visible
+        G = self.world
+        q0, q1 = (nq * self.rank) // G, (nq * (self.rank + 1)) // G
+        arr = lambda ptrs: (C.c_void_p * G)(*ptrs)  # noqa: E731
+        stream = int(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().cmx_merge_topk_peers(arr(D_ptrs), arr(I_ptrs), G, nq, k, q0, q1, arr(Do_ptrs), arr(Io_ptrs), G,
+                                                   D_out.device.index, stream))
+        hdl.barrier(channel=1)  # every rank's slice has landed in every output buffer
+        self.exchange_used = "p2p"
+        return D_out.view(*lead_shape, k), I_out.view(*lead_shape, k)
+
+    def _run(self, like, lead_shape, k: int, run_local):
+        if self._p2p_ok(like):
+            try:
+                return self._search_p2p(lead_shape, k, run_local)
+            except Exception as exc:  # symmetric memory unavailable: keep the NCCL exchange
+                if self.exchange == "p2p":
+                    raise
+                self.exchange = "allgather"
+                self.exchange_error = repr(exc)
+        D, I = run_local(None)
+        return self._exchange_and_merge(D, I, k)
+
     def search(self, x, k: int):
-        D, I = self.local.search(x, k, id_base=self.row0, path=self.path)
-        return self._exchange_and_merge(D, I, int(k))
+        k = int(k)
+        nq = int(x.shape[0]) if hasattr(x, "shape") and len(x.shape) == 2 else 1
+        return self._run(x, (nq,), k, lambda out: self.local.search(x, k, id_base=self.row0, path=self.path, **({"out": out} if out else {})))
 
     def search_mixed(self, P, S, alphas: Sequence[float], k: int):
-        D, I = self.local.search_mixed(P, S, alphas, k, id_base=self.row0, path=self.path)
-        return self._exchange_and_merge(D, I, int(k))
+        k = int(k)
+        lead = (len(alphas), int(P.shape[0]))
+        return self._run(P, lead, k, lambda out: self.local.search_mixed(P, S, alphas, k, id_base=self.row0, path=self.path,
+                                                                         **({"out": out} if out else {})))

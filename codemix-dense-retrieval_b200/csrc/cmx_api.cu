@@ -674,6 +674,19 @@ int cmx_merge_topk(const float* D_parts, const int64_t* I_parts, int nparts, int
   return rc;
 }
 
+int cmx_merge_topk_peers(const float* const* D_parts, const int64_t* const* I_parts, int nparts, int64_t nq, int k,
+                         int64_t q0, int64_t q1, float* const* D_outs, int64_t* const* I_outs, int nouts, int device,
+                         void* stream) {
+  CMX_CHECK(D_parts && I_parts && D_outs && I_outs, "null pointer table");
+  CMX_CHECK(k >= 1 && k <= CMX_MAX_K, "k=%d out of range [1, %d]", k, CMX_MAX_K);
+  CMX_CHECK(q0 >= 0 && q0 <= q1 && q1 <= nq, "bad query slice [%lld, %lld) of %lld", (long long)q0, (long long)q1, (long long)nq);
+  int ndev = 0;
+  CMX_TRY(cmx_device_count(&ndev));
+  CMX_CHECK(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+  DevGuard g(device);
+  return launch_merge_peers(D_parts, I_parts, nparts, k, q0, q1, D_outs, I_outs, nouts, (cudaStream_t)stream);
+}
+
 /* test hook (not in cmx.h): tensor tile width 256 / 128 */
 CMX_API int cmx_debug_set_tensor_tile(int bn) { set_tensor_tile(bn); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_pair(int on) { set_tensor_pair(on); return CMX_OK; }

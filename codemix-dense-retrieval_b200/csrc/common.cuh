@@ -75,6 +75,7 @@ __host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row)
 __host__ __device__ __forceinline__ float key_score(uint64_t k) { return ordered_to_f32((uint32_t)(k >> 32)); }
 __host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return 0xffffffffu - (uint32_t)(k & 0xffffffffu); }
 
+#define CMX_MAX_PEERS 16
 #define CMX_NEG_PAD (-3.402823466e+38f) /* FAISS pads IP results with lowest float */
 
 // ---- search workspace (device) ----------------------------------------------
@@ -122,5 +123,9 @@ int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float*
                    int64_t id_base, cudaStream_t st);
 int launch_merge(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,
                  float* D, int64_t* I, cudaStream_t st);
+
+int launch_merge_peers(const float* const* D_parts, const int64_t* const* I_parts, int nparts, int k,
+                       int64_t q0, int64_t q1, float* const* D_outs, int64_t* const* I_outs, int nouts,
+                       cudaStream_t st);
 
 }  // namespace cmx

@@ -301,6 +301,96 @@ merge_kernel(const float* __restrict__ Dp, const int64_t* __restrict__ Ip, int n
   }
 }
 
+// Fused exchange + merge over peer memory: part g's list lives in GPU g's memory and is read
+// here directly through NVLink peer pointers (no all_gather, no staging copy); the merged
+// rows of queries [q0, q1) are stored into every rank's output buffer (peer stores), so
+// after one cross-rank barrier each rank holds the full result.
+struct MergePeerArgs {
+  const float* D[CMX_MAX_PEERS];
+  const int64_t* I[CMX_MAX_PEERS];
+  float* Do[CMX_MAX_PEERS];
+  int64_t* Io[CMX_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(kSelThreads)
+merge_peers_kernel(const MergePeerArgs a, int nparts, int nouts, int64_t q0, int k) {
+  extern __shared__ __align__(16) uint64_t keys[];
+  __shared__ SelectShared sh;
+  __shared__ uint32_t s_valid;
+  const int64_t q = q0 + blockIdx.x;
+  const int n_all = nparts * k;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  {
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < n_all; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      bool valid = false;
+      uint64_t key = 0ull;
+      if (i < n_all) {
+        const int g = i / k, pos = i - g * k;
+        const int64_t src = q * k + pos;
+        valid = a.I[g][src] >= 0;
+        if (valid) key = make_key(a.D[g][src], (uint32_t)i);
+      }
+      const uint32_t ballot = __ballot_sync(0xffffffffu, valid);
+      uint32_t wbase = 0;
+      if (lane == 0 && ballot) wbase = atomicAdd(&s_valid, (uint32_t)__popc(ballot));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (valid) keys[wbase + __popc(ballot & ((1u << lane) - 1u))] = key;
+    }
+  }
+  __syncthreads();
+  const int n = (int)s_valid;
+  uint64_t* top = keys + n_all;
+  int kk = n;
+  if (n > k) {
+    const uint64_t kth = block_kth_largest(keys, n, k, sh);
+    kk = block_partition(keys, n, kth, top, sh);
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) top[i] = keys[i];
+    __syncthreads();
+  }
+  const int P = next_pow2(max(kk, 2));
+  for (int i = kk + threadIdx.x; i < P; i += blockDim.x) top[i] = 0ull;
+  __syncthreads();
+  bitonic_sort_desc(top, P);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    float s = CMX_NEG_PAD;
+    int64_t id = -1;
+    if (i < kk) {
+      const uint32_t src_i = key_row(top[i]);
+      const int g = src_i / k, pos = src_i - g * k;
+      s = a.D[g][q * k + pos];
+      id = a.I[g][q * k + pos];
+    }
+    for (int o = 0; o < nouts; ++o) {
+      a.Do[o][q * k + i] = s;
+      a.Io[o][q * k + i] = id;
+    }
+  }
+}
+
+int launch_merge_peers(const float* const* D_parts, const int64_t* const* I_parts, int nparts, int k,
+                       int64_t q0, int64_t q1, float* const* D_outs, int64_t* const* I_outs, int nouts,
+                       cudaStream_t st) {
+  if (q1 <= q0) return CMX_OK;
+  CMX_CHECK(nparts >= 1 && nparts <= CMX_MAX_PEERS && nouts >= 1 && nouts <= CMX_MAX_PEERS,
+            "merge_peers: at most %d parts / outputs", CMX_MAX_PEERS);
+  const size_t smem = ((size_t)nparts * k + pow2_at_least(k)) * sizeof(uint64_t);
+  if (smem > 200 * 1024) {
+    set_error("merge: nparts*k = %d too large for one shared-memory selection", nparts * k);
+    return CMX_ERR_INVALID;
+  }
+  MergePeerArgs a;
+  for (int g = 0; g < nparts; ++g) { a.D[g] = D_parts[g]; a.I[g] = I_parts[g]; }
+  for (int o = 0; o < nouts; ++o) { a.Do[o] = D_outs[o]; a.Io[o] = I_outs[o]; }
+  CMX_CUDA(cudaFuncSetAttribute(merge_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_peers_kernel<<<(unsigned)(q1 - q0), kSelThreads, smem, st>>>(a, nparts, nouts, q0, k);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
 int launch_merge(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,
                  float* D, int64_t* I, cudaStream_t st) {
   if (nq == 0) return CMX_OK;

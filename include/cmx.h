@@ -125,6 +125,17 @@ CMX_API int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int6
 CMX_API int cmx_merge_topk(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,
                    float* D, int64_t* I, int io_on_device, int device, void* stream);
 
+/* fused exchange + merge over peer memory (NVLink P2P / symmetric memory): D_parts[g] /
+ * I_parts[g] are DEVICE pointers to part g's [nq,k] lists, each possibly resident on another
+ * GPU and mapped into this process; the kernel reads them in place, merges queries
+ * [q0, q1) and stores the merged rows into each of the nouts output buffers D_outs[o] /
+ * I_outs[o] ([nq,k], local or peer).  The caller provides the cross-rank barriers before
+ * (parts complete) and after (outputs complete).  Asynchronous on `stream` unlike the
+ * other entry points: it returns once the kernel is enqueued.  nparts, nouts <= 16. */
+CMX_API int cmx_merge_topk_peers(const float* const* D_parts, const int64_t* const* I_parts, int nparts,
+                                 int64_t nq, int k, int64_t q0, int64_t q1, float* const* D_outs,
+                                 int64_t* const* I_outs, int nouts, int device, void* stream);
+
 /* ---- instrumentation --------------------------------------------------------*/
 typedef struct cmx_search_stats {
   int32_t path;            /* CMX_PATH_STREAM / CMX_PATH_TENSOR actually used       */
