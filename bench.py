@@ -268,8 +268,9 @@ def run_cmx(a) -> None:
             Pd = P_h.to(dev, non_blocking=True)
             Sd = S_h.to(dev, non_blocking=True)
             Dd, Id = index.search_mixed(Pd, Sd, [ALPHA], k)
-            D_h.copy_(Dd, non_blocking=True)
-            I_h.copy_(Id, non_blocking=True)
+            if rank == 0:  # the merged result is delivered to the host once (rank 0 writes the run file)
+                D_h.copy_(Dd, non_blocking=True)
+                I_h.copy_(Id, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return D_h, I_h
 

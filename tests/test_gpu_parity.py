@@ -477,3 +477,56 @@ def test_large_properties_tensor_vs_stream_and_recompute():
     rep = oracle.compare_topk(Ds.cpu().numpy(), Is.cpu().numpy(), D[:8].cpu().numpy(), I[:8].cpu().numpy(),
                               rtol=RTOL, atol=ATOL)
     assert rep["ok"], rep
+
+
+# ---------------------------------------------------------------- limits and workspace reuse
+def test_k_max_2048_and_over_limit():
+    rng = np.random.default_rng(40)
+    X, Q = _unit(rng, 50000, 64), _unit(rng, 40, 64)
+    sh = _shard(X)
+    D, I = sh.search(Q, 2048, path="tensor")
+    _check(D, I, X, Q, 2048)
+    D, I = sh.search(Q[:2], 2048, path="stream")
+    _check(D, I, X, Q[:2], 2048)
+    with pytest.raises(RuntimeError):
+        sh.search(Q, 2049)
+    with pytest.raises(AssertionError):
+        sh.search(Q, 0)
+
+
+def test_query_chunking_above_8192_queries():
+    """More queries than one corpus pass handles (8192): the passes are stitched correctly."""
+    rng = np.random.default_rng(41)
+    X = _unit(rng, 20000, 64)
+    P, S = _unit(rng, 3100, 64), _unit(rng, 3100, 64)
+    sh = _shard(X)
+    D, I = sh.search_mixed(P, S, [0.0, 0.5, 1.0], 10)  # 9300 queries in one call
+    Qo, _ = oracle.mix_normalize(P, S, [0.0, 0.5, 1.0])
+    for ai in range(3):
+        for rows in (slice(0, 64), slice(2660, 2760), slice(3036, 3100)):  # around the 8192 boundary too
+            Dr, Ir = oracle.flat_ip_search(X, Qo[ai][rows], 10)
+            assert oracle.compare_topk(D[ai][rows], I[ai][rows], Dr, Ir, rtol=RTOL, atol=ATOL)["ok"]
+
+
+def test_workspace_reuse_reset_and_two_indexes():
+    from cmx.engine import Shard
+
+    rng = np.random.default_rng(42)
+    Xa, Xb = _unit(rng, 7000, 64), _unit(rng, 9000, 128)
+    a, b = Shard(64, 0), Shard(128, 0)
+    a.add(Xa)
+    b.add(Xb)
+    for nq, k in ((300, 50), (3, 7), (1000, 300), (17, 1)):  # growing and shrinking workspaces
+        Qa, Qb = _unit(rng, nq, 64), _unit(rng, nq, 128)
+        Da, Ia = a.search(Qa, k)
+        Db, Ib = b.search(Qb, k)
+        _check(Da, Ia, Xa, Qa, k)
+        _check(Db, Ib, Xb, Qb, k)
+    a.reset()
+    assert a.ntotal == 0
+    D, I = a.search(_unit(rng, 2, 64), 3)
+    assert (I == -1).all()
+    a.add(Xa[:100])
+    Q = _unit(rng, 20, 64)
+    D, I = a.search(Q, 5)
+    _check(D, I, Xa[:100], Q, 5)
