@@ -138,6 +138,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel: str, rows: int, d: int):
+    """DRAM bytes per step for the dominant kernel, from the committed ncu --set full capture:
+    measured bytes per corpus row (profiles/ncu_traffic.json, captured at d=1024) x rows."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        j = json.loads(p.read_text())[kernel]
+        return j["dram_bytes_per_corpus_row"] * (d / 1024.0) * rows, j["dram_bytes_per_corpus_row"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -342,8 +353,12 @@ def run_cmx(a) -> None:
         executed = 3.0 * 2.0 * nq * n_local * d_pad  # three fp16 MMA passes (hi*hi, hi*lo, lo*hi)
         achieved = executed / (per_step_score_ms / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        traffic, per_row = ncu_traffic("tc_score_kernel", n_local, d)
         roofline = {"bound": "tensor", "kernel": "tc_score_kernel", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "passes": 3,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_note": f"DRAM bytes of the step's scoring launches = {per_row} B per corpus row (ncu capture, "
+                                    "profiles/ncu_traffic.json) x rows; algorithmic = 4096 B per row (fp16 hi+lo planes read once)",
+                    "passes": 3,
                     "achieved_alg_fp32_equiv": alg_flops / (per_step_score_ms / 1e3) / 1e12,
                     "kernel_ms_per_step": per_step_score_ms, "launches_per_step": score_launches / a.steps,
                     "peak_source": peaks["source"] + ", sustained dense 16-bit (fp16 == bf16 rate)",
@@ -352,8 +367,11 @@ def run_cmx(a) -> None:
         groups = (nq + 7) // 8
         alg_bytes = groups * 4.0 * n_local * d
         achieved = alg_bytes / (per_step_score_ms / 1e3) / 1e9
+        traffic, per_row = ncu_traffic("stream_score_kernel", n_local, d)
         roofline = {"bound": "hbm", "kernel": "stream_score_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                    "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                    "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None if traffic is None else traffic * groups,
+                    "traffic_note": f"{per_row} DRAM B per corpus row per pass (ncu capture, profiles/ncu_traffic.json); the measured "
+                                    "peak is a copy (read+write) figure, a read-only stream can exceed it",
                     "kernel_ms_per_step": per_step_score_ms, "peak_source": peaks["source"]}
 
     cpu_baseline = None

@@ -76,7 +76,8 @@ struct SelectShared {
   uint64_t red_min[32];
   uint64_t red_max[32];
   uint64_t kmin, kmax;
-  uint32_t bin, above, count;
+  uint32_t bin, above, count, bin_count;
+  uint64_t found;
 };
 
 // Exact k-th largest of the n DISTINCT keys in smem (1 <= k < n).  All threads of the
@@ -137,7 +138,7 @@ __device__ uint64_t block_kth_largest(const uint64_t* keys, int n, int k, Select
       uint32_t running = incl - s;  // keys in digits above this lane's range
 #pragma unroll
       for (int j = 7; j >= 0; --j) {
-        if (running < want && want <= running + h[j]) { sh.bin = lane * 8 + j; sh.above = running; }
+        if (running < want && want <= running + h[j]) { sh.bin = lane * 8 + j; sh.above = running; sh.bin_count = h[j]; }
         running += h[j];
       }
     }
@@ -145,7 +146,17 @@ __device__ uint64_t block_kth_largest(const uint64_t* keys, int n, int k, Select
     want -= sh.above;
     prefix |= (uint64_t)sh.bin << shift;
     mask |= 0xffull << shift;
+    const bool unique = sh.bin_count == 1u;
     __syncthreads();
+    if (unique && shift > 0) {
+      // a single key carries this prefix: it is the k-th largest, no need to resolve lower digits
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t v = keys[i];
+        if ((v & mask) == prefix) sh.found = v;
+      }
+      __syncthreads();
+      return sh.found;
+    }
   }
   return prefix;
 }

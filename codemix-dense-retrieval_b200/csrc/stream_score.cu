@@ -190,7 +190,8 @@ int launch_stream_score(const float* X, int64_t row0, int64_t nrows, int d, cons
     const float* Qg = Q + (int64_t)g0 * d;
     const int64_t qq = q0 + g0;
     if (b > 4) {
-      if (g_stream_variant == 1) CMX_TRY((launch_one<8, 2, 2, 3>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
+      if (g_stream_variant == 3) CMX_TRY((launch_one<8, 4, 2, 2>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
+      else if (g_stream_variant == 1) CMX_TRY((launch_one<8, 2, 2, 3>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
       else if (g_stream_variant == 2) CMX_TRY((launch_one<8, 2, 4, 2>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
       else CMX_TRY((launch_one<8, 2, 4, 3>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
     } else if (b > 2) CMX_TRY((launch_one<4, 2, 4, 3>(X, row0, nrows, d, Qg, b, ws, qq, dense, dense_row0, st, sm_count)));
