@@ -689,6 +689,7 @@ int cmx_merge_topk_peers(const float* const* D_parts, const int64_t* const* I_pa
 
 /* test hook (not in cmx.h): tensor tile width 256 / 128 */
 CMX_API int cmx_debug_set_tensor_tile(int bn) { set_tensor_tile(bn); return CMX_OK; }
+CMX_API int cmx_debug_set_tensor_small(int on) { set_tensor_small(on); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_pair(int on) { set_tensor_pair(on); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_flags(int f) { set_tensor_flags(f); return CMX_OK; }
 CMX_API int cmx_debug_set_stream_variant(int v) { set_stream_variant(v); return CMX_OK; }

@@ -562,6 +562,189 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
   }
 }
 
+
+// ---- small-batch variant: corpus rows on the M side, queries on the N side ----------
+// For nq <= 128 the 128 x BN tile above wastes tensor work on padded query rows (three
+// MMA passes over 128 rows for, say, 8 real queries) and under the power cap that waste
+// keeps the pass above the HBM time.  Here the roles are swapped: A = a 128-row corpus
+// tile (M = 128), B = the NQ (16..128) query rows (N = NQ), D = [128 corpus rows x NQ
+// queries] in TMEM.  MMA work scales with the real batch, the stage is almost pure corpus
+// bytes (32 KB + NQ*256 B) so 3-5 stages fit, and the kernel is bound by the HBM stream
+// of the operand planes.  Epilogue: one corpus row per thread; survivors of one query
+// (= one TMEM column) are found with a warp ballot and appended with ONE atomicAdd per
+// warp and column.
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int NQ, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant__ CUtensorMap tmQlo,
+                      const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                      const TcParams p) {
+  constexpr int A_BYTES = 128 * TC_BK * 2;  // corpus tile, one plane
+  constexpr int Q_BYTES = NQ * TC_BK * 2;   // query tile, one plane
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * Q_BYTES;
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t TMEM_COLS = (2 * NQ < 32) ? 32u : (uint32_t)(2 * NQ);
+  constexpr int CW = (NQ < 32) ? NQ : 32;  // columns per TMEM load
+  static_assert(NQ == 16 || NQ == 32 || NQ == 64 || NQ == 128, "NQ must be 16/32/64/128");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  float* tau_s = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 8u * (2 * STAGES + 6));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmQhi); tma_prefetch_desc(&tmQlo);
+    tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    // thresholds in accumulator units, one per query column (padding columns never pass)
+    const float inv0 = p.q_inv_scale[0] * p.b_inv_scale;
+    for (int j = threadIdx.x; j < NQ; j += blockDim.x)
+      tau_s[j] = (j < p.nq) ? p.tau[j] * (1.0f / inv0) : __int_as_float(0x7f800000);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        const int32_t brow = (int32_t)(p.row0 + t * 128);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d_hint(sbase, &tmBhi, full_bar(stage), kb * TC_BK, brow, kL2EvictFirst);
+          tma_load_2d_hint(sbase + A_BYTES, &tmBlo, full_bar(stage), kb * TC_BK, brow, kL2EvictFirst);
+          tma_load_2d_hint(sbase + 2 * A_BYTES, &tmQhi, full_bar(stage), kb * TC_BK, 0, kL2EvictLast);
+          tma_load_2d_hint(sbase + 2 * A_BYTES + Q_BYTES, &tmQlo, full_bar(stage), kb * TC_BK, 0, kL2EvictLast);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NQ);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+          const uint64_t bhi = make_smem_desc(sbase);
+          const uint64_t blo = make_smem_desc(sbase + A_BYTES);
+          const uint64_t qhi = make_smem_desc(sbase + 2 * A_BYTES);
+          const uint64_t qlo = make_smem_desc(sbase + 2 * A_BYTES + Q_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 32) >> 4);
+            tc_mma_f16(d_tmem, bhi + koff, qlo + koff, IDESC, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_f16(d_tmem, blo + koff, qhi + koff, IDESC, 1u);
+            tc_mma_f16(d_tmem, bhi + koff, qhi + koff, IDESC, 1u);
+          }
+          tc_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue: one corpus row per thread =====================
+    const int lane_base = (warp & 3) * 32;
+    const float inv = p.q_inv_scale[0] * p.b_inv_scale;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+      const int64_t grow = p.row0 + t * 128 + lane_base + lane;
+      const bool rvalid = grow < p.row0 + p.nrows;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * NQ);
+#pragma unroll 1
+      for (int c = 0; c < NQ / CW; ++c) {
+        uint32_t v[32];
+        __syncwarp();
+        if (CW == 16) tmem_ld_x16(taddr_row + (uint32_t)(c * CW), v);
+        else tmem_ld_x32(taddr_row + (uint32_t)(c * CW), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          const int qj = c * CW + j;
+          if (qj < p.nq) {  // warp-uniform
+            const float raw = __uint_as_float(v[j]);
+            if (p.dense) {
+              if (rvalid) {
+                const float s = raw * inv;
+                p.cand[(int64_t)qj * p.cap + (grow - p.dense_row0)] = (s > CMX_NEG_PAD) ? make_key(s, (uint32_t)grow) : 0ull;
+              }
+            } else {
+              const bool pass = rvalid && raw > tau_s[qj];
+              const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+              if (ballot) {
+                const int leader = __ffs(ballot) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(&p.cnt[qj], (uint32_t)__popc(ballot));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (pass) {
+                  const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
+                  if (pos < (uint32_t)p.cap) p.cand[(int64_t)qj * p.cap + pos] = make_key(raw * inv, (uint32_t)grow);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---- host side ------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -630,6 +813,29 @@ static int launch_tc_pair(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, co
   return CMX_OK;
 }
 
+template <int NQ, int STAGES>
+static int launch_tc_small(const __half* Bhi, const __half* Blo, int64_t plane_rows, const __half* Qhi, const __half* Qlo,
+                           int64_t nq_pad, int d_pad, TcParams p, cudaStream_t st, int sm_count) {
+  CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;
+  CMX_TRY(make_plane_map(&tq_hi, Qhi, nq_pad, d_pad, NQ));
+  CMX_TRY(make_plane_map(&tq_lo, Qlo, nq_pad, d_pad, NQ));
+  CMX_TRY(make_plane_map(&tb_hi, Bhi, plane_rows, d_pad, 128));
+  CMX_TRY(make_plane_map(&tb_lo, Blo, plane_rows, d_pad, 128));
+  constexpr int STAGE_BYTES = 2 * (128 * TC_BK * 2) + 2 * (NQ * TC_BK * 2);
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + NQ * sizeof(float);
+  CMX_CUDA(cudaFuncSetAttribute(tc_score_small_kernel<NQ, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p.mtiles = 1;
+  p.ntiles = (p.nrows + 127) / 128;
+  int64_t grid = p.ntiles < sm_count ? p.ntiles : sm_count;
+  if (grid < 1) return CMX_OK;
+  tc_score_small_kernel<NQ, STAGES><<<(unsigned)grid, TC_THREADS, smem, st>>>(tq_hi, tq_lo, tb_hi, tb_lo, p);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+static int g_tc_small = 1;  // nq <= 128: corpus-as-M kernel
+void set_tensor_small(int on) { g_tc_small = on ? 1 : 0; }
+
 int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
                         int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,
                         int64_t nq, int64_t nq_pad, const float* q_inv_scale_dev, float b_inv_scale,
@@ -638,6 +844,17 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   if (nrows <= 0 || nq <= 0) return CMX_OK;
   CMX_CHECK(d_pad % TC_BK == 0, "tensor path: padded dim must be a multiple of %d", TC_BK);
   CMX_CHECK(plane_rows < (int64_t)0x7fffffff, "tensor path: more than 2^31 rows per shard");
+  if (g_tc_small && nq <= 128) {
+    TcParams p;
+    p.row0 = row0; p.nrows = nrows; p.kblocks = d_pad / TC_BK; p.nq = nq;
+    p.q_inv_scale = q_inv_scale_dev; p.b_inv_scale = b_inv_scale;
+    p.tau = ws.tau; p.cnt = ws.cnt; p.cand = ws.cand; p.cap = ws.cap;
+    p.dense = dense; p.dense_row0 = dense_row0; p.flags = g_tc_flags; p.mtiles = 1; p.ntiles = 0;
+    if (nq <= 16) return launch_tc_small<16, 5>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
+    if (nq <= 32) return launch_tc_small<32, 4>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
+    if (nq <= 64) return launch_tc_small<64, 4>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
+    return launch_tc_small<128, 3>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
+  }
   const bool pair = g_tc_pair && nq > 128;
   const int bn = pair ? 128 : g_tc_bn;  // pair: each CTA loads a 128-row half of the 256-row tile
   CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;

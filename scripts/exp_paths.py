@@ -37,19 +37,12 @@ def run(nq, k, path, reps=5, variant=None):
                       "select_ms": round(se / reps, 3), "corpus_GBps_total": round(gb * passes / (ms / 1e3), 1),
                       "corpus_GBps_score_kernel": round(gb * passes / (sc / reps / 1e3), 1), "slabs": st["slabs"]}), flush=True)
 
-for v in (2, 3):
-    run(8, 100, "stream", variant=v)
-    run(8, 1000, "stream", variant=v)
-_lib.check(_lib.lib().cmx_debug_set_stream_variant(2))
-for nq in (1, 2, 4):
+for small in (0, 1):
+    _lib.check(_lib.lib().cmx_debug_set_tensor_small(small))
+    for nq in (5, 8, 16, 32, 64, 128):
+        run(nq, 100, "tensor", variant=small)
+    run(128, 1000, "tensor", variant=small)
+_lib.check(_lib.lib().cmx_debug_set_tensor_small(1))
+for nq in (1, 4):
     run(nq, 100, "stream")
-run(16, 100, "stream")
-for nq in (8, 32, 128, 256, 1024):
-    run(nq, 100, "tensor")
-run(128, 1000, "tensor")
-for bn in (128,):
-    _lib.check(_lib.lib().cmx_debug_set_tensor_tile(bn))
-    for nq in (8, 32, 128):
-        run(nq, 100, "tensor", variant=bn)
-_lib.check(_lib.lib().cmx_debug_set_tensor_tile(256))
-run(6980, 1000, "tensor", reps=3)
+run(256, 100, "tensor")

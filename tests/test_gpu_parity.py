@@ -173,6 +173,26 @@ def test_tensor_single_and_pair_kernels(pair, shape):
         _lib.check(_lib.lib().cmx_debug_set_tensor_pair(-1))
 
 
+@pytest.mark.parametrize("small", [0, 1])
+@pytest.mark.parametrize("nq", [5, 16, 17, 33, 64, 100, 128])
+def test_tensor_small_batch_kernel(small, nq):
+    """nq <= 128: the corpus-as-M tensor kernel (and, for comparison, the padded 128-row one)."""
+    from cmx import _lib
+
+    rng = np.random.default_rng(400 + nq)
+    d = 1024 if nq in (16, 128) else 128
+    X, Q = _unit(rng, 20011, d), _unit(rng, nq, d)
+    X[9000:9040] = X[100:140]  # ties
+    _lib.check(_lib.lib().cmx_debug_set_tensor_small(small))
+    try:
+        sh = _shard(X)
+        for k in (1, 100, 1000):
+            D, I = sh.search(Q, k, path="tensor")
+            _check(D, I, X, Q, k)
+    finally:
+        _lib.check(_lib.lib().cmx_debug_set_tensor_small(1))
+
+
 @pytest.mark.parametrize("d", [96, 100, 768])
 def test_tensor_ragged_dims(d):
     """d not a multiple of 64 -> zero-padded operand planes; N, nq not tile multiples."""
