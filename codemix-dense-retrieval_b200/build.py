@@ -29,12 +29,12 @@ NVCC_FLAGS = [
 
 
 def _sources():
-    return sorted(CSRC.glob("*.cu"))
+    return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")))
 
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "cmx.h"]):
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "cmx.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())

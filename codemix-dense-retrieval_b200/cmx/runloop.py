@@ -8,8 +8,9 @@ Mirrors (same names, argument meaning, file names and byte-for-byte file content
 
 What changed relative to the reference loop: the ~7000 per-query ``safe_mix`` GPU
 round-trips per alpha become one fused kernel (``search_mixed``), and the ~700k
-f-strings per alpha become vectorised numpy string ops.  Output files are
-identical to what the reference loop would write for the same (D, I).
+f-strings per alpha (7 M at k=1000) are formatted by a multi-threaded C++ routine in
+libcmx.so (``cmx_trec_mono`` / ``cmx_trec_bilingual``, csrc/trec_text.cpp).  Output
+files are byte-identical to what the reference loop would write for the same (D, I).
 """
 from __future__ import annotations
 
@@ -75,154 +76,204 @@ def format_scores(D: np.ndarray, decimals: int) -> np.ndarray:
     return txt.reshape(x.shape)
 
 
+class StrTable:
+    """A list of strings as ONE utf-8 buffer + n+1 offsets (the layout the C formatter reads)."""
+
+    def __init__(self, items):
+        enc = [str(v).encode("utf-8") for v in items]
+        self.n = len(enc)
+        self.buf = b"".join(enc)
+        off = np.zeros(self.n + 1, dtype=np.int64)
+        if self.n:
+            np.cumsum(np.fromiter((len(b) for b in enc), dtype=np.int64, count=self.n), out=off[1:])
+        self.off = off
+
+
 class DocTable:
-    """int id -> document-id string, vectorised; ids missing from the table print as
-    ``str(id)`` (the reference's ``id_lookup.get(int(doc), str(doc))``)."""
+    """int id -> document-id string; ids missing from the table print as ``str(id)``
+    (the reference's ``id_lookup.get(int(doc), str(doc))``)."""
 
     def __init__(self, id_lookup):
         if isinstance(id_lookup, DocTable):
-            self.keys, self.names = id_lookup.keys, id_lookup.names
+            self.keys, self.table = id_lookup.keys, id_lookup.table
             return
         if isinstance(id_lookup, dict):
             keys = np.fromiter(id_lookup.keys(), dtype=np.int64, count=len(id_lookup))
-            names = np.array(list(id_lookup.values()), dtype=_SDT)
+            names = list(id_lookup.values())
+            order = np.argsort(keys, kind="stable")
+            keys = keys[order]
+            names = [names[i] for i in order]
+            if keys.size and keys[0] == 0 and keys[-1] == keys.size - 1 and np.all(np.diff(keys) == 1):
+                keys = None  # ids are exactly 0..n-1: direct indexing
         else:  # sequence: position = id
-            names = np.array(list(id_lookup), dtype=_SDT)
-            keys = np.arange(len(names), dtype=np.int64)
-        order = np.argsort(keys, kind="stable")
-        self.keys, self.names = keys[order], names[order]
+            names, keys = list(id_lookup), None
+        self.keys = keys
+        self.table = StrTable(names)
 
-    def lookup(self, ids: np.ndarray) -> np.ndarray:
-        ids = np.asarray(ids, dtype=np.int64)
-        flat = ids.reshape(-1)
-        out = flat.astype(_SDT)
-        if self.keys.size:
-            pos = np.clip(np.searchsorted(self.keys, flat), 0, self.keys.size - 1)
-            hit = self.keys[pos] == flat
-            out = np.where(hit, self.names[pos], out)
-        return out.reshape(ids.shape)
+    def lookup(self, ids) -> list:
+        """Python-level equivalent (small inputs / tests)."""
+        out = []
+        buf, off = self.table.buf, self.table.off
+        for v in np.asarray(ids, dtype=np.int64).reshape(-1).tolist():
+            if self.keys is None:
+                pos = v if 0 <= v < self.table.n else -1
+            else:
+                pos = int(np.searchsorted(self.keys, v))
+                pos = pos if pos < self.keys.size and self.keys[pos] == v else -1
+            out.append(buf[off[pos]:off[pos + 1]].decode("utf-8") if pos >= 0 else str(v))
+        return out
 
 
-def mono_trec_text(qids: Sequence[str], D: np.ndarray, I: np.ndarray, docs: DocTable, tag: str = "onepass-cm") -> str:
+def _host_f32_i64(D, I):
+    D = np.ascontiguousarray(_to_host(D), dtype=np.float32)
+    I = np.ascontiguousarray(_to_host(I), dtype=np.int64)
+    assert D.ndim == 2 and D.shape == I.shape
+    return D, I
+
+
+def _take_bytes(ptr, length) -> bytes:
+    import ctypes as C
+
+    from . import _lib
+
+    try:
+        return C.string_at(ptr.value, length.value)
+    finally:
+        _lib.lib().cmx_free_text(ptr)
+
+
+def mono_trec_text(qids: Sequence[str], D, I, docs, tag: str = "onepass-cm", nthreads: int = 0) -> str:
+    return mono_trec_bytes(qids, D, I, docs, tag, nthreads).decode("utf-8")
+
+
+def mono_trec_bytes(qids: Sequence[str], D, I, docs, tag: str = "onepass-cm", nthreads: int = 0) -> bytes:
     """Text of one mono run file: lines ``qid\\tQ0\\tdoc\\trank\\tscore(.4f)\\ttag`` joined
-    with newlines, no trailing newline (onepass_dense_mix_run_custom_lang.py:879-888)."""
-    D = np.asarray(D)
-    I = np.asarray(I)
+    with newlines, no trailing newline (onepass_dense_mix_run_custom_lang.py:879-888).
+    Formatted by the multi-threaded C routine ``cmx_trec_mono``."""
+    import ctypes as C
+
+    from . import _lib
+
+    D, I = _host_f32_i64(D, I)
     nq, k = D.shape
     if nq == 0:
-        return ""
-    q = np.repeat(np.array(list(qids), dtype=_SDT), k).reshape(nq, k)
-    rank = np.tile(np.arange(1, k + 1, dtype=np.int64).astype(_SDT), (nq, 1))
-    line = np.strings.add(q, "\tQ0\t")
-    line = np.strings.add(line, docs.lookup(I))
-    line = np.strings.add(np.strings.add(line, "\t"), rank)
-    line = np.strings.add(np.strings.add(line, "\t"), format_scores(D, 4))
-    line = np.strings.add(line, "\t" + tag)
-    return "\n".join(line.reshape(-1).tolist())
+        return b""
+    docs = docs if isinstance(docs, DocTable) else DocTable(docs)
+    q = StrTable(qids)
+    assert q.n == nq
+    out, n = C.c_void_p(), C.c_int64(0)
+    keys_ptr = None if docs.keys is None else docs.keys.ctypes.data
+    _lib.check(_lib.lib().cmx_trec_mono(D.ctypes.data, I.ctypes.data, nq, k, q.buf, q.off.ctypes.data, docs.table.buf,
+                                        docs.table.off.ctypes.data, keys_ptr, docs.table.n, tag.encode("utf-8"),
+                                        int(nthreads), C.byref(out), C.byref(n)))
+    return _take_bytes(out, n)
 
 
-def bilingual_raw_text(qids: Sequence[str], D: np.ndarray, I: np.ndarray, id2doc: Sequence[str], tag: str) -> str:
-    """Raw bilingual run: ``qid Q0 did rank score(.6f) tag\\n``; rows with an id outside
-    [0, len(id2doc)) are skipped and keep their rank number
-    (onepass_bilingual_mix_hub_custom_lang.py:950-958)."""
-    D = np.asarray(D)
-    I = np.asarray(I)
+class BaseTable:
+    """derived ids ``base#lang`` by position, plus their base-id grouping for the collapse."""
+
+    def __init__(self, id2doc: Sequence[str]):
+        names = list(id2doc)
+        self.docs = StrTable(names)
+        code_of, bases, codes = {}, [], np.empty(len(names), dtype=np.int32)
+        for i, nme in enumerate(names):
+            b = nme.split("#", 1)[0]
+            c = code_of.get(b)
+            if c is None:
+                c = code_of[b] = len(bases)
+                bases.append(b)
+            codes[i] = c
+        self.codes = codes
+        self.bases = StrTable(bases)
+
+
+def bilingual_texts(qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int = 0):
+    raw, col = bilingual_bytes(qids, D, I, id2doc, tag, nthreads)
+    return raw.decode("utf-8"), col.decode("utf-8")
+
+
+def bilingual_bytes(qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int = 0):
+    """(raw run text, collapsed run text) of one bilingual alpha
+    (onepass_bilingual_mix_hub_custom_lang.py:950-958 and collapse_run_max :165-181):
+    raw lines ``qid Q0 did rank score(.6f) tag\\n`` for ids inside [0, len(id2doc)) -- others are
+    skipped and keep their rank number; collapse groups a query's hits by
+    ``base = did.split('#',1)[0]``, takes the max of the 6-decimal ROUNDED scores, sorts stably
+    descending (ties keep first-seen order), re-ranks, tag ``bilingual-mix``."""
+    import ctypes as C
+
+    from . import _lib
+
+    D, I = _host_f32_i64(D, I)
     nq, k = D.shape
     if nq == 0:
-        return ""
-    names = id2doc if isinstance(id2doc, np.ndarray) and id2doc.dtype == _SDT else np.array(list(id2doc), dtype=_SDT)
-    valid = (I >= 0) & (I < len(names))
-    did = names[np.clip(I, 0, max(len(names) - 1, 0))] if len(names) else np.full(I.shape, "", dtype=_SDT)
-    q = np.repeat(np.array(list(qids), dtype=_SDT), k).reshape(nq, k)
-    rank = np.tile(np.arange(1, k + 1, dtype=np.int64).astype(_SDT), (nq, 1))
-    line = np.strings.add(np.strings.add(q, " Q0 "), did)
-    line = np.strings.add(np.strings.add(line, " "), rank)
-    line = np.strings.add(np.strings.add(line, " "), format_scores(D, 6))
-    line = np.strings.add(line, " " + tag + "\n")
-    return "".join(line[valid].tolist())
+        return b"", b""
+    qids = list(qids)
+    if len(set(qids)) != len(qids):  # the reference merges rows of a repeated qid: rare, keep it exact
+        raw = bilingual_raw_text_py(qids, D, I, id2doc, tag)
+        return raw.encode("utf-8"), collapse_text_py(raw.splitlines(keepends=True)).encode("utf-8")
+    bt = id2doc if isinstance(id2doc, BaseTable) else BaseTable(id2doc)
+    q = StrTable(qids)
+    raw, nraw, col, ncol = C.c_void_p(), C.c_int64(0), C.c_void_p(), C.c_int64(0)
+    _lib.check(_lib.lib().cmx_trec_bilingual(D.ctypes.data, I.ctypes.data, nq, k, q.buf, q.off.ctypes.data, bt.docs.buf,
+                                             bt.docs.off.ctypes.data, bt.docs.n, bt.codes.ctypes.data, bt.bases.buf,
+                                             bt.bases.off.ctypes.data, bt.bases.n, tag.encode("utf-8"), int(nthreads),
+                                             C.byref(raw), C.byref(nraw), C.byref(col), C.byref(ncol)))
+    return _take_bytes(raw, nraw), _take_bytes(col, ncol)
 
 
-def collapse_by_base(qids: Sequence[str], D: np.ndarray, I: np.ndarray, id2doc: Sequence[str]) -> str:
-    """``collapse_run_max`` computed from (D, I) instead of re-parsing the raw text:
-    group hits of a query by ``base = did.split('#',1)[0]``, score = max of the
-    6-decimal-ROUNDED scores, stable descending sort (ties keep first-seen order),
-    re-rank, tag ``bilingual-mix`` (onepass_bilingual_mix_hub_custom_lang.py:165-181)."""
-    D = np.asarray(D)
-    I = np.asarray(I)
-    nq, k = D.shape
-    names = list(id2doc)
-    bases_all = np.array([n.split("#", 1)[0] for n in names], dtype=_SDT) if names else np.empty((0,), dtype=_SDT)
-    # integer code per base string (first-seen order is restored per query below)
-    uniq, base_code = (np.unique(bases_all, return_inverse=True) if len(names) else (bases_all, np.empty((0,), np.int64)))
-    valid = (I >= 0) & (I < len(names))
-    # scores as the raw file would carry them: rounded to 6 decimals, then float()
-    x = np.asarray(D, dtype=np.float32).astype(np.float64)
-    rounded = np.copysign(np.rint(np.abs(x) * 1e6), x) / 1e6
-    out: List[str] = []
-    # a qid occurring in several rows is one group in the reference (dict keyed by qid)
-    first_row: Dict[str, int] = {}
-    rows_of: Dict[str, List[int]] = {}
+def bilingual_raw_text(qids, D, I, id2doc, tag: str) -> str:
+    return bilingual_texts(qids, D, I, id2doc, tag)[0]
+
+
+def collapse_by_base(qids, D, I, id2doc) -> str:
+    return bilingual_texts(qids, D, I, id2doc, "x")[1]
+
+
+def bilingual_raw_text_py(qids, D, I, id2doc, tag: str) -> str:
+    names = id2doc.docs if isinstance(id2doc, BaseTable) else None
+    lst = list(id2doc) if names is None else [names.buf[names.off[i]:names.off[i + 1]].decode() for i in range(names.n)]
+    out = []
     for r, qid in enumerate(qids):
-        rows_of.setdefault(qid, []).append(r)
-        first_row.setdefault(qid, r)
-    for qid, rows in rows_of.items():
-        sel_codes = np.concatenate([base_code[I[r][valid[r]]] for r in rows]) if rows else np.empty((0,), np.int64)
-        sel_scores = np.concatenate([rounded[r][valid[r]] for r in rows])
-        if sel_codes.size == 0:
-            continue
-        # first-seen order of bases + max score per base
-        u, first_idx, inv = np.unique(sel_codes, return_index=True, return_inverse=True)
-        mx = np.full(u.shape, -np.inf)
-        np.maximum.at(mx, inv, sel_scores)
-        seen_order = np.argsort(first_idx, kind="stable")
-        u, mx = u[seen_order], mx[seen_order]
-        order = np.argsort(-mx, kind="stable")
-        u, mx = u[order], mx[order]
-        base_txt = uniq[u]
-        score_txt = _format_f64(mx, 6)
-        ranks = np.arange(1, u.size + 1, dtype=np.int64).astype(_SDT)
-        line = np.strings.add(qid + " Q0 ", base_txt)
-        line = np.strings.add(np.strings.add(line, " "), ranks)
-        line = np.strings.add(np.strings.add(line, " "), score_txt)
-        line = np.strings.add(line, " bilingual-mix\n")
-        out.append("".join(line.tolist()))
+        for rank, (sc, ix) in enumerate(zip(D[r].tolist(), I[r].tolist()), 1):
+            if ix < 0 or ix >= len(lst):
+                continue
+            out.append(f"{qid} Q0 {lst[ix]} {rank} {sc:.6f} {tag}\n")
     return "".join(out)
 
 
-def _format_f64(x: np.ndarray, decimals: int) -> np.ndarray:
-    """f"{v:.6f}" for doubles that are already multiples of 1e-6 (up to rounding)."""
-    scale = 10 ** decimals
-    n = np.rint(np.abs(x) * scale).astype(np.int64)
-    ip = (n // scale).astype(_SDT)
-    fp = np.strings.zfill((n % scale).astype(_SDT), decimals)
-    sign = np.where(np.signbit(x), "-", "").astype(_SDT)
-    return np.strings.add(np.strings.add(np.strings.add(sign, ip), "."), fp)
+def collapse_text_py(raw_lines) -> str:
+    by_q: Dict[str, Dict[str, float]] = {}
+    for line in raw_lines:
+        line = line.strip()
+        if not line:
+            continue
+        qid, _, did, _rk, sc, _tag = line.split()
+        base = did.split("#", 1)[0]
+        score = float(sc)
+        g = by_q.setdefault(qid, {})
+        if base not in g or score > g[base]:
+            g[base] = score
+    out = []
+    for qid, groups in by_q.items():
+        for rank, (base, val) in enumerate(sorted(groups.items(), key=lambda kv: kv[1], reverse=True), 1):
+            out.append(f"{qid} Q0 {base} {rank} {val:.6f} bilingual-mix\n")
+    return "".join(out)
 
 
 def collapse_run_max(in_run, out_run) -> None:
     """Text-to-text form with the reference's signature (used when only the raw file exists)."""
-    by_q: Dict[str, Dict[str, float]] = {}
     with open(in_run, "r", encoding="utf-8") as f:
-        for line in f:
-            line = line.strip()
-            if not line:
-                continue
-            qid, _, did, _rk, sc, _tag = line.split()
-            base = did.split("#", 1)[0]
-            score = float(sc)
-            g = by_q.setdefault(qid, {})
-            if base not in g or score > g[base]:
-                g[base] = score
+        text = collapse_text_py(f)
     with open(out_run, "w", encoding="utf-8") as out:
-        for qid, groups in by_q.items():
-            items = sorted(groups.items(), key=lambda kv: kv[1], reverse=True)
-            for rank, (base, val) in enumerate(items, 1):
-                out.write(f"{qid} Q0 {base} {rank} {val:.6f} bilingual-mix\n")
+        out.write(text)
 
 
-def _atomic_write(path: pathlib.Path, text: str) -> None:
+def _atomic_write(path: pathlib.Path, text) -> None:
     tmp = path.with_name(path.name + f".tmp{os.getpid()}")
-    tmp.write_text(text, encoding="utf-8")
+    if isinstance(text, bytes):
+        tmp.write_bytes(text)
+    else:
+        tmp.write_text(text, encoding="utf-8")
     os.replace(tmp, path)
 
 
@@ -257,7 +308,7 @@ def run_alpha_sweep(index, id_lookup, qids: Sequence[str], P, S, alphas: Sequenc
         for gi, alpha in enumerate(group):
             label = format_alpha(alpha)
             run_path = outdir / f"cm-alpha-{label}.trec"
-            _atomic_write(run_path, mono_trec_text(qids, D[gi], I[gi], docs, tag))
+            _atomic_write(run_path, mono_trec_bytes(qids, D[gi], I[gi], docs, tag))
             written.append(run_path)
             if log:
                 log(f"Run saved: {run_path}  ({len(qids)} queries, alpha={label}, search {t1 - t0:.3f}s)")
@@ -273,7 +324,7 @@ def run_alpha_sweep_bilingual(index, id2doc: Sequence[str], qids: Sequence[str],
     outdir = pathlib.Path(outdir)
     outdir.mkdir(parents=True, exist_ok=True)
     qids = list(qids)
-    names = np.array(list(id2doc), dtype=_SDT)
+    table = BaseTable(id2doc)
     written: List[pathlib.Path] = []
     alphas = [float(a) for a in alphas]
     for a0 in range(0, len(alphas), max(1, alpha_batch)):
@@ -285,8 +336,9 @@ def run_alpha_sweep_bilingual(index, id2doc: Sequence[str], qids: Sequence[str],
             set_name = f"cm-alpha-{label}"
             run_raw = outdir / f"{set_name}_raw.trec"
             run_base = outdir / f"{set_name}.trec"
-            _atomic_write(run_raw, bilingual_raw_text(qids, D[gi], I[gi], names, tag))
-            _atomic_write(run_base, collapse_by_base(qids, D[gi], I[gi], id2doc))
+            raw_text, collapsed = bilingual_bytes(qids, D[gi], I[gi], table, tag)
+            _atomic_write(run_raw, raw_text)
+            _atomic_write(run_base, collapsed)
             m = dict(meta or {})
             m.update({"alpha": label, "runs": {"raw": str(run_raw), "base": str(run_base)},
                       "index": {"type": "IndexIDMap(IndexFlatIP)", "size": int(index.ntotal), "dim": int(index.d)},

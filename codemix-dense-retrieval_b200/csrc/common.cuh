@@ -109,7 +109,7 @@ void set_stream_variant(int v);  // tuning experiments
 int tensor_path_available();
 void set_tensor_tile(int bn);  // 256 (default) or 128 corpus rows per tile
 void set_tensor_flags(int f);  // tuning experiments (cache hints)
-void set_tensor_small(int on);  // corpus-as-M kernel for nq <= 128
+void set_tensor_small(int on);  // corpus-as-M kernel for nq <= 64
 void set_tensor_pair(int on);  // CTA-pair (cta_group::2) scorer for nq > 128
 int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
                         int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,

@@ -136,6 +136,28 @@ CMX_API int cmx_merge_topk_peers(const float* const* D_parts, const int64_t* con
                                  int64_t nq, int k, int64_t q0, int64_t q1, float* const* D_outs,
                                  int64_t* const* I_outs, int nouts, int device, void* stream);
 
+/* ---- run-file text (host side, multi-threaded) -------------------------------------
+ * replaces the per-line f-string loops: onepass_dense_mix_run_custom_lang.py:879-888 (mono),
+ * onepass_bilingual_mix_hub_custom_lang.py:950-958 (raw) and :165-181 (collapse_run_max).
+ * Strings travel as one UTF-8 buffer plus n+1 offsets.  D, I are HOST arrays [nq,k].
+ * The returned buffers are malloc'ed; release them with cmx_free_text.
+ * mono: lines "qid\tQ0\tdoc\trank\tscore(.4f)\ttag" joined by '\n' (no trailing newline);
+ *   doc = docs[pos] where pos = position of the id in the sorted doc_keys (or the id itself
+ *   when doc_keys is NULL), else the decimal id (id_lookup.get(int(doc), str(doc))).
+ * bilingual: raw lines "qid Q0 did rank score(.6f) tag\n" for ids inside [0, ndocs) (others
+ *   skipped, rank kept) and the collapsed run: per query group by base_code[id], max of the
+ *   6-decimal rounded scores, stable sort descending, "qid Q0 base rank score bilingual-mix\n". */
+CMX_API int cmx_trec_mono(const float* D, const int64_t* I, int64_t nq, int k, const char* qids,
+                          const int64_t* qid_off, const char* docs, const int64_t* doc_off,
+                          const int64_t* doc_keys, int64_t ndocs, const char* tag, int nthreads,
+                          char** out, int64_t* out_len);
+CMX_API int cmx_trec_bilingual(const float* D, const int64_t* I, int64_t nq, int k, const char* qids,
+                               const int64_t* qid_off, const char* docs, const int64_t* doc_off,
+                               int64_t ndocs, const int32_t* base_code, const char* bases,
+                               const int64_t* base_off, int64_t nbases, const char* tag, int nthreads,
+                               char** raw_out, int64_t* raw_len, char** col_out, int64_t* col_len);
+CMX_API void cmx_free_text(char* p);
+
 /* ---- instrumentation --------------------------------------------------------*/
 typedef struct cmx_search_stats {
   int32_t path;            /* CMX_PATH_STREAM / CMX_PATH_TENSOR actually used       */
