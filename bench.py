@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--nq", type=int, default=NQ_FULL)
     ap.add_argument("--k", type=int, default=K_FULL)
     ap.add_argument("--path", default="auto", choices=["auto", "stream", "tensor"])
+    ap.add_argument("--precision", default="rescore", choices=["rescore", "split"],
+                    help="tensor-path arithmetic: one fp16 MMA pass + exact fp32 rescoring (default) or 3-pass split precision")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "allgather"],
                     help="multi-GPU merge: fused peer-memory kernel (p2p) or NCCL all_gather + merge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -251,6 +253,7 @@ def run_cmx(a) -> None:
     assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
 
     d, k, nq, N = a.dim, a.k, a.nq, a.rows
+    _lib.set_default_precision(a.precision)
     index = ShardedIndex(d, N, device=local_rank, exchange=a.exchange)
     index.path = a.path
     fill_shard(index, index.row0, index.row1, d, dev)
@@ -348,9 +351,10 @@ def run_cmx(a) -> None:
     d_pad = (d + 63) // 64 * 64
     used_tensor = stats["path"] == 2
     per_step_score_ms = score_ms_max / a.steps
+    passes = 3 if a.precision == "split" else 1
     if used_tensor:
         alg_flops = 2.0 * nq * n_local * d  # per step on this rank
-        executed = 3.0 * 2.0 * nq * n_local * d_pad  # three fp16 MMA passes (hi*hi, hi*lo, lo*hi)
+        executed = passes * 2.0 * nq * n_local * d_pad  # fp16 MMA passes actually issued
         achieved = executed / (per_step_score_ms / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
         traffic, per_row = ncu_traffic("tc_score_kernel", n_local, d)
@@ -358,11 +362,12 @@ def run_cmx(a) -> None:
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_note": f"DRAM bytes of the step's scoring launches = {per_row} B per corpus row (ncu capture, "
                                     "profiles/ncu_traffic.json) x rows; algorithmic = 4096 B per row (fp16 hi+lo planes read once)",
-                    "passes": 3,
+                    "passes": passes,
                     "achieved_alg_fp32_equiv": alg_flops / (per_step_score_ms / 1e3) / 1e12,
                     "kernel_ms_per_step": per_step_score_ms, "launches_per_step": score_launches / a.steps,
                     "peak_source": peaks["source"] + ", sustained dense 16-bit (fp16 == bf16 rate)",
-                    "note": "achieved = executed MMA flops (3 x 2*nq*N*d_pad) / CUDA-event time of the scoring launches of one step"}
+                    "note": "achieved = executed MMA flops (passes x 2*nq*N*d_pad) / CUDA-event time of the scoring launches of one step; "
+                            "rescore precision: 1 fp16 pass filters, the survivors are then scored exactly in fp32 (time in select_ms_per_step)"}
     else:
         groups = (nq + 7) // 8
         alg_bytes = groups * 4.0 * n_local * d
@@ -390,12 +395,13 @@ def run_cmx(a) -> None:
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f16x3-split+f32acc" if used_tensor else "f32",
+        "dtype": ("f16-filter+f32-exact-rescore" if a.precision == "rescore" else "f16x3-split+f32acc") if used_tensor else "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(a), "rows": N, "dim": d, "queries": nq, "k": k, "alpha": ALPHA,
                    "parallelism": f"corpus row shards x{world}, exchange={index.exchange_used}" if world > 1 else "single GPU",
                    "cache": "inputs_larger_than_L2 (corpus %.1f GB per GPU)" % (n_local * d * 4 / 1e9),
-                   "path": "tensor" if used_tensor else "stream", "slabs": stats["slabs"], "reruns": stats["reruns"]},
+                   "path": "tensor" if used_tensor else "stream", "precision": a.precision if used_tensor else "fp32",
+                   "slabs": stats["slabs"], "reruns": stats["reruns"]},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": t_e2e_ms / a.steps,
                 "h2d_bytes_per_step": 2 * nq * d * 4, "d2h_bytes_per_step": nq * k * 12},

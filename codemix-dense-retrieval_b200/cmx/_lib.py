@@ -14,6 +14,7 @@ _HERE = pathlib.Path(__file__).resolve().parent
 LIB_PATH = pathlib.Path(os.environ.get("CMX_LIB", _HERE.parent / "lib" / "libcmx.so"))
 
 PATH_AUTO, PATH_STREAM, PATH_TENSOR = 0, 1, 2
+PRECISION_SPLIT, PRECISION_RESCORE = 0, 1
 MAX_K = 2048
 
 
@@ -80,6 +81,8 @@ def lib() -> C.CDLL:
     L.cmx_index_last_stats.argtypes = [vp, C.POINTER(SearchStats)]
     L.cmx_set_profiling.argtypes = [i32]
     L.cmx_index_set_cand_capacity.argtypes = [vp, i32]
+    L.cmx_index_set_precision.argtypes = [vp, i32]
+    L.cmx_set_default_precision.argtypes = [i32]
     L.cmx_debug_set_tensor_tile.argtypes = [i32]
     L.cmx_debug_set_stream_variant.argtypes = [i32]
     L.cmx_debug_set_tensor_flags.argtypes = [i32]
@@ -89,7 +92,7 @@ def lib() -> C.CDLL:
         "cmx_device_count cmx_index_create cmx_index_free cmx_index_reserve cmx_index_add cmx_index_reset "
         "cmx_index_ntotal cmx_index_dim cmx_index_device cmx_index_reconstruct cmx_index_data cmx_index_search "
         "cmx_mix_normalize cmx_search_mixed cmx_merge_topk cmx_merge_topk_peers cmx_trec_mono cmx_trec_bilingual cmx_index_last_stats cmx_set_profiling "
-        "cmx_index_set_cand_capacity cmx_debug_set_tensor_tile cmx_debug_set_stream_variant cmx_debug_set_tensor_flags cmx_debug_set_tensor_pair cmx_debug_set_tensor_small"
+        "cmx_index_set_cand_capacity cmx_index_set_precision cmx_set_default_precision cmx_debug_set_tensor_tile cmx_debug_set_stream_variant cmx_debug_set_tensor_flags cmx_debug_set_tensor_pair cmx_debug_set_tensor_small"
     ).split():
         getattr(L, name).restype = i32
     _lib = L
@@ -111,6 +114,12 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return int(lib().cmx_launch_count())
+
+
+def set_default_precision(mode) -> None:
+    """'rescore' (default) or 'split' for indexes created afterwards."""
+    m = {"split": PRECISION_SPLIT, "rescore": PRECISION_RESCORE}.get(mode, mode)
+    check(lib().cmx_set_default_precision(int(m)))
 
 
 def set_profiling(on: bool) -> None:

@@ -111,6 +111,12 @@ class Shard:
         check(_lib.lib().cmx_index_data(self._h, C.byref(p)))
         return int(p.value or 0)
 
+    def set_precision(self, mode) -> None:
+        """'rescore' (default: one fp16 MMA pass + exact fp32 rescoring of a provably sufficient
+        candidate superset) or 'split' (three fp16 MMA passes, fp32-faithful tensor-core scores)."""
+        m = {"split": _lib.PRECISION_SPLIT, "rescore": _lib.PRECISION_RESCORE}.get(mode, mode)
+        check(_lib.lib().cmx_index_set_precision(self._h, int(m)))
+
     def set_cand_capacity(self, cap: int) -> None:
         check(_lib.lib().cmx_index_set_cand_capacity(self._h, int(cap)))
 

@@ -14,6 +14,7 @@ namespace cmx {
 static thread_local std::string t_error;
 std::atomic<uint64_t> g_launches{0};
 int g_profiling = 0;
+static int g_default_precision = CMX_PRECISION_RESCORE;
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -65,13 +66,16 @@ struct cmx_index {
   // fp16 hi/lo planes for the tensor path [cap_rows, d_pad], built lazily
   __half* Bhi = nullptr;
   __half* Blo = nullptr;
-  int64_t plane_cap = 0, plane_rows = 0;
+  int64_t plane_cap = 0, plane_rows = 0;       // hi plane
+  int64_t lo_cap = 0, lo_rows = 0;             // lo plane (split precision only)
   float plane_scale = 0.f;
   uint32_t absmax_bits = 0;  // max |x| over all finite stored elements
-  uint32_t* absmax_dev = nullptr;
+  uint32_t* absmax_dev = nullptr;   // [2]: absmax bits, max row norm bits
+  float row_norm_max = 0.f;  // max ||row||_2 over finite rows (rescore-mode error bound)
+  int precision = CMX_PRECISION_RESCORE;  // set from the process default at creation
   // search workspace
   SearchWs ws;
-  int64_t tau_cap = 0, cnt_cap = 0, cand_cap_elems = 0;
+  int64_t tau_cap = 0, cnt_cap = 0, cand_cap_elems = 0, margin_cap = 0;
   int cand_cap_override = 0;
   float* q_dev = nullptr; int64_t q_cap = 0;        // staged / mixed queries
   float* p_dev = nullptr; int64_t p_cap = 0;        // staged P
@@ -79,6 +83,7 @@ struct cmx_index {
   __half* Qhi = nullptr; int64_t qhi_cap = 0;
   __half* Qlo = nullptr; int64_t qlo_cap = 0;
   uint32_t* q_absmax = nullptr;
+  float* margin_buf = nullptr;
   float* q_scale = nullptr;  // {scale, 1/scale}
   float* D_dev = nullptr; int64_t D_cap = 0;
   int64_t* I_dev = nullptr; int64_t I_cap = 0;
@@ -120,40 +125,54 @@ static int grow_store(cmx_index* ix, int64_t need_rows) {
   // planes follow the store lazily
   if (ix->Bhi) { cudaFree(ix->Bhi); ix->Bhi = nullptr; }
   if (ix->Blo) { cudaFree(ix->Blo); ix->Blo = nullptr; }
-  ix->plane_cap = 0;
-  ix->plane_rows = 0;
+  ix->plane_cap = ix->plane_rows = 0;
+  ix->lo_cap = ix->lo_rows = 0;
   return CMX_OK;
 }
 
-// build / extend the fp16 hi/lo planes so they cover rows [0, n)
-static int ensure_planes(cmx_index* ix, cudaStream_t st) {
+// build / extend the fp16 operand planes so they cover rows [0, n): the hi plane always,
+// the lo plane only for the split-precision scorer
+static int ensure_planes(cmx_index* ix, bool need_lo, cudaStream_t st) {
   const float want_scale = host_scale_for_absmax_bits(ix->absmax_bits);
-  if (ix->plane_cap < ix->cap_rows || !ix->Bhi || !ix->Blo) {
+  const size_t bytes = (size_t)ix->cap_rows * ix->d_pad * sizeof(__half);
+  if (ix->plane_scale != want_scale) {  // a later add() raised max|x|: re-split everything
+    ix->plane_rows = 0;
+    ix->lo_rows = 0;
+    ix->plane_scale = want_scale;
+  }
+  if (ix->plane_cap < ix->cap_rows || !ix->Bhi) {
     if (ix->Bhi) { cudaFree(ix->Bhi); ix->Bhi = nullptr; }
-    if (ix->Blo) { cudaFree(ix->Blo); ix->Blo = nullptr; }
-    const size_t bytes = (size_t)ix->cap_rows * ix->d_pad * sizeof(__half);
-    cudaError_t e1 = cudaMalloc((void**)&ix->Bhi, bytes);
-    cudaError_t e2 = (e1 == cudaSuccess) ? cudaMalloc((void**)&ix->Blo, bytes) : e1;
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-      if (ix->Bhi) { cudaFree(ix->Bhi); ix->Bhi = nullptr; }
-      ix->Blo = nullptr;
+    if (cudaMalloc((void**)&ix->Bhi, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      ix->Bhi = nullptr;
       ix->plane_cap = 0;
-      set_error("cannot allocate 2 x %.2f GB for the fp16 hi/lo planes (tensor path); shard the index over more GPUs",
+      set_error("cannot allocate %.2f GB for the fp16 operand plane (tensor path); shard the index over more GPUs",
                 (double)bytes / 1e9);
       return CMX_ERR_NOMEM;
     }
     ix->plane_cap = ix->cap_rows;
     ix->plane_rows = 0;
   }
-  if (ix->plane_scale != want_scale) {
-    ix->plane_rows = 0;
-    ix->plane_scale = want_scale;
+  if (need_lo && (ix->lo_cap < ix->cap_rows || !ix->Blo)) {
+    if (ix->Blo) { cudaFree(ix->Blo); ix->Blo = nullptr; }
+    if (cudaMalloc((void**)&ix->Blo, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      ix->Blo = nullptr;
+      ix->lo_cap = 0;
+      set_error("cannot allocate %.2f GB for the fp16 lo plane (split-precision tensor path); use the rescore "
+                "precision or shard the index over more GPUs", (double)bytes / 1e9);
+      return CMX_ERR_NOMEM;
+    }
+    ix->lo_cap = ix->cap_rows;
+    ix->lo_rows = 0;
   }
-  if (ix->plane_rows < ix->n) {
-    const int64_t r0 = ix->plane_rows;
+  // rows that still miss a plane (lo is written together with hi; hi-only rows are re-split for lo)
+  const int64_t r0 = need_lo ? std::min(ix->plane_rows, ix->lo_rows) : ix->plane_rows;
+  if (r0 < ix->n) {
     CMX_TRY(launch_split_planes(ix->X + r0 * ix->d, ix->n - r0, ix->d, ix->d_pad, nullptr, ix->plane_scale,
-                                ix->Bhi + r0 * ix->d_pad, ix->Blo + r0 * ix->d_pad, st));
+                                ix->Bhi + r0 * ix->d_pad, need_lo ? ix->Blo + r0 * ix->d_pad : nullptr, st));
     ix->plane_rows = ix->n;
+    if (need_lo) ix->lo_rows = ix->n;
   }
   return CMX_OK;
 }
@@ -201,8 +220,12 @@ static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe) {
 }
 
 // one pass over the corpus for queries q_d[0..nq) (nq <= kQueryChunk)
+// rescore = true: the tensor kernels run ONE fp16 MMA pass (approximate scores), the buffers keep
+// everything within 2*eps(q) of the k-th best approximate score, and the survivors get exact fp32
+// scores at the end; rescore = false: three-pass split precision, scores final as they come
 static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d,
-                       int64_t id_base, int path, bool safe, cudaStream_t st, bool* overflowed) {
+                       int64_t id_base, int path, bool rescore, bool safe, cudaStream_t st, bool* overflowed) {
+  if (path != CMX_PATH_TENSOR) rescore = false;
   const int cap = pick_cap(ix, k);
   const int64_t nq_pad = (nq + 127) / 128 * 128;
   CMX_TRY(ensure_buf(&ix->ws.tau, &ix->tau_cap, nq_pad));
@@ -210,12 +233,13 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
   CMX_TRY(ensure_buf(&ix->ws.cand, &ix->cand_cap_elems, nq * (int64_t)cap));
   if (!ix->ws.overflow) CMX_CUDA(cudaMalloc((void**)&ix->ws.overflow, sizeof(uint32_t)));
   ix->ws.cap = cap;
+  ix->ws.margin = nullptr;
   CMX_TRY(launch_ws_init(ix->ws, nq, nq_pad, st));
 
   if (path == CMX_PATH_TENSOR) {
-    CMX_TRY(ensure_planes(ix, st));
+    CMX_TRY(ensure_planes(ix, !rescore, st));
     CMX_TRY(ensure_buf(&ix->Qhi, &ix->qhi_cap, nq_pad * (int64_t)ix->d_pad));
-    CMX_TRY(ensure_buf(&ix->Qlo, &ix->qlo_cap, nq_pad * (int64_t)ix->d_pad));
+    if (!rescore) CMX_TRY(ensure_buf(&ix->Qlo, &ix->qlo_cap, nq_pad * (int64_t)ix->d_pad));
     if (!ix->q_absmax) CMX_CUDA(cudaMalloc((void**)&ix->q_absmax, sizeof(uint32_t)));
     if (!ix->q_scale) CMX_CUDA(cudaMalloc((void**)&ix->q_scale, 2 * sizeof(float)));
     CMX_CUDA(cudaMemsetAsync(ix->q_absmax, 0, sizeof(uint32_t), st));
@@ -223,13 +247,25 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
     CMX_TRY(launch_scale_from_absmax(ix->q_absmax, ix->q_scale, st));
     if (nq_pad > nq) {
       CMX_CUDA(cudaMemsetAsync(ix->Qhi + nq * (int64_t)ix->d_pad, 0, (size_t)(nq_pad - nq) * ix->d_pad * sizeof(__half), st));
-      CMX_CUDA(cudaMemsetAsync(ix->Qlo + nq * (int64_t)ix->d_pad, 0, (size_t)(nq_pad - nq) * ix->d_pad * sizeof(__half), st));
+      if (!rescore)
+        CMX_CUDA(cudaMemsetAsync(ix->Qlo + nq * (int64_t)ix->d_pad, 0, (size_t)(nq_pad - nq) * ix->d_pad * sizeof(__half), st));
     }
-    CMX_TRY(launch_split_planes(q_d, nq, ix->d, ix->d_pad, ix->q_scale, 1.0f, ix->Qhi, ix->Qlo, st));
+    CMX_TRY(launch_split_planes(q_d, nq, ix->d, ix->d_pad, ix->q_scale, 1.0f, ix->Qhi, rescore ? nullptr : ix->Qlo, st));
+    if (rescore) {
+      // |approx - exact| <= eps(q) = c_d * ||q|| * max_row ||x||:  2^-10 (1+2^-11) bounds the fp16 rounding
+      // of both operands (Cauchy-Schwarz over the element-wise relative errors), 2*d*2^-23 the fp32
+      // accumulation error of the tensor core and of the exact rescoring chain.  margin = 2 * eps.
+      const float c_d = 1.06f * 0.0009765625f + 2.0f * (float)ix->d * 1.1920929e-07f;
+      CMX_TRY(ensure_buf(&ix->margin_buf, &ix->margin_cap, nq_pad));
+      CMX_TRY(launch_query_margin(q_d, nq, ix->d, 2.0f * c_d * ix->row_norm_max, ix->margin_buf, st));
+      ix->ws.margin = ix->margin_buf;
+    }
   }
 
   const int align = (path == CMX_PATH_TENSOR) ? 256 : 32;
-  SlabPlan pl = plan_slabs(ix->n, k, cap, align, safe);
+  // rescore mode keeps the margin band on top of the k best: plan for ~4/3 k resident candidates
+  const int k_plan = rescore ? std::min(cap / 2, k + k / 3 + 8) : k;
+  SlabPlan pl = plan_slabs(ix->n, k_plan, cap, align, safe);
   const bool prof = g_profiling && !safe && (int)pl.rows.size() <= kMaxSlabEvents;
   if (prof) CMX_TRY(ensure_events(ix));
   int64_t seen = 0;
@@ -240,14 +276,21 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
     if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 0], st));
     if (path == CMX_PATH_TENSOR) {
       CMX_TRY(launch_tensor_score(ix->Bhi, ix->Blo, ix->n, seen, rows, ix->d_pad, ix->Qhi, ix->Qlo, nq, nq_pad,
-                                  ix->q_scale + 1, 1.0f / ix->plane_scale, ix->ws, dense, seen, st, ix->sm_count));
+                                  ix->q_scale + 1, 1.0f / ix->plane_scale, ix->ws, dense, seen, rescore ? 1 : 3, st,
+                                  ix->sm_count));
     } else {
       CMX_TRY(launch_stream_score(ix->X, seen, rows, ix->d, q_d, (int)nq, ix->ws, 0, dense, seen, st, ix->sm_count));
     }
     if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 1], st));
     if (dense) CMX_TRY(launch_set_counts(ix->ws, nq, (uint32_t)rows, st));
     const int last = (s == nslabs - 1) ? 1 : 0;
-    CMX_TRY(launch_compact(ix->ws, nq, k, last, D_d, I_d, id_base, st));
+    if (rescore) {
+      // keep the margin band, then (after the last slab) exact fp32 scores + exact top-k
+      CMX_TRY(launch_compact(ix->ws, nq, k, 0, D_d, I_d, id_base, st));
+      if (last) CMX_TRY(launch_rescore(ix->X, ix->d, q_d, ix->ws, nq, k, D_d, I_d, id_base, st));
+    } else {
+      CMX_TRY(launch_compact(ix->ws, nq, k, last, D_d, I_d, id_base, st));
+    }
     if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 2], st));
     seen += rows;
   }
@@ -257,7 +300,7 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
   *overflowed = (ovf != 0);
   ix->stats.slabs += nslabs;
   ix->stats.score_launches += nslabs * ((path == CMX_PATH_TENSOR) ? 1 : (int)((nq + 7) / 8));
-  ix->stats.select_launches += nslabs;
+  ix->stats.select_launches += nslabs + (rescore ? 1 : 0);
   if (prof) {
     for (int s = 0; s < nslabs; ++s) {
       float a = 0.f, b = 0.f;
@@ -292,12 +335,19 @@ static int search_device(cmx_index* ix, const float* q_d, int64_t nq, int k, flo
   for (int64_t q0 = 0; q0 < nq; q0 += kQueryChunk) {
     const int64_t nqc = std::min<int64_t>(kQueryChunk, nq - q0);
     bool ovf = false;
-    CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, false, st, &ovf));
+    bool rescore = ix->precision == CMX_PRECISION_RESCORE && ix->row_norm_max > 0.f;
+    CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, rescore, false, st, &ovf));
     if (ovf) {
       // some query's candidate buffer overflowed (rows arrived in an adversarial order for the
       // stale threshold); redo this chunk with the worst-case-safe slab schedule
       ix->stats.reruns = 1;
-      CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, true, st, &ovf));
+      CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, rescore, true, st, &ovf));
+      if (ovf && rescore && path == CMX_PATH_TENSOR) {
+        // more than `cap` rows inside the margin band of one query (e.g. thousands of near-duplicate
+        // rows): the approximate pass cannot separate them -- use the split-precision scorer
+        ix->stats.reruns = 2;
+        CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, false, true, st, &ovf));
+      }
       if (ovf) { set_error("internal: candidate buffer overflow in safe mode"); return CMX_ERR_INTERNAL; }
     }
   }
@@ -353,8 +403,9 @@ int cmx_index_create(int d, int device, cmx_index** out) {
   ix->d_pad = (d + 63) / 64 * 64;
   ix->device = device;
   ix->sm_count = prop.multiProcessorCount;
+  ix->precision = g_default_precision;
   memset(&ix->stats, 0, sizeof(ix->stats));
-  cudaError_t e = cudaMalloc((void**)&ix->absmax_dev, sizeof(uint32_t));
+  cudaError_t e = cudaMalloc((void**)&ix->absmax_dev, 2 * sizeof(uint32_t));
   if (e != cudaSuccess) { delete ix; set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return CMX_ERR_NOMEM; }
   *out = ix;
   return CMX_OK;
@@ -364,7 +415,7 @@ int cmx_index_free(cmx_index* ix) {
   if (!ix) return CMX_OK;
   DevGuard g(ix->device);
   void* ptrs[] = {ix->X, ix->Bhi, ix->Blo, ix->absmax_dev, ix->ws.tau, ix->ws.cnt, ix->ws.cand, ix->ws.overflow,
-                  ix->q_dev, ix->p_dev, ix->s_dev, ix->Qhi, ix->Qlo, ix->q_absmax, ix->q_scale, ix->D_dev, ix->I_dev,
+                  ix->q_dev, ix->p_dev, ix->s_dev, ix->Qhi, ix->Qlo, ix->q_absmax, ix->q_scale, ix->margin_buf, ix->D_dev, ix->I_dev,
                   ix->flags_dev, ix->w_dev, ix->mode_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -392,11 +443,17 @@ int cmx_index_add(cmx_index* ix, const float* x, int64_t n, int x_on_device) {
   float* dst = ix->X + ix->n * ix->d;
   CMX_CUDA(cudaMemcpy(dst, x, (size_t)n * ix->d * sizeof(float), x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
   // track max |x| (finite) for the fp16 operand scale of the tensor path
-  CMX_CUDA(cudaMemset(ix->absmax_dev, 0, sizeof(uint32_t)));
+  CMX_CUDA(cudaMemset(ix->absmax_dev, 0, 2 * sizeof(uint32_t)));
   CMX_TRY(launch_absmax(dst, n * (int64_t)ix->d, ix->absmax_dev, 0));
-  uint32_t bits = 0;
-  CMX_CUDA(cudaMemcpy(&bits, ix->absmax_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-  ix->absmax_bits = std::max(ix->absmax_bits, bits);
+  CMX_TRY(launch_row_norm_max(dst, n, ix->d, ix->absmax_dev + 1, 0));
+  uint32_t bits[2] = {0, 0};
+  CMX_CUDA(cudaMemcpy(bits, ix->absmax_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  ix->absmax_bits = std::max(ix->absmax_bits, bits[0]);
+  {
+    float nrm;
+    memcpy(&nrm, &bits[1], sizeof(float));
+    ix->row_norm_max = std::max(ix->row_norm_max, nrm);
+  }
   ix->n += n;
   return CMX_OK;
 }
@@ -405,7 +462,9 @@ int cmx_index_reset(cmx_index* ix) {
   CMX_CHECK(ix != nullptr, "null index");
   ix->n = 0;
   ix->plane_rows = 0;
+  ix->lo_rows = 0;
   ix->absmax_bits = 0;
+  ix->row_norm_max = 0.f;
   return CMX_OK;
 }
 
@@ -445,6 +504,19 @@ int cmx_index_set_cand_capacity(cmx_index* ix, int cap) {
   CMX_CHECK(ix != nullptr, "null index");
   CMX_CHECK(cap >= 0 && cap <= 16384, "candidate capacity %d out of range [0, 16384]", cap);
   ix->cand_cap_override = cap;
+  return CMX_OK;
+}
+
+int cmx_set_default_precision(int mode) {
+  CMX_CHECK(mode == CMX_PRECISION_SPLIT || mode == CMX_PRECISION_RESCORE, "bad precision mode %d", mode);
+  g_default_precision = mode;
+  return CMX_OK;
+}
+
+int cmx_index_set_precision(cmx_index* ix, int mode) {
+  CMX_CHECK(ix != nullptr, "null index");
+  CMX_CHECK(mode == CMX_PRECISION_SPLIT || mode == CMX_PRECISION_RESCORE, "bad precision mode %d", mode);
+  ix->precision = mode;
   return CMX_OK;
 }
 

@@ -84,6 +84,8 @@ struct SearchWs {
   uint32_t* cnt = nullptr;     // [nq_pad] candidates appended per query (may exceed cap)
   uint64_t* cand = nullptr;    // [nq_pad, cap] candidate keys
   uint32_t* overflow = nullptr;// [1] set when some query's buffer overflowed
+  float* margin = nullptr;     // [nq_pad] rescore mode: 2*eps(q), the slack kept below the k-th best
+                               // APPROXIMATE score so that the exact top-k is provably contained; else 0
   int cap = 0;
   int64_t nq_cap = 0;
 };
@@ -100,6 +102,10 @@ int launch_split_planes(const float* x, int64_t rows, int d, int d_pad, const fl
 // scale_out[0] = 2^e with absmax*2^e in [2^12,2^13); scale_out[1] = 1/scale
 int launch_scale_from_absmax(const uint32_t* absmax_bits, float* scale_out, cudaStream_t st);
 float host_scale_for_absmax_bits(uint32_t bits);
+// max over rows of ||x||_2 (finite rows only), as float bits via atomicMax
+int launch_row_norm_max(const float* x, int64_t rows, int d, uint32_t* max_bits, cudaStream_t st);
+// margin[q] = coef * ||Q[q]||_2   (coef = 2 * c_d * max corpus row norm)
+int launch_query_margin(const float* Q, int64_t nq, int d, float coef, float* margin, cudaStream_t st);
 
 int launch_stream_score(const float* X, int64_t row0, int64_t nrows, int d, const float* Q,
                         int nq, const SearchWs& ws, int64_t q0, int dense, int64_t dense_row0,
@@ -111,10 +117,12 @@ void set_tensor_tile(int bn);  // 256 (default) or 128 corpus rows per tile
 void set_tensor_flags(int f);  // tuning experiments (cache hints)
 void set_tensor_small(int on);  // corpus-as-M kernel for nq <= 64
 void set_tensor_pair(int on);  // CTA-pair (cta_group::2) scorer for nq > 128
+// passes = 3: split precision (hi*hi + hi*lo + lo*hi, fp32-faithful scores);
+// passes = 1: hi*hi only (approximate filter scores; Blo/Qlo may be NULL) for the rescore mode
 int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
                         int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,
                         int64_t nq, int64_t nq_pad, const float* q_inv_scale_dev, float b_inv_scale,
-                        const SearchWs& ws, int dense, int64_t dense_row0, cudaStream_t st,
+                        const SearchWs& ws, int dense, int64_t dense_row0, int passes, cudaStream_t st,
                         int sm_count);
 
 int launch_ws_init(const SearchWs& ws, int64_t nq, int64_t nq_pad, cudaStream_t st);
@@ -122,6 +130,10 @@ int launch_set_counts(const SearchWs& ws, int64_t nq, uint32_t value, cudaStream
 // sort candidates, keep top-k, refresh tau; final=1 also writes D/I (+id_base, padded)
 int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float* D, int64_t* I,
                    int64_t id_base, cudaStream_t st);
+// rescore mode: exact fp32 scores of every surviving candidate from the fp32 row store, then
+// the exact top-k (score desc, row asc) -> D, I
+int launch_rescore(const float* X, int d, const float* Q, const SearchWs& ws, int64_t nq, int k, float* D,
+                   int64_t* I, int64_t id_base, cudaStream_t st);
 int launch_merge(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,
                  float* D, int64_t* I, cudaStream_t st);
 

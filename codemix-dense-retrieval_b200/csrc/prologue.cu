@@ -167,6 +167,54 @@ int launch_scale_from_absmax(const uint32_t* absmax_bits, float* scale_out, cuda
 
 float host_scale_for_absmax_bits(uint32_t bits) { return scale_for_absmax_bits(bits); }
 
+// ---- row norms (rescore mode error bound) ----------------------------------------
+// one warp per row; rows with a non-finite norm are ignored
+__global__ void __launch_bounds__(256)
+row_norm_max_kernel(const float* __restrict__ x, int64_t rows, int d, uint32_t* __restrict__ max_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float best = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    const float* row = x + r * d;
+    float ss = 0.f;
+    for (int i = lane; i < d; i += 32) { const float v = row[i]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    if (is_finite_f(nrm)) best = fmaxf(best, nrm);
+  }
+  if (lane == 0 && best > 0.f) atomicMax(max_bits, __float_as_uint(best));
+}
+
+int launch_row_norm_max(const float* x, int64_t rows, int d, uint32_t* max_bits, cudaStream_t st) {
+  if (rows == 0) return CMX_OK;
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  row_norm_max_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, rows, d, max_bits);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+__global__ void __launch_bounds__(256)
+query_margin_kernel(const float* __restrict__ Q, int64_t nq, int d, float coef, float* __restrict__ margin) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const float* row = Q + q * d;
+  float ss = 0.f;
+  for (int i = lane; i < d; i += 32) { const float v = row[i]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  // a non-finite query norm gives a non-finite margin: every score passes the filter, the
+  // buffers overflow and the search falls back to the split-precision path
+  if (lane == 0) margin[q] = coef * sqrtf(ss) * 1.0001f;
+}
+
+int launch_query_margin(const float* Q, int64_t nq, int d, float coef, float* margin, cudaStream_t st) {
+  if (nq == 0) return CMX_OK;
+  query_margin_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(Q, nq, d, coef, margin);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
 // ---- fp32 -> fp16 hi/lo planes --------------------------------------------------
 // x*scale = hi + lo + O(2^-22 |x*scale|) with hi, lo fp16; scale is a power of two.
 __global__ void __launch_bounds__(256)
@@ -205,7 +253,7 @@ split_planes_kernel(const float* __restrict__ x, int64_t rows, int d, int d_pad,
       l[j] = __float2half_rn(res);
     }
     *reinterpret_cast<uint4*>(hi + r * d_pad + c0) = *reinterpret_cast<uint4*>(h);
-    *reinterpret_cast<uint4*>(lo + r * d_pad + c0) = *reinterpret_cast<uint4*>(l);
+    if (lo != nullptr) *reinterpret_cast<uint4*>(lo + r * d_pad + c0) = *reinterpret_cast<uint4*>(l);
   }
 }
 

@@ -162,8 +162,9 @@ __device__ uint64_t block_kth_largest(const uint64_t* keys, int n, int k, Select
 }
 
 // Appends the survivors to dst (smem or global), order arbitrary, and returns how many:
-// the keys >= kth (exactly k of them, real keys are distinct), or -- when the k-th largest
-// is the null key, i.e. fewer than k real candidates exist -- all non-null keys.
+// the keys >= kth (exactly k of them when kth is the k-th largest: real keys are distinct;
+// more when kth is a lowered cut-off), or -- when kth is the null key, i.e. fewer than k
+// real candidates exist -- all non-null keys.
 __device__ int block_partition(const uint64_t* keys, int n, uint64_t kth, uint64_t* dst, SelectShared& sh) {
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) sh.count = 0;
@@ -189,7 +190,7 @@ __device__ int block_partition(const uint64_t* keys, int n, uint64_t kth, uint64
 // dynamic smem: cap keys, then next_pow2(k) keys for the final sort
 __global__ void __launch_bounds__(kSelThreads)
 compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* __restrict__ tau,
-               uint32_t* __restrict__ overflow, int cap, int k, int final_pass,
+               uint32_t* __restrict__ overflow, const float* __restrict__ margin, int cap, int k, int final_pass,
                float* __restrict__ D, int64_t* __restrict__ I, int64_t id_base) {
   extern __shared__ __align__(16) uint64_t keys[];
   __shared__ SelectShared sh;
@@ -205,10 +206,20 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
   int kk = n;
   if (n > k) {
     const uint64_t kth = block_kth_largest(keys, n, k, sh);
-    kk = block_partition(keys, n, kth, final_pass ? top : buf, sh);
+    // rescore mode: scores are approximate (|approx - exact| <= margin/2), so everything within
+    // `margin` below the k-th best approximate score is kept -- that provably contains the exact
+    // top-k -- and the filter threshold is lowered by the same amount
+    const float m = margin ? margin[q] : 0.f;
+    uint64_t thr = kth;
+    float new_tau = key_score(kth);
+    if (m > 0.f && kth != 0ull) {
+      new_tau = key_score(kth) - m;
+      thr = make_key(new_tau, 0xffffffffu);  // smallest key carrying that score
+    }
+    kk = block_partition(keys, n, thr, final_pass ? top : buf, sh);
     if (threadIdx.x == 0) {
       cnt[q] = (uint32_t)kk;
-      if (kth != 0ull) tau[q] = key_score(kth);
+      if (kth != 0ull) tau[q] = new_tau;
     }
   } else if (final_pass) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) top[i] = keys[i];
@@ -232,6 +243,77 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
   }
 }
 
+// Rescore mode, last step.  One CTA per query: every surviving candidate (a superset of the
+// exact top-k, selected on approximate fp16 tensor-core scores) gets its EXACT fp32 score
+// from the fp32 row store -- one warp per candidate row, 128-bit coalesced loads, fp32 FMA
+// chain + shuffle reduction, deterministic for a given (query, row) -- then the exact top-k
+// under (score desc, row asc) is selected, sorted and written to D / I.
+// dynamic smem: cap keys | next_pow2(k) keys | d floats (the query)
+__global__ void __launch_bounds__(kSelThreads)
+rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, const uint64_t* __restrict__ cand,
+               const uint32_t* __restrict__ cnt, uint32_t* __restrict__ overflow, int cap, int k, int topn,
+               float* __restrict__ D, int64_t* __restrict__ I, int64_t id_base) {
+  extern __shared__ __align__(16) uint64_t keys[];
+  __shared__ SelectShared sh;
+  uint64_t* top = keys + cap;
+  float* qv = reinterpret_cast<float*>(top + topn);
+  const int64_t q = blockIdx.x;
+  const uint32_t n_raw = cnt[q];
+  if (n_raw > (uint32_t)cap && threadIdx.x == 0) atomicExch(overflow, 1u);
+  const int n = (int)min(n_raw, (uint32_t)cap);
+  for (int i = threadIdx.x; i < d; i += blockDim.x) qv[i] = Q[q * (int64_t)d + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint64_t* buf = cand + q * (int64_t)cap;
+  const bool vec = (d & 3) == 0;
+  for (int i = warp; i < n; i += nwarps) {
+    const uint64_t key = buf[i];
+    uint64_t out = 0ull;
+    if (key != 0ull) {
+      const uint32_t row = key_row(key);
+      const float* x = X + (int64_t)row * d;
+      float acc = 0.f;
+      if (vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const float4* q4 = reinterpret_cast<const float4*>(qv);
+        for (int j = lane; j < (d >> 2); j += 32) {
+          const float4 a = x4[j], b = q4[j];
+          acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+        }
+      } else {
+        for (int j = lane; j < d; j += 32) acc = fmaf(x[j], qv[j], acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (acc > CMX_NEG_PAD) out = make_key(acc, row);
+    }
+    if (lane == 0) keys[i] = out;
+  }
+  __syncthreads();
+  int kk = n;
+  if (n > k) {
+    const uint64_t kth = block_kth_largest(keys, n, k, sh);
+    kk = block_partition(keys, n, kth, top, sh);
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) top[i] = keys[i];
+    __syncthreads();
+  }
+  const int P = next_pow2(max(kk, 2));
+  for (int i = kk + threadIdx.x; i < P; i += blockDim.x) top[i] = 0ull;
+  __syncthreads();
+  bitonic_sort_desc(top, P);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    float s = CMX_NEG_PAD;
+    int64_t id = -1;
+    if (i < kk && top[i] != 0ull) {
+      s = key_score(top[i]);
+      id = id_base + (int64_t)key_row(top[i]);
+    }
+    D[q * k + i] = s;
+    I[q * k + i] = id;
+  }
+}
+
 static int pow2_at_least(int n) {
   int p = 2;
   while (p < n) p <<= 1;
@@ -243,8 +325,21 @@ int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float*
   if (nq == 0) return CMX_OK;
   const size_t smem = ((size_t)ws.cap + pow2_at_least(k)) * sizeof(uint64_t);
   CMX_CUDA(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  compact_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(ws.cand, ws.cnt, ws.tau, ws.overflow, ws.cap, k,
+  compact_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(ws.cand, ws.cnt, ws.tau, ws.overflow, ws.margin, ws.cap, k,
                                                           final_pass, D, I, id_base);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+int launch_rescore(const float* X, int d, const float* Q, const SearchWs& ws, int64_t nq, int k, float* D,
+                   int64_t* I, int64_t id_base, cudaStream_t st) {
+  if (nq == 0) return CMX_OK;
+  const int topn = pow2_at_least(k);
+  const size_t smem = ((size_t)ws.cap + topn) * sizeof(uint64_t) + (size_t)d * sizeof(float);
+  CMX_CHECK(smem <= 220 * 1024, "rescore: d=%d too large for the shared-memory query copy", d);
+  CMX_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rescore_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(X, d, Q, ws.cand, ws.cnt, ws.overflow, ws.cap, k, topn, D, I,
+                                                          id_base);
   CMX_LAUNCHED();
   return CMX_OK;
 }

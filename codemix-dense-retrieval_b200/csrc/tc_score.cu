@@ -233,13 +233,19 @@ __device__ __forceinline__ void epilogue_filter_tile(const TcParams& p, uint32_t
   }
 }
 
-template <int BN, int STAGES>
+// PASSES = 3: split precision (Qlo*Bhi + Qhi*Blo + Qhi*Bhi); PASSES = 1: Qhi*Bhi only
+// (approximate filter scores of the rescore mode; the lo tiles are neither staged nor read)
+template <int BN, int STAGES, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant__ CUtensorMap tmQlo,
                 const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
                 const TcParams p) {
+  constexpr bool SPLIT = PASSES == 3;
   constexpr int B_BYTES = BN * TC_BK * 2;
-  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  constexpr int OFF_QLO = TC_A_BYTES;                       // split only
+  constexpr int OFF_BHI = SPLIT ? 2 * TC_A_BYTES : TC_A_BYTES;
+  constexpr int OFF_BLO = OFF_BHI + B_BYTES;                // split only
+  constexpr int STAGE_BYTES = SPLIT ? 2 * TC_A_BYTES + 2 * B_BYTES : TC_A_BYTES + B_BYTES;
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
 
@@ -292,9 +298,11 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           tma_load_2d_hint(sbase, &tmQhi, full_bar(stage), kb * TC_BK, qrow, pol_q);
-          tma_load_2d_hint(sbase + TC_A_BYTES, &tmQlo, full_bar(stage), kb * TC_BK, qrow, pol_q);
-          tma_load_2d_hint(sbase + 2 * TC_A_BYTES, &tmBhi, full_bar(stage), kb * TC_BK, brow, pol_b);
-          tma_load_2d_hint(sbase + 2 * TC_A_BYTES + B_BYTES, &tmBlo, full_bar(stage), kb * TC_BK, brow, pol_b);
+          tma_load_2d_hint(sbase + OFF_BHI, &tmBhi, full_bar(stage), kb * TC_BK, brow, pol_b);
+          if (SPLIT) {
+            tma_load_2d_hint(sbase + OFF_QLO, &tmQlo, full_bar(stage), kb * TC_BK, qrow, pol_q);
+            tma_load_2d_hint(sbase + OFF_BLO, &tmBlo, full_bar(stage), kb * TC_BK, brow, pol_b);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -315,15 +323,20 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
           tc_fence_after();
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           const uint64_t qhi = make_smem_desc(sbase);
-          const uint64_t qlo = make_smem_desc(sbase + TC_A_BYTES);
-          const uint64_t bhi = make_smem_desc(sbase + 2 * TC_A_BYTES);
-          const uint64_t blo = make_smem_desc(sbase + 2 * TC_A_BYTES + B_BYTES);
+          const uint64_t qlo = make_smem_desc(sbase + OFF_QLO);
+          const uint64_t bhi = make_smem_desc(sbase + OFF_BHI);
+          const uint64_t blo = make_smem_desc(sbase + OFF_BLO);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t koff = (uint64_t)((k * 32) >> 4);  // 16 fp16 = 32 bytes per k-step
-            tc_mma_f16(d_tmem, qlo + koff, bhi + koff, IDESC, (kb | k) != 0 ? 1u : 0u);
-            tc_mma_f16(d_tmem, qhi + koff, blo + koff, IDESC, 1u);
-            tc_mma_f16(d_tmem, qhi + koff, bhi + koff, IDESC, 1u);
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            if (SPLIT) {
+              tc_mma_f16(d_tmem, qlo + koff, bhi + koff, IDESC, first);
+              tc_mma_f16(d_tmem, qhi + koff, blo + koff, IDESC, 1u);
+              tc_mma_f16(d_tmem, qhi + koff, bhi + koff, IDESC, 1u);
+            } else {
+              tc_mma_f16(d_tmem, qhi + koff, bhi + koff, IDESC, first);
+            }
           }
           tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -420,14 +433,16 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc,
       : "memory");
 }
 
-template <int STAGES>
+template <int STAGES, int PASSES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant__ CUtensorMap tmQlo,
                      const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
                      const TcParams p) {
   constexpr int BN = 256;                        // corpus rows per pair tile (TMEM columns)
+  constexpr bool SPLIT = PASSES == 3;
   constexpr int HALF_BYTES = 128 * TC_BK * 2;    // 16 KB: 128 rows x 64 fp16
-  constexpr int STAGE_BYTES = 4 * HALF_BYTES;    // Qhi, Qlo, Bhi-half, Blo-half
+  constexpr int OFF_QLO = HALF_BYTES, OFF_BHI = SPLIT ? 2 * HALF_BYTES : HALF_BYTES, OFF_BLO = 3 * HALF_BYTES;
+  constexpr int STAGE_BYTES = (SPLIT ? 4 : 2) * HALF_BYTES;    // Qhi, [Qlo,] Bhi-half[, Blo-half]
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
@@ -484,9 +499,11 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
           // the leader's barrier collects the bytes of both CTAs
           if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
           tma_load_2d_pair(sbase, &tmQhi, full_bar(stage), kb * TC_BK, qrow, pol_q);
-          tma_load_2d_pair(sbase + HALF_BYTES, &tmQlo, full_bar(stage), kb * TC_BK, qrow, pol_q);
-          tma_load_2d_pair(sbase + 2 * HALF_BYTES, &tmBhi, full_bar(stage), kb * TC_BK, brow, pol_b);
-          tma_load_2d_pair(sbase + 3 * HALF_BYTES, &tmBlo, full_bar(stage), kb * TC_BK, brow, pol_b);
+          tma_load_2d_pair(sbase + OFF_BHI, &tmBhi, full_bar(stage), kb * TC_BK, brow, pol_b);
+          if (SPLIT) {
+            tma_load_2d_pair(sbase + OFF_QLO, &tmQlo, full_bar(stage), kb * TC_BK, qrow, pol_q);
+            tma_load_2d_pair(sbase + OFF_BLO, &tmBlo, full_bar(stage), kb * TC_BK, brow, pol_b);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -507,15 +524,20 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
           tc_fence_after();
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           const uint64_t qhi = make_smem_desc(sbase);
-          const uint64_t qlo = make_smem_desc(sbase + HALF_BYTES);
-          const uint64_t bhi = make_smem_desc(sbase + 2 * HALF_BYTES);
-          const uint64_t blo = make_smem_desc(sbase + 3 * HALF_BYTES);
+          const uint64_t qlo = make_smem_desc(sbase + OFF_QLO);
+          const uint64_t bhi = make_smem_desc(sbase + OFF_BHI);
+          const uint64_t blo = make_smem_desc(sbase + OFF_BLO);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t koff = (uint64_t)((k * 32) >> 4);
-            tc_mma_f16_pair(d_tmem, qlo + koff, bhi + koff, IDESC, (kb | k) != 0 ? 1u : 0u);
-            tc_mma_f16_pair(d_tmem, qhi + koff, blo + koff, IDESC, 1u);
-            tc_mma_f16_pair(d_tmem, qhi + koff, bhi + koff, IDESC, 1u);
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            if (SPLIT) {
+              tc_mma_f16_pair(d_tmem, qlo + koff, bhi + koff, IDESC, first);
+              tc_mma_f16_pair(d_tmem, qhi + koff, blo + koff, IDESC, 1u);
+              tc_mma_f16_pair(d_tmem, qhi + koff, bhi + koff, IDESC, 1u);
+            } else {
+              tc_mma_f16_pair(d_tmem, qhi + koff, bhi + koff, IDESC, first);
+            }
           }
           tc_commit_pair(empty_bar(stage));  // frees this stage in BOTH CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -583,14 +605,16 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
-template <int NQ, int STAGES>
+template <int NQ, int STAGES, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant__ CUtensorMap tmQlo,
                       const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
                       const TcParams p) {
+  constexpr bool SPLIT = PASSES == 3;
   constexpr int A_BYTES = 128 * TC_BK * 2;  // corpus tile, one plane
   constexpr int Q_BYTES = NQ * TC_BK * 2;   // query tile, one plane
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * Q_BYTES;
+  constexpr int OFF_BLO = A_BYTES, OFF_QHI = SPLIT ? 2 * A_BYTES : A_BYTES, OFF_QLO = OFF_QHI + Q_BYTES;
+  constexpr int STAGE_BYTES = SPLIT ? 2 * A_BYTES + 2 * Q_BYTES : A_BYTES + Q_BYTES;
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   constexpr uint32_t TMEM_COLS = (2 * NQ < 32) ? 32u : (uint32_t)(2 * NQ);
   constexpr int CW = (NQ < 32) ? NQ : 32;  // columns per TMEM load
@@ -644,9 +668,11 @@ tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_co
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           tma_load_2d_hint(sbase, &tmBhi, full_bar(stage), kb * TC_BK, brow, kL2EvictFirst);
-          tma_load_2d_hint(sbase + A_BYTES, &tmBlo, full_bar(stage), kb * TC_BK, brow, kL2EvictFirst);
-          tma_load_2d_hint(sbase + 2 * A_BYTES, &tmQhi, full_bar(stage), kb * TC_BK, 0, kL2EvictLast);
-          tma_load_2d_hint(sbase + 2 * A_BYTES + Q_BYTES, &tmQlo, full_bar(stage), kb * TC_BK, 0, kL2EvictLast);
+          tma_load_2d_hint(sbase + OFF_QHI, &tmQhi, full_bar(stage), kb * TC_BK, 0, kL2EvictLast);
+          if (SPLIT) {
+            tma_load_2d_hint(sbase + OFF_BLO, &tmBlo, full_bar(stage), kb * TC_BK, brow, kL2EvictFirst);
+            tma_load_2d_hint(sbase + OFF_QLO, &tmQlo, full_bar(stage), kb * TC_BK, 0, kL2EvictLast);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -667,15 +693,20 @@ tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_co
           tc_fence_after();
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           const uint64_t bhi = make_smem_desc(sbase);
-          const uint64_t blo = make_smem_desc(sbase + A_BYTES);
-          const uint64_t qhi = make_smem_desc(sbase + 2 * A_BYTES);
-          const uint64_t qlo = make_smem_desc(sbase + 2 * A_BYTES + Q_BYTES);
+          const uint64_t blo = make_smem_desc(sbase + OFF_BLO);
+          const uint64_t qhi = make_smem_desc(sbase + OFF_QHI);
+          const uint64_t qlo = make_smem_desc(sbase + OFF_QLO);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t koff = (uint64_t)((k * 32) >> 4);
-            tc_mma_f16(d_tmem, bhi + koff, qlo + koff, IDESC, (kb | k) != 0 ? 1u : 0u);
-            tc_mma_f16(d_tmem, blo + koff, qhi + koff, IDESC, 1u);
-            tc_mma_f16(d_tmem, bhi + koff, qhi + koff, IDESC, 1u);
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            if (SPLIT) {
+              tc_mma_f16(d_tmem, bhi + koff, qlo + koff, IDESC, first);
+              tc_mma_f16(d_tmem, blo + koff, qhi + koff, IDESC, 1u);
+              tc_mma_f16(d_tmem, bhi + koff, qhi + koff, IDESC, 1u);
+            } else {
+              tc_mma_f16(d_tmem, bhi + koff, qhi + koff, IDESC, first);
+            }
           }
           tc_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -787,48 +818,57 @@ void set_tensor_pair(int on) { g_tc_pair = (on < 0) ? kTcPairDefault : (on ? 1 :
 void set_tensor_tile(int bn) { g_tc_bn = (bn == 128) ? 128 : 256; }
 void set_tensor_flags(int f) { g_tc_flags = f; }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int PASSES>
 static int launch_tc(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const CUtensorMap& tb_hi,
                      const CUtensorMap& tb_lo, const TcParams& p, cudaStream_t st, int sm_count) {
-  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TC_A_BYTES + BN * TC_BK * 2);
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
-  CMX_CUDA(cudaFuncSetAttribute(tc_score_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static_assert((size_t)STAGES * STAGE_BYTES + 1024 + 256 <= 227 * 1024, "stage ring exceeds shared memory");
+  CMX_CUDA(cudaFuncSetAttribute(tc_score_kernel<BN, STAGES, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = p.ntiles < sm_count ? p.ntiles : sm_count;
   if (grid < 1) return CMX_OK;
-  tc_score_kernel<BN, STAGES><<<(unsigned)grid, TC_THREADS, smem, st>>>(tq_hi, tq_lo, tb_hi, tb_lo, p);
+  tc_score_kernel<BN, STAGES, PASSES><<<(unsigned)grid, TC_THREADS, smem, st>>>(tq_hi, tq_lo, tb_hi, tb_lo, p);
   CMX_LAUNCHED();
   return CMX_OK;
 }
 
+template <int STAGES, int PASSES>
 static int launch_tc_pair(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const CUtensorMap& tb_hi,
                           const CUtensorMap& tb_lo, const TcParams& p, cudaStream_t st, int sm_count) {
-  constexpr int STAGES = 3;
-  const size_t smem = (size_t)STAGES * 4 * (128 * TC_BK * 2) + 1024 + 256;
-  CMX_CUDA(cudaFuncSetAttribute(tc_score_pair_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  constexpr int STAGE_BYTES = (PASSES == 3 ? 4 : 2) * (128 * TC_BK * 2);
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert((size_t)STAGES * STAGE_BYTES + 1024 + 256 <= 227 * 1024, "stage ring exceeds shared memory");
+  CMX_CUDA(cudaFuncSetAttribute(tc_score_pair_kernel<STAGES, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t clusters = sm_count / 2;
   if (p.ntiles < clusters) clusters = p.ntiles;
   if (clusters < 1) return CMX_OK;
-  tc_score_pair_kernel<STAGES><<<(unsigned)(2 * clusters), TC_THREADS, smem, st>>>(tq_hi, tq_lo, tb_hi, tb_lo, p);
+  tc_score_pair_kernel<STAGES, PASSES><<<(unsigned)(2 * clusters), TC_THREADS, smem, st>>>(tq_hi, tq_lo, tb_hi, tb_lo, p);
   CMX_LAUNCHED();
   return CMX_OK;
 }
 
-template <int NQ, int STAGES>
+template <int NQ, int STAGES, int PASSES>
 static int launch_tc_small(const __half* Bhi, const __half* Blo, int64_t plane_rows, const __half* Qhi, const __half* Qlo,
                            int64_t nq_pad, int d_pad, TcParams p, cudaStream_t st, int sm_count) {
   CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;
   CMX_TRY(make_plane_map(&tq_hi, Qhi, nq_pad, d_pad, NQ));
-  CMX_TRY(make_plane_map(&tq_lo, Qlo, nq_pad, d_pad, NQ));
   CMX_TRY(make_plane_map(&tb_hi, Bhi, plane_rows, d_pad, 128));
-  CMX_TRY(make_plane_map(&tb_lo, Blo, plane_rows, d_pad, 128));
-  constexpr int STAGE_BYTES = 2 * (128 * TC_BK * 2) + 2 * (NQ * TC_BK * 2);
+  if (PASSES == 3) {
+    CMX_TRY(make_plane_map(&tq_lo, Qlo, nq_pad, d_pad, NQ));
+    CMX_TRY(make_plane_map(&tb_lo, Blo, plane_rows, d_pad, 128));
+  } else {
+    tq_lo = tq_hi;
+    tb_lo = tb_hi;
+  }
+  constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * ((128 * TC_BK * 2) + (NQ * TC_BK * 2));
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + NQ * sizeof(float);
-  CMX_CUDA(cudaFuncSetAttribute(tc_score_small_kernel<NQ, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static_assert((size_t)STAGES * STAGE_BYTES + 1024 + 256 + NQ * sizeof(float) <= 227 * 1024, "stage ring exceeds shared memory");
+  CMX_CUDA(cudaFuncSetAttribute(tc_score_small_kernel<NQ, STAGES, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.mtiles = 1;
   p.ntiles = (p.nrows + 127) / 128;
   int64_t grid = p.ntiles < sm_count ? p.ntiles : sm_count;
   if (grid < 1) return CMX_OK;
-  tc_score_small_kernel<NQ, STAGES><<<(unsigned)grid, TC_THREADS, smem, st>>>(tq_hi, tq_lo, tb_hi, tb_lo, p);
+  tc_score_small_kernel<NQ, STAGES, PASSES><<<(unsigned)grid, TC_THREADS, smem, st>>>(tq_hi, tq_lo, tb_hi, tb_lo, p);
   CMX_LAUNCHED();
   return CMX_OK;
 }
@@ -839,34 +879,17 @@ void set_tensor_small(int on) { g_tc_small = on ? 1 : 0; }
 int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
                         int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,
                         int64_t nq, int64_t nq_pad, const float* q_inv_scale_dev, float b_inv_scale,
-                        const SearchWs& ws, int dense, int64_t dense_row0, cudaStream_t st,
+                        const SearchWs& ws, int dense, int64_t dense_row0, int passes, cudaStream_t st,
                         int sm_count) {
   if (nrows <= 0 || nq <= 0) return CMX_OK;
+  CMX_CHECK(passes == 1 || passes == 3, "tensor path: passes must be 1 or 3");
   CMX_CHECK(d_pad % TC_BK == 0, "tensor path: padded dim must be a multiple of %d", TC_BK);
   CMX_CHECK(plane_rows < (int64_t)0x7fffffff, "tensor path: more than 2^31 rows per shard");
-  if (g_tc_small && nq <= 64) {
-    TcParams p;
-    p.row0 = row0; p.nrows = nrows; p.kblocks = d_pad / TC_BK; p.nq = nq;
-    p.q_inv_scale = q_inv_scale_dev; p.b_inv_scale = b_inv_scale;
-    p.tau = ws.tau; p.cnt = ws.cnt; p.cand = ws.cand; p.cap = ws.cap;
-    p.dense = dense; p.dense_row0 = dense_row0; p.flags = g_tc_flags; p.mtiles = 1; p.ntiles = 0;
-    if (nq <= 16) return launch_tc_small<16, 5>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
-    if (nq <= 32) return launch_tc_small<32, 4>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
-    return launch_tc_small<64, 4>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
-  }
-  const bool pair = g_tc_pair && nq > 128;
-  const int bn = pair ? 128 : g_tc_bn;  // pair: each CTA loads a 128-row half of the 256-row tile
-  CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;
-  CMX_TRY(make_plane_map(&tq_hi, Qhi, nq_pad, d_pad, TC_BM));
-  CMX_TRY(make_plane_map(&tq_lo, Qlo, nq_pad, d_pad, TC_BM));
-  CMX_TRY(make_plane_map(&tb_hi, Bhi, plane_rows, d_pad, bn));
-  CMX_TRY(make_plane_map(&tb_lo, Blo, plane_rows, d_pad, bn));
+  const bool split = passes == 3;
   TcParams p;
   p.row0 = row0;
   p.nrows = nrows;
   p.kblocks = d_pad / TC_BK;
-  p.mtiles = pair ? (int)((nq + 255) / 256) : (int)((nq + TC_BM - 1) / TC_BM);
-  p.ntiles = pair ? (int64_t)p.mtiles * ((nrows + 255) / 256) : (int64_t)p.mtiles * ((nrows + bn - 1) / bn);
   p.nq = nq;
   p.q_inv_scale = q_inv_scale_dev;
   p.b_inv_scale = b_inv_scale;
@@ -877,9 +900,42 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   p.dense = dense;
   p.dense_row0 = dense_row0;
   p.flags = g_tc_flags;
-  if (pair) return launch_tc_pair(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
-  if (bn == 256) return launch_tc<256, 2>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
-  return launch_tc<128, 3>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
+  p.mtiles = 1;
+  p.ntiles = 0;
+  if (g_tc_small && nq <= 64) {
+    if (split) {
+      if (nq <= 16) return launch_tc_small<16, 5, 3>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
+      if (nq <= 32) return launch_tc_small<32, 4, 3>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
+      return launch_tc_small<64, 4, 3>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
+    }
+    if (nq <= 16) return launch_tc_small<16, 8, 1>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
+    if (nq <= 32) return launch_tc_small<32, 8, 1>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
+    return launch_tc_small<64, 8, 1>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
+  }
+  const bool pair = g_tc_pair && nq > 128;
+  const int bn = pair ? 128 : g_tc_bn;  // pair: each CTA loads a 128-row half of the 256-row tile
+  CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;
+  CMX_TRY(make_plane_map(&tq_hi, Qhi, nq_pad, d_pad, TC_BM));
+  CMX_TRY(make_plane_map(&tb_hi, Bhi, plane_rows, d_pad, bn));
+  if (split) {
+    CMX_TRY(make_plane_map(&tq_lo, Qlo, nq_pad, d_pad, TC_BM));
+    CMX_TRY(make_plane_map(&tb_lo, Blo, plane_rows, d_pad, bn));
+  } else {
+    tq_lo = tq_hi;
+    tb_lo = tb_hi;
+  }
+  p.mtiles = pair ? (int)((nq + 255) / 256) : (int)((nq + TC_BM - 1) / TC_BM);
+  p.ntiles = pair ? (int64_t)p.mtiles * ((nrows + 255) / 256) : (int64_t)p.mtiles * ((nrows + bn - 1) / bn);
+  if (pair) {
+    if (split) return launch_tc_pair<3, 3>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
+    return launch_tc_pair<6, 1>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
+  }
+  if (split) {
+    if (bn == 256) return launch_tc<256, 2, 3>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
+    return launch_tc<128, 3, 3>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
+  }
+  if (bn == 256) return launch_tc<256, 4, 1>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
+  return launch_tc<128, 6, 1>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
 }
 
 }  // namespace cmx

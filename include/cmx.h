@@ -51,6 +51,14 @@ typedef struct cmx_index cmx_index;
 #define CMX_PATH_STREAM 1   /* CUDA-core fp32 streaming scorer (HBM-bound)  */
 #define CMX_PATH_TENSOR 2   /* tcgen05 fp16-split (hi/lo) tensor-core scorer */
 
+/* arithmetic of the tensor path (the stream path is always exact fp32) */
+#define CMX_PRECISION_SPLIT 0   /* three fp16 MMA passes (hi*hi + hi*lo + lo*hi), fp32 accumulate:
+                                   fp32-faithful scores straight out of the tensor core            */
+#define CMX_PRECISION_RESCORE 1 /* default: ONE fp16 MMA pass selects a provably sufficient superset
+                                   (everything within 2*eps(q) of the k-th best approximate score,
+                                   eps from the fp16 rounding bound), then the survivors are scored
+                                   EXACTLY in fp32 from the row store and the exact top-k is taken  */
+
 /* FAISS-GPU's own cap on k is 2048; kept here. */
 #define CMX_MAX_K 2048
 
@@ -163,7 +171,8 @@ typedef struct cmx_search_stats {
   int32_t path;            /* CMX_PATH_STREAM / CMX_PATH_TENSOR actually used       */
   int32_t slabs;           /* corpus slabs (score launches) of the last search      */
   int32_t reruns;          /* 1 if the candidate buffers overflowed and the search
-                              was repeated with worst-case-safe slabs               */
+                              was repeated with worst-case-safe slabs; 2 if the
+                              rescore mode additionally fell back to split precision */
   int32_t launches;        /* kernels launched by the last search                   */
   int64_t nq, ntotal;      /* shape of the last search                              */
   float score_ms;          /* CUDA-event time inside the scoring kernels (0 unless
@@ -176,6 +185,10 @@ typedef struct cmx_search_stats {
 CMX_API int cmx_index_last_stats(const cmx_index* ix, cmx_search_stats* out);
 /* 1: bracket kernel groups with CUDA events on the launching stream. */
 CMX_API int cmx_set_profiling(int on);
+/* arithmetic of the tensor path: CMX_PRECISION_RESCORE (default) or CMX_PRECISION_SPLIT. */
+CMX_API int cmx_index_set_precision(cmx_index* ix, int mode);
+/* precision given to indexes created afterwards (process-wide default: CMX_PRECISION_RESCORE). */
+CMX_API int cmx_set_default_precision(int mode);
 /* tuning knob (tests): candidate-buffer capacity per query (0 = automatic). */
 CMX_API int cmx_index_set_cand_capacity(cmx_index* ix, int cap);
 

@@ -17,8 +17,8 @@ for N in sizes:
     while c * bench.CHUNK < N:
         x = bench.corpus_chunk(c, d, dev)
         sh.add(x[: min(bench.CHUNK, N - c * bench.CHUNK)]); del x; c += 1
-    for pair in (0, 1):
-        bn = 256
+    for prec, pair in (("split", 0), ("rescore", 0), ("rescore", 1)):
+        sh.set_precision(prec)
         _lib.check(_lib.lib().cmx_debug_set_tensor_pair(pair))
         for flags in (0,):
             _lib.check(_lib.lib().cmx_debug_set_tensor_flags(flags))
@@ -29,8 +29,8 @@ for N in sizes:
             for _ in range(reps):
                 sh.search_mixed(P, S, [0.5], 1000, path="tensor"); st = sh.last_stats()
                 sc += st["score_ms"]; se += st["select_ms"]; tot += st["total_ms"]
-            tf = 3 * 2.0 * 6980 * N * d / (sc / reps / 1e3) / 1e12
-            print(json.dumps({"N": N, "pair": pair, "flags": flags, "score_ms": round(sc / reps, 2), "select_ms": round(se / reps, 2),
+            tf = (3 if prec == "split" else 1) * 2.0 * 6980 * N * d / (sc / reps / 1e3) / 1e12
+            print(json.dumps({"N": N, "precision": prec, "pair": pair, "reruns": st["reruns"], "qps": round(6980 / (tot / reps / 1e3)), "score_ms": round(sc / reps, 2), "select_ms": round(se / reps, 2),
                               "total_ms": round(tot / reps, 2), "exec_TFLOPs": round(tf, 1)}), flush=True)
     del sh
     torch.cuda.empty_cache()

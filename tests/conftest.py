@@ -40,3 +40,13 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(params=["rescore", "split"])
+def precision(request):
+    """Run a GPU test under both tensor-path arithmetic modes."""
+    from cmx import _lib
+
+    _lib.set_default_precision(request.param)
+    yield request.param
+    _lib.set_default_precision("rescore")

@@ -119,7 +119,7 @@ def test_stream_many_queries_and_k1000():
 # ---------------------------------------------------------------- tensor path
 @pytest.mark.parametrize("d", [64, 256, 1024])
 @pytest.mark.parametrize("k", [10, 100, 1000])
-def test_tensor_search_parity(d, k):
+def test_tensor_search_parity(d, k, precision):
     rng = np.random.default_rng(200 + d + k)
     X, Q = _unit(rng, 30077, d), _unit(rng, 301, d)
     sh = _shard(X)
@@ -129,7 +129,7 @@ def test_tensor_search_parity(d, k):
     assert rep["max_rel_err"] < RTOL
 
 
-def test_tensor_anisotropic_realistic_scores():
+def test_tensor_anisotropic_realistic_scores(precision):
     rng = np.random.default_rng(12)
     X, Q = _aniso(rng, 40000, 1024), _aniso(rng, 200, 1024)
     sh = _shard(X)
@@ -157,7 +157,7 @@ def test_tensor_tile_variants(bn):
 
 @pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("shape", [(30077, 301, 256, 100), (9000, 130, 192, 50), (70001, 700, 1024, 1000), (5003, 257, 96, 20)])
-def test_tensor_single_and_pair_kernels(pair, shape):
+def test_tensor_single_and_pair_kernels(pair, shape, precision):
     """Both tensor-core kernels (one CTA per tile / CTA pair with cta_group::2) against the oracle."""
     from cmx import _lib
 
@@ -175,7 +175,7 @@ def test_tensor_single_and_pair_kernels(pair, shape):
 
 @pytest.mark.parametrize("small", [0, 1])
 @pytest.mark.parametrize("nq", [5, 16, 17, 33, 64, 100, 128])
-def test_tensor_small_batch_kernel(small, nq):
+def test_tensor_small_batch_kernel(small, nq, precision):
     """nq <= 128: the corpus-as-M tensor kernel (and, for comparison, the padded 128-row one)."""
     from cmx import _lib
 
@@ -194,7 +194,7 @@ def test_tensor_small_batch_kernel(small, nq):
 
 
 @pytest.mark.parametrize("d", [96, 100, 768])
-def test_tensor_ragged_dims(d):
+def test_tensor_ragged_dims(d, precision):
     """d not a multiple of 64 -> zero-padded operand planes; N, nq not tile multiples."""
     rng = np.random.default_rng(14 + d)
     X, Q = _unit(rng, 5003, d), _unit(rng, 129, d)
@@ -205,7 +205,7 @@ def test_tensor_ragged_dims(d):
     assert oracle.compare_topk(D2, I2, D[:5], I[:5], rtol=RTOL, atol=ATOL)["ok"]
 
 
-def test_tensor_unnormalised_wide_range():
+def test_tensor_unnormalised_wide_range(precision):
     """Raw (non unit-norm) vectors with a wide dynamic range: the power-of-two operand
     scaling keeps the split exact enough."""
     rng = np.random.default_rng(15)
@@ -219,7 +219,7 @@ def test_tensor_unnormalised_wide_range():
 
 # ---------------------------------------------------------------- edge cases
 @pytest.mark.parametrize("path", ["stream", "tensor"])
-def test_k_larger_than_ntotal_pads(path):
+def test_k_larger_than_ntotal_pads(path, precision):
     rng = np.random.default_rng(16)
     X, Q = _unit(rng, 7, 64), _unit(rng, 3, 64)
     D, I = _shard(X).search(Q, 12, path=path)
@@ -241,7 +241,7 @@ def test_empty_index_and_empty_queries():
 
 
 @pytest.mark.parametrize("path", ["stream", "tensor"])
-def test_duplicate_rows_tie_order(path):
+def test_duplicate_rows_tie_order(path, precision):
     """Exact ties come out in ascending row order (deterministic; one of FAISS' legal orders)."""
     rng = np.random.default_rng(17)
     X = _unit(rng, 3000, 64)
@@ -262,7 +262,7 @@ def test_duplicate_rows_tie_order(path):
 
 
 @pytest.mark.parametrize("path", ["stream", "tensor"])
-def test_zero_and_nan_queries(path):
+def test_zero_and_nan_queries(path, precision):
     rng = np.random.default_rng(18)
     X = _unit(rng, 900, 64)
     Q = _unit(rng, 4, 64)
@@ -276,7 +276,7 @@ def test_zero_and_nan_queries(path):
 
 
 @pytest.mark.parametrize("path", ["stream", "tensor"])
-def test_adversarial_order_triggers_safe_rerun(path):
+def test_adversarial_order_triggers_safe_rerun(path, precision):
     """Rows sorted by ascending score for one query: every row beats the stale threshold,
     the candidate buffer overflows, the search is redone with worst-case-safe slabs."""
     rng = np.random.default_rng(19)
@@ -289,11 +289,15 @@ def test_adversarial_order_triggers_safe_rerun(path):
     sh.set_cand_capacity(256)
     D, I = sh.search(Q, 100, path=path)
     st = sh.last_stats()
-    assert st["reruns"] == 1, st
+    # split / stream: the worst-case-safe slab schedule (1) is enough; rescore: the margin band of
+    # the sorted query still overflows the tiny buffer, so it ends in the split fallback (2)
+    assert st["reruns"] >= 1, st
+    if path == "stream" or precision == "split":
+        assert st["reruns"] == 1, st
     _check(D, I, X, Q, 100)
 
 
-def test_incremental_add_and_reconstruct():
+def test_incremental_add_and_reconstruct(precision):
     rng = np.random.default_rng(20)
     X, Q = _unit(rng, 5000, 128), _unit(rng, 40, 128)
     from cmx.engine import Shard
@@ -350,7 +354,7 @@ def test_search_mixed_equals_mix_then_search():
         _check(D[ai], I[ai], X, Qo[ai], 100)
 
 
-def test_merge_and_sharded_equal_single():
+def test_merge_and_sharded_equal_single(precision):
     from cmx.engine import merge_topk
     import cmx.faiss as faiss
 
@@ -460,7 +464,7 @@ def test_run_alpha_sweep_files(tmp_path):
 
 
 # ---------------------------------------------------------------- larger-size properties
-def test_large_properties_tensor_vs_stream_and_recompute():
+def test_large_properties_tensor_vs_stream_and_recompute(precision):
     """1M x 1024 on device: size-independent properties + agreement of the two paths."""
     import torch
     from cmx.engine import Shard
@@ -500,7 +504,7 @@ def test_large_properties_tensor_vs_stream_and_recompute():
 
 
 # ---------------------------------------------------------------- limits and workspace reuse
-def test_k_max_2048_and_over_limit():
+def test_k_max_2048_and_over_limit(precision):
     rng = np.random.default_rng(40)
     X, Q = _unit(rng, 50000, 64), _unit(rng, 40, 64)
     sh = _shard(X)
@@ -550,3 +554,30 @@ def test_workspace_reuse_reset_and_two_indexes():
     Q = _unit(rng, 20, 64)
     D, I = a.search(Q, 5)
     _check(D, I, Xa[:100], Q, 5)
+
+
+def test_rescore_scores_are_exact_fp32_and_near_duplicates_fall_back():
+    """rescore mode: D carries fp32 FMA scores (error ~1e-7, far inside the 1e-5 bar), and a corpus
+    with more near-duplicates than the candidate buffer holds ends in the split fallback, still exact."""
+    from cmx.engine import Shard
+
+    rng = np.random.default_rng(43)
+    X, Q = _unit(rng, 60000, 256), _unit(rng, 150, 256)
+    sh = Shard(256, 0)
+    sh.set_precision("rescore")
+    sh.add(X)
+    D, I = sh.search(Q, 100, path="tensor")
+    Dt, It = oracle.flat_ip_search_f64(X, Q, 100)
+    rep = oracle.compare_topk(D, I, Dt, It, rtol=RTOL, atol=ATOL)
+    assert rep["ok"] and rep["max_abs_err"] < 5e-7, rep
+    assert sh.last_stats()["reruns"] == 0
+    # 12 000 copies of one row, jittered far below the fp16 resolution: all inside every margin band
+    Xd = X.copy()
+    Xd[20000:32000] = Xd[7] + rng.standard_normal((12000, 256)).astype(np.float32) * 1e-6
+    qd = Xd[7:8] + 0.01 * _unit(rng, 1, 256)
+    sh2 = Shard(256, 0)
+    sh2.add(Xd)
+    Qd = np.concatenate([qd, Q[:130]])
+    D2, I2 = sh2.search(Qd, 50, path="tensor")
+    assert sh2.last_stats()["reruns"] == 2
+    _check(D2, I2, Xd, Qd, 50)
