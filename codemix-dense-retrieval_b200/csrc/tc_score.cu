@@ -171,20 +171,56 @@ __device__ __forceinline__ void epilogue_dense_tile(const TcParams& p, uint32_t 
 }
 
 // Filter epilogue of one 128 x BN accumulator tile for the calling thread's query row.
-// Pass 1 reads the row from TMEM and records which columns beat the threshold (one bit
-// per column); ONE atomicAdd per thread reserves room for all of them; pass 2 re-reads
-// the chunks that had survivors (warp-uniform decision: tcgen05.ld is .aligned) and
-// stores the keys contiguously.  A warp therefore pays one atomic round trip per tile
-// instead of one per surviving column of any of its lanes.
+// ONE pass over the row in TMEM: columns that beat the threshold are parked in a small
+// per-thread staging area in shared memory (value + column).  The caller then releases the
+// TMEM buffer to the MMA warp and only afterwards calls epilogue_flush, which reserves room
+// in the query's candidate buffer with ONE atomicAdd and stores the keys contiguously -- the
+// atomic's round trip is off the TMEM critical path and a warp pays it once per tile, not
+// once per surviving column of any of its lanes.  When a thread's staging area fills up
+// (dense early slabs) it is flushed in place.
+constexpr int TC_STAGE_SLOTS = 8;
+constexpr int TC_EPI_THREADS = 128;
+constexpr int TC_EPI_SMEM = TC_STAGE_SLOTS * TC_EPI_THREADS * 8;  // float value + int column per slot
+
+struct EpiStage {
+  float* val;  // [TC_STAGE_SLOTS][TC_EPI_THREADS]
+  int* col;    // [TC_STAGE_SLOTS][TC_EPI_THREADS]
+  int e;       // this thread's index among the epilogue threads
+};
+
+__device__ __forceinline__ void epilogue_flush(const TcParams& p, const EpiStage& st, int& nst, int64_t q, float inv,
+                                               int64_t tile_row0) {
+  if (nst == 0) return;
+  const uint32_t pos = atomicAdd(&p.cnt[q], (uint32_t)nst);
+  uint64_t* qcand = p.cand + q * (int64_t)p.cap;
+  for (int i = 0; i < nst; ++i) {
+    if (pos + i < (uint32_t)p.cap) {
+      const uint64_t key = make_key(st.val[i * TC_EPI_THREADS + st.e] * inv,
+                                    (uint32_t)(tile_row0 + st.col[i * TC_EPI_THREADS + st.e]));
+      if (p.flags & 4) st_stream_u64(qcand + pos + i, key);
+      else qcand[pos + i] = key;
+    }
+  }
+  nst = 0;
+}
+
+// staging area full in the middle of a row (dense early slabs only): one out-of-line copy so
+// that the 32-way unrolled compare loop stays small
+__device__ __noinline__ void epilogue_flush_full(uint32_t* cnt_q, uint64_t* qcand, int cap, const float* val, const int* col,
+                                                 float inv, int64_t tile_row0) {
+  const uint32_t pos = atomicAdd(cnt_q, (uint32_t)TC_STAGE_SLOTS);
+  for (int i = 0; i < TC_STAGE_SLOTS; ++i)
+    if (pos + i < (uint32_t)cap)
+      qcand[pos + i] = make_key(val[i * TC_EPI_THREADS] * inv, (uint32_t)(tile_row0 + col[i * TC_EPI_THREADS]));
+}
+
 template <int BN>
-__device__ __forceinline__ void epilogue_filter_tile(const TcParams& p, uint32_t taddr_row, int64_t q,
-                                                     float tau_raw, float inv, int64_t tile_row0,
+__device__ __forceinline__ void epilogue_filter_tile(const TcParams& p, uint32_t taddr_row, const EpiStage& st, int& nst,
+                                                     int64_t q, float tau_raw, float inv, int64_t tile_row0,
                                                      int64_t cols_valid) {
   constexpr int NC = BN / 32;
-  // Both loops stay rolled: the whole epilogue must fit the instruction cache (a fully
-  // unrolled version was 180 KB of SASS and ran 2.4x slower than the MMAs it hides behind).
-  uint32_t total = 0;
-  uint32_t chunk_bits = 0;  // bit c: chunk c holds at least one survivor of this thread
+  // rolled loop: the whole epilogue must fit the instruction cache (a fully unrolled version
+  // was 180 KB of SASS and ran 2.4x slower than the MMAs it hides behind)
 #pragma unroll 1
   for (int c = 0; c < NC; ++c) {
     uint32_t v[32];
@@ -196,37 +232,17 @@ __device__ __forceinline__ void epilogue_filter_tile(const TcParams& p, uint32_t
 #pragma unroll
     for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (j < jmax) ? __uint_as_float(v[j]) : mx);
     if (mx > tau_raw) {
-      uint32_t n = 0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) n += (j < jmax && __uint_as_float(v[j]) > tau_raw) ? 1u : 0u;
-      total += n;
-      chunk_bits |= 1u << c;
-    }
-  }
-  if (!__any_sync(0xffffffffu, total != 0)) return;
-  uint32_t pos = 0;
-  if (total) pos = atomicAdd(&p.cnt[q], total);
-  uint64_t* qcand = p.cand + q * (int64_t)p.cap;
-#pragma unroll 1
-  for (int c = 0; c < NC; ++c) {
-    const bool mine = (chunk_bits >> c) & 1u;
-    if (!__any_sync(0xffffffffu, mine)) continue;
-    uint32_t v[32];
-    __syncwarp();
-    tmem_ld_x32(taddr_row + (uint32_t)(c * 32), v);
-    tmem_ld_wait();
-    if (mine) {
-      const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float raw = __uint_as_float(v[j]);
         if (j < jmax && raw > tau_raw) {
-          if (pos < (uint32_t)p.cap) {
-            const uint64_t key = make_key(raw * inv, (uint32_t)(tile_row0 + c * 32 + j));
-            if (p.flags & 4) st_stream_u64(qcand + pos, key);
-            else qcand[pos] = key;
+          if (nst == TC_STAGE_SLOTS) {
+            epilogue_flush_full(&p.cnt[q], p.cand + q * (int64_t)p.cap, p.cap, st.val + st.e, st.col + st.e, inv, tile_row0);
+            nst = 0;
           }
-          ++pos;
+          st.val[nst * TC_EPI_THREADS + st.e] = raw;
+          st.col[nst * TC_EPI_THREADS + st.e] = c * 32 + j;
+          ++nst;
         }
       }
     }
@@ -258,6 +274,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint8_t* epi_smem = smem_raw + (bar_base - smem_u32(smem_raw)) + 256;  // after the barrier block
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -350,6 +367,11 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
     const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may touch
     const float inv = p.q_inv_scale[0] * p.b_inv_scale;
     const float fwd = 1.0f / inv;  // power of two
+    EpiStage stg;
+    stg.val = reinterpret_cast<float*>(epi_smem);
+    stg.col = reinterpret_cast<int*>(epi_smem + TC_STAGE_SLOTS * TC_EPI_THREADS * 4);
+    stg.e = (warp - 2) * 32 + lane;
+    int nst = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -366,10 +388,11 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
       if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid);
-      else epilogue_filter_tile<BN>(p, taddr_row, q, tau_raw, inv, tile_row0, cols_valid);
+      else epilogue_filter_tile<BN>(p, taddr_row, stg, nst, q, tau_raw, inv, tile_row0, cols_valid);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) mbar_arrive(tempty_bar(acc));  // TMEM buffer back to the MMA warp ...
+      epilogue_flush(p, stg, nst, q, inv, tile_row0);  // ... before the atomic round trip
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -453,6 +476,7 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };       // one per CTA
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };  // used in the leader
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint8_t* epi_smem = smem_raw + (bar_base - smem_u32(smem_raw)) + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -551,6 +575,11 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
     const int lane_base = (warp & 3) * 32;
     const float inv = p.q_inv_scale[0] * p.b_inv_scale;
     const float fwd = 1.0f / inv;
+    EpiStage stg;
+    stg.val = reinterpret_cast<float*>(epi_smem);
+    stg.col = reinterpret_cast<int*>(epi_smem + TC_STAGE_SLOTS * TC_EPI_THREADS * 4);
+    stg.e = (warp - 2) * 32 + lane;
+    int nst = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = cid; t < p.ntiles; t += ncl) {
@@ -566,11 +595,12 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
       if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid);
-      else epilogue_filter_tile<BN>(p, taddr_row, q, tau_raw, inv, tile_row0, cols_valid);
+      else epilogue_filter_tile<BN>(p, taddr_row, stg, nst, q, tau_raw, inv, tile_row0, cols_valid);
       tc_fence_before();
       __syncwarp();
       // the leader's MMA thread waits for the epilogues of both CTAs (8 warps)
       if (lane == 0) mbar_arrive_cluster(mapa_cta(tempty_bar(acc), 0));
+      epilogue_flush(p, stg, nst, q, inv, tile_row0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -812,9 +842,11 @@ int tensor_path_available() { return get_encode() != nullptr; }
 
 static int g_tc_bn = 256;  // tile width in corpus rows: 256 (2 stages) or 128 (3 stages)
 static int g_tc_flags = 0;
-constexpr int kTcPairDefault = 0;
-static int g_tc_pair = kTcPairDefault;  // 1: CTA-pair kernel (cta_group::2) for nq > 128
-void set_tensor_pair(int on) { g_tc_pair = (on < 0) ? kTcPairDefault : (on ? 1 : 0); }
+// CTA-pair kernel (cta_group::2) for nq > 128: -1 = automatic (measured on B200: the pair kernel
+// wins when one MMA pass makes the kernel shared-memory / L2 bound -- 150.7 vs 174.3 ms at C2 --
+// and ties within 3 % with three passes, where the single-CTA kernel already sits at the tensor peak)
+static int g_tc_pair = -1;
+void set_tensor_pair(int on) { g_tc_pair = (on < 0) ? -1 : (on ? 1 : 0); }
 void set_tensor_tile(int bn) { g_tc_bn = (bn == 128) ? 128 : 256; }
 void set_tensor_flags(int f) { g_tc_flags = f; }
 
@@ -822,8 +854,8 @@ template <int BN, int STAGES, int PASSES>
 static int launch_tc(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const CUtensorMap& tb_hi,
                      const CUtensorMap& tb_lo, const TcParams& p, cudaStream_t st, int sm_count) {
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TC_A_BYTES + BN * TC_BK * 2);
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
-  static_assert((size_t)STAGES * STAGE_BYTES + 1024 + 256 <= 227 * 1024, "stage ring exceeds shared memory");
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + TC_EPI_SMEM;
+  static_assert((size_t)STAGES * STAGE_BYTES + 1024 + 256 + TC_EPI_SMEM <= 227 * 1024, "stage ring exceeds shared memory");
   CMX_CUDA(cudaFuncSetAttribute(tc_score_kernel<BN, STAGES, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = p.ntiles < sm_count ? p.ntiles : sm_count;
   if (grid < 1) return CMX_OK;
@@ -836,8 +868,8 @@ template <int STAGES, int PASSES>
 static int launch_tc_pair(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const CUtensorMap& tb_hi,
                           const CUtensorMap& tb_lo, const TcParams& p, cudaStream_t st, int sm_count) {
   constexpr int STAGE_BYTES = (PASSES == 3 ? 4 : 2) * (128 * TC_BK * 2);
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
-  static_assert((size_t)STAGES * STAGE_BYTES + 1024 + 256 <= 227 * 1024, "stage ring exceeds shared memory");
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + TC_EPI_SMEM;
+  static_assert((size_t)STAGES * STAGE_BYTES + 1024 + 256 + TC_EPI_SMEM <= 227 * 1024, "stage ring exceeds shared memory");
   CMX_CUDA(cudaFuncSetAttribute(tc_score_pair_kernel<STAGES, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t clusters = sm_count / 2;
   if (p.ntiles < clusters) clusters = p.ntiles;
@@ -912,7 +944,7 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
     if (nq <= 32) return launch_tc_small<32, 8, 1>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
     return launch_tc_small<64, 8, 1>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
   }
-  const bool pair = g_tc_pair && nq > 128;
+  const bool pair = (g_tc_pair < 0 ? !split : g_tc_pair != 0) && nq > 128;
   const int bn = pair ? 128 : g_tc_bn;  // pair: each CTA loads a 128-row half of the 256-row tile
   CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;
   CMX_TRY(make_plane_map(&tq_hi, Qhi, nq_pad, d_pad, TC_BM));
