@@ -1,0 +1,19 @@
+#!/bin/bash
+# final evidence for the default (rescore) path: plain bench lines, launch list, full captures
+mkdir -p gpurun_out
+python __graft_entry__.py > gpurun_out/build.log 2>&1
+python bench.py > gpurun_out/bench_default.log 2>&1
+echo "bench exit $?" >> gpurun_out/bench_default.log
+python bench.py --precision split --no-cpu-baseline > gpurun_out/bench_split.log 2>&1
+KRE='regex:tc_score|stream_score|compact_kernel|rescore_kernel|mix_normalize|split_planes|absmax|ws_init|set_counts|merge|scale_from|row_norm|query_margin'
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+$CMD > gpurun_out/plain_full.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -c 600 --csv --log-file gpurun_out/launches_full.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+echo "launch list exit $?" >> gpurun_out/ncu_launches.log
+CMD1="python bench.py --rows 4420912 --steps 1 --warmup 1 --no-cpu-baseline"
+$CMD1 > gpurun_out/plain_half.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:tc_score -s 7 -c 7 -f -o gpurun_out/prof_tc4 $CMD1 > gpurun_out/ncu_tc4.log 2>&1
+echo "tc capture exit $?" >> gpurun_out/ncu_tc4.log
+ncu --set full --clock-control none --import-source on -k regex:rescore_kernel -s 1 -c 1 -f -o gpurun_out/prof_rescore4 $CMD1 > gpurun_out/ncu_rescore4.log 2>&1
+echo "rescore capture exit $?" >> gpurun_out/ncu_rescore4.log
+tail -n 2 gpurun_out/bench_default.log | cut -c1-1500
