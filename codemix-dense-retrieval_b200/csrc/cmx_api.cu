@@ -84,6 +84,7 @@ struct cmx_index {
   __half* Qlo = nullptr; int64_t qlo_cap = 0;
   uint32_t* q_absmax = nullptr;
   float* margin_buf = nullptr;
+  unsigned long long* progress = nullptr;  // tile-progress counter of the tensor kernels
   float* q_scale = nullptr;  // {scale, 1/scale}
   float* D_dev = nullptr; int64_t D_cap = 0;
   int64_t* I_dev = nullptr; int64_t I_cap = 0;
@@ -242,6 +243,7 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
     if (!rescore) CMX_TRY(ensure_buf(&ix->Qlo, &ix->qlo_cap, nq_pad * (int64_t)ix->d_pad));
     if (!ix->q_absmax) CMX_CUDA(cudaMalloc((void**)&ix->q_absmax, sizeof(uint32_t)));
     if (!ix->q_scale) CMX_CUDA(cudaMalloc((void**)&ix->q_scale, 2 * sizeof(float)));
+    if (!ix->progress) CMX_CUDA(cudaMalloc((void**)&ix->progress, sizeof(unsigned long long)));
     CMX_CUDA(cudaMemsetAsync(ix->q_absmax, 0, sizeof(uint32_t), st));
     CMX_TRY(launch_absmax(q_d, nq * (int64_t)ix->d, ix->q_absmax, st));
     CMX_TRY(launch_scale_from_absmax(ix->q_absmax, ix->q_scale, st));
@@ -276,8 +278,8 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
     if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 0], st));
     if (path == CMX_PATH_TENSOR) {
       CMX_TRY(launch_tensor_score(ix->Bhi, ix->Blo, ix->n, seen, rows, ix->d_pad, ix->Qhi, ix->Qlo, nq, nq_pad,
-                                  ix->q_scale + 1, 1.0f / ix->plane_scale, ix->ws, dense, seen, rescore ? 1 : 3, st,
-                                  ix->sm_count));
+                                  ix->q_scale + 1, 1.0f / ix->plane_scale, ix->ws, dense, seen, rescore ? 1 : 3,
+                                  seen > 0 ? (double)k_plan / (double)seen : 1.0, ix->progress, st, ix->sm_count));
     } else {
       CMX_TRY(launch_stream_score(ix->X, seen, rows, ix->d, q_d, (int)nq, ix->ws, 0, dense, seen, st, ix->sm_count));
     }
@@ -415,7 +417,7 @@ int cmx_index_free(cmx_index* ix) {
   if (!ix) return CMX_OK;
   DevGuard g(ix->device);
   void* ptrs[] = {ix->X, ix->Bhi, ix->Blo, ix->absmax_dev, ix->ws.tau, ix->ws.cnt, ix->ws.cand, ix->ws.overflow,
-                  ix->q_dev, ix->p_dev, ix->s_dev, ix->Qhi, ix->Qlo, ix->q_absmax, ix->q_scale, ix->margin_buf, ix->D_dev, ix->I_dev,
+                  ix->q_dev, ix->p_dev, ix->s_dev, ix->Qhi, ix->Qlo, ix->q_absmax, ix->q_scale, ix->margin_buf, ix->progress, ix->D_dev, ix->I_dev,
                   ix->flags_dev, ix->w_dev, ix->mode_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -761,6 +763,7 @@ int cmx_merge_topk_peers(const float* const* D_parts, const int64_t* const* I_pa
 
 /* test hook (not in cmx.h): tensor tile width 256 / 128 */
 CMX_API int cmx_debug_set_tensor_tile(int bn) { set_tensor_tile(bn); return CMX_OK; }
+CMX_API int cmx_debug_set_tensor_window(int w) { set_tensor_window(w); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_small(int on) { set_tensor_small(on); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_pair(int on) { set_tensor_pair(on); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_flags(int f) { set_tensor_flags(f); return CMX_OK; }

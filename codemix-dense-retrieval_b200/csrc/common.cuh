@@ -122,8 +122,9 @@ void set_tensor_pair(int on);  // CTA-pair (cta_group::2) scorer for nq > 128
 int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
                         int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,
                         int64_t nq, int64_t nq_pad, const float* q_inv_scale_dev, float b_inv_scale,
-                        const SearchWs& ws, int dense, int64_t dense_row0, int passes, cudaStream_t st,
-                        int sm_count);
+                        const SearchWs& ws, int dense, int64_t dense_row0, int passes, double expected_pass_rate,
+                        unsigned long long* progress, cudaStream_t st, int sm_count);
+void set_tensor_window(int w);  // progress throttle slack in round-robin iterations (0 = off)
 
 int launch_ws_init(const SearchWs& ws, int64_t nq, int64_t nq_pad, cudaStream_t st);
 int launch_set_counts(const SearchWs& ws, int64_t nq, uint32_t value, cudaStream_t st);

@@ -114,6 +114,19 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void throttle_wait(const unsigned long long* done, long long t, long long window) {
+  if (window <= 0) return;
+  unsigned long long d;
+  for (;;) {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(d) : "l"(done) : "memory");
+    if (t < (long long)d + window) break;
+    __nanosleep(200);
+  }
+}
+__device__ __forceinline__ void throttle_tile_done(unsigned long long* done) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(done) : "memory");
+}
+
 // K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 "version 1"):
 // start address >> 4 | LBO (unused for swizzled K-major) | SBO = 1024 B (8 rows x
 // 128 B) | version = 1 | layout = SWIZZLE_128B (2)
@@ -143,6 +156,14 @@ struct TcParams {
   int dense;
   int64_t dense_row0;
   int flags;  // bit0: Q tiles evict_last, bit1: corpus tiles evict_first, bit2: streaming (.cs) appends
+  // Progress throttle: tiles are assigned round-robin (m fastest) so that CTAs running at the
+  // same time share corpus tiles through L2 -- but in a long launch CTAs drift apart (they are
+  // paced by memory latency, not by a clock) and the set of corpus tiles in flight outgrows
+  // L2: ncu showed 8x the algorithmic DRAM reads on a 3 M-row slab.  `done` counts finished
+  // tiles; a producer does not start tile t before t < done + window.
+  unsigned long long* done;
+  long long window;
+  int two_pass;  // 1: count-then-store epilogue (dense early slabs), 0: staged epilogue
 };
 
 // Dense epilogue (first slab): every column of the calling thread's query row becomes a
@@ -178,6 +199,54 @@ __device__ __forceinline__ void epilogue_dense_tile(const TcParams& p, uint32_t 
 // atomic's round trip is off the TMEM critical path and a warp pays it once per tile, not
 // once per surviving column of any of its lanes.  When a thread's staging area fills up
 // (dense early slabs) it is flushed in place.
+template <int BN>
+__device__ __forceinline__ void epilogue_filter_tile_two_pass(const TcParams& p, uint32_t taddr_row, int64_t q,
+                                                              float tau_raw, float inv, int64_t tile_row0,
+                                                              int64_t cols_valid) {
+  // dense early slabs (tens of survivors per row and tile): count first, reserve with ONE
+  // atomicAdd, then re-read the chunks that had survivors and store them contiguously
+  constexpr int NC = BN / 32;
+  uint32_t total = 0;
+  uint32_t chunk_bits = 0;
+#pragma unroll 1
+  for (int c = 0; c < NC; ++c) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(taddr_row + (uint32_t)(c * 32), v);
+    tmem_ld_wait();
+    const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
+    uint32_t n = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) n += (j < jmax && __uint_as_float(v[j]) > tau_raw) ? 1u : 0u;
+    total += n;
+    if (n) chunk_bits |= 1u << c;
+  }
+  if (!__any_sync(0xffffffffu, total != 0)) return;
+  uint32_t pos = 0;
+  if (total) pos = atomicAdd(&p.cnt[q], total);
+  uint64_t* qcand = p.cand + q * (int64_t)p.cap;
+#pragma unroll 1
+  for (int c = 0; c < NC; ++c) {
+    const bool mine = (chunk_bits >> c) & 1u;
+    if (!__any_sync(0xffffffffu, mine)) continue;
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(taddr_row + (uint32_t)(c * 32), v);
+    tmem_ld_wait();
+    if (mine) {
+      const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float raw = __uint_as_float(v[j]);
+        if (j < jmax && raw > tau_raw) {
+          if (pos < (uint32_t)p.cap) qcand[pos] = make_key(raw * inv, (uint32_t)(tile_row0 + c * 32 + j));
+          ++pos;
+        }
+      }
+    }
+  }
+}
+
 constexpr int TC_STAGE_SLOTS = 8;
 constexpr int TC_EPI_THREADS = 128;
 constexpr int TC_EPI_SMEM = TC_STAGE_SLOTS * TC_EPI_THREADS * 8;  // float value + int column per slot
@@ -310,6 +379,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
         const int64_t n = t / mtiles;
         const int32_t qrow = m * TC_BM;
         const int32_t brow = (int32_t)(p.row0 + n * BN);
+        throttle_wait(p.done, t, p.window);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
@@ -388,10 +458,12 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
       if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid);
+      else if (p.two_pass) epilogue_filter_tile_two_pass<BN>(p, taddr_row, q, tau_raw, inv, tile_row0, cols_valid);
       else epilogue_filter_tile<BN>(p, taddr_row, stg, nst, q, tau_raw, inv, tile_row0, cols_valid);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));  // TMEM buffer back to the MMA warp ...
+      if (threadIdx.x == 64 && p.window > 0) throttle_tile_done(p.done);
       epilogue_flush(p, stg, nst, q, inv, tile_row0);  // ... before the atomic round trip
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -517,6 +589,7 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
         const int64_t n = t / mtiles;
         const int32_t qrow = m * 256 + (int32_t)rank * 128;
         const int32_t brow = (int32_t)(p.row0 + n * BN) + (int32_t)rank * 128;
+        throttle_wait(p.done, t, p.window);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
@@ -595,11 +668,13 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
       if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid);
+      else if (p.two_pass) epilogue_filter_tile_two_pass<BN>(p, taddr_row, q, tau_raw, inv, tile_row0, cols_valid);
       else epilogue_filter_tile<BN>(p, taddr_row, stg, nst, q, tau_raw, inv, tile_row0, cols_valid);
       tc_fence_before();
       __syncwarp();
       // the leader's MMA thread waits for the epilogues of both CTAs (8 warps)
       if (lane == 0) mbar_arrive_cluster(mapa_cta(tempty_bar(acc), 0));
+      if (threadIdx.x == 64 && leader && p.window > 0) throttle_tile_done(p.done);
       epilogue_flush(p, stg, nst, q, inv, tile_row0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -842,6 +917,8 @@ int tensor_path_available() { return get_encode() != nullptr; }
 
 static int g_tc_bn = 256;  // tile width in corpus rows: 256 (2 stages) or 128 (3 stages)
 static int g_tc_flags = 0;
+static int g_tc_window = 3;  // progress throttle: a CTA may run this many round-robin iterations ahead (0 = off)
+void set_tensor_window(int w) { g_tc_window = w < 0 ? 3 : w; }
 // CTA-pair kernel (cta_group::2) for nq > 128: -1 = automatic (measured on B200: the pair kernel
 // wins when one MMA pass makes the kernel shared-memory / L2 bound -- 150.7 vs 174.3 ms at C2 --
 // and ties within 3 % with three passes, where the single-CTA kernel already sits at the tensor peak)
@@ -911,8 +988,8 @@ void set_tensor_small(int on) { g_tc_small = on ? 1 : 0; }
 int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
                         int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,
                         int64_t nq, int64_t nq_pad, const float* q_inv_scale_dev, float b_inv_scale,
-                        const SearchWs& ws, int dense, int64_t dense_row0, int passes, cudaStream_t st,
-                        int sm_count) {
+                        const SearchWs& ws, int dense, int64_t dense_row0, int passes, double expected_pass_rate,
+                        unsigned long long* progress, cudaStream_t st, int sm_count) {
   if (nrows <= 0 || nq <= 0) return CMX_OK;
   CMX_CHECK(passes == 1 || passes == 3, "tensor path: passes must be 1 or 3");
   CMX_CHECK(d_pad % TC_BK == 0, "tensor path: padded dim must be a multiple of %d", TC_BK);
@@ -934,6 +1011,11 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   p.flags = g_tc_flags;
   p.mtiles = 1;
   p.ntiles = 0;
+  p.done = nullptr;
+  p.window = 0;
+  // more than ~6 expected survivors per row and tile (slab right after the dense one): the staging
+  // area would be flushed several times per tile with the TMEM buffer held
+  p.two_pass = (!dense && expected_pass_rate * 256.0 > 6.0) ? 1 : 0;
   if (g_tc_small && nq <= 64) {
     if (split) {
       if (nq <= 16) return launch_tc_small<16, 5, 3>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
@@ -958,6 +1040,11 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   }
   p.mtiles = pair ? (int)((nq + 255) / 256) : (int)((nq + TC_BM - 1) / TC_BM);
   p.ntiles = pair ? (int64_t)p.mtiles * ((nrows + 255) / 256) : (int64_t)p.mtiles * ((nrows + bn - 1) / bn);
+  if (g_tc_window > 0 && progress != nullptr) {
+    CMX_CUDA(cudaMemsetAsync(progress, 0, sizeof(unsigned long long), st));
+    p.done = progress;
+    p.window = (long long)g_tc_window * (pair ? sm_count / 2 : sm_count);  // iterations of slack
+  }
   if (pair) {
     if (split) return launch_tc_pair<3, 3>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
     return launch_tc_pair<6, 1>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);

@@ -37,12 +37,12 @@ def run(nq, k, path, reps=5, variant=None):
                       "select_ms": round(se / reps, 3), "corpus_GBps_total": round(gb * passes / (ms / 1e3), 1),
                       "corpus_GBps_score_kernel": round(gb * passes / (sc / reps / 1e3), 1), "slabs": st["slabs"]}), flush=True)
 
-for small in (0, 1):
-    _lib.check(_lib.lib().cmx_debug_set_tensor_small(small))
-    for nq in (5, 8, 16, 32, 64, 128):
-        run(nq, 100, "tensor", variant=small)
-    run(128, 1000, "tensor", variant=small)
-_lib.check(_lib.lib().cmx_debug_set_tensor_small(1))
+for prec in ("rescore", "split"):
+    sh.set_precision(prec)
+    for nq in (1, 2, 4, 8, 16, 32, 64, 128, 256):
+        run(nq, 100, "tensor", variant=prec)
+    run(32, 1000, "tensor", variant=prec)
+sh.set_precision("rescore")
 for nq in (1, 4):
     run(nq, 100, "stream")
-run(256, 100, "tensor")
+    run(nq, 1000, "stream")

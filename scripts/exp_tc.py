@@ -17,11 +17,11 @@ for N in sizes:
     while c * bench.CHUNK < N:
         x = bench.corpus_chunk(c, d, dev)
         sh.add(x[: min(bench.CHUNK, N - c * bench.CHUNK)]); del x; c += 1
-    for prec, pair in (("split", 0), ("rescore", 0), ("rescore", 1)):
+    for prec, pair, flags in (("split", 0, 3), ("split", 0, 0), ("rescore", 0, 0), ("rescore", 0, 3), ("rescore", 1, 0), ("rescore", 1, 3), ("rescore", 1, 6)):
         sh.set_precision(prec)
         _lib.check(_lib.lib().cmx_debug_set_tensor_pair(pair))
-        for flags in (0,):
-            _lib.check(_lib.lib().cmx_debug_set_tensor_flags(flags))
+        for _ in (0,):
+            _lib.check(_lib.lib().cmx_debug_set_tensor_window(flags))
             for _ in range(2):
                 sh.search_mixed(P, S, [0.5], 1000, path="tensor")
             sc = se = tot = 0.0
@@ -30,7 +30,7 @@ for N in sizes:
                 sh.search_mixed(P, S, [0.5], 1000, path="tensor"); st = sh.last_stats()
                 sc += st["score_ms"]; se += st["select_ms"]; tot += st["total_ms"]
             tf = (3 if prec == "split" else 1) * 2.0 * 6980 * N * d / (sc / reps / 1e3) / 1e12
-            print(json.dumps({"N": N, "precision": prec, "pair": pair, "reruns": st["reruns"], "qps": round(6980 / (tot / reps / 1e3)), "score_ms": round(sc / reps, 2), "select_ms": round(se / reps, 2),
+            print(json.dumps({"N": N, "precision": prec, "pair": pair, "window": flags, "reruns": st["reruns"], "qps": round(6980 / (tot / reps / 1e3)), "score_ms": round(sc / reps, 2), "select_ms": round(se / reps, 2),
                               "total_ms": round(tot / reps, 2), "exec_TFLOPs": round(tf, 1)}), flush=True)
     del sh
     torch.cuda.empty_cache()
