@@ -919,9 +919,10 @@ static int g_tc_bn = 256;  // tile width in corpus rows: 256 (2 stages) or 128 (
 static int g_tc_flags = 0;
 static int g_tc_window = 3;  // progress throttle: a CTA may run this many round-robin iterations ahead (0 = off)
 void set_tensor_window(int w) { g_tc_window = w < 0 ? 3 : w; }
-// CTA-pair kernel (cta_group::2) for nq > 128: -1 = automatic (measured on B200: the pair kernel
-// wins when one MMA pass makes the kernel shared-memory / L2 bound -- 150.7 vs 174.3 ms at C2 --
-// and ties within 3 % with three passes, where the single-CTA kernel already sits at the tensor peak)
+// CTA-pair kernel (cta_group::2) for nq > 128.  Measured on B200 at C2 (profiles/): with three MMA
+// passes both kernels sit at the tensor peak (within 3 %); with one pass and the progress throttle
+// the single-CTA kernel is ahead (116.6 vs 122.3 ms), so it is the default and the pair kernel
+// stays selectable (-1 = default = off).
 static int g_tc_pair = -1;
 void set_tensor_pair(int on) { g_tc_pair = (on < 0) ? -1 : (on ? 1 : 0); }
 void set_tensor_tile(int bn) { g_tc_bn = (bn == 128) ? 128 : 256; }
@@ -1026,7 +1027,7 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
     if (nq <= 32) return launch_tc_small<32, 8, 1>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
     return launch_tc_small<64, 8, 1>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
   }
-  const bool pair = (g_tc_pair < 0 ? !split : g_tc_pair != 0) && nq > 128;
+  const bool pair = g_tc_pair > 0 && nq > 128;
   const int bn = pair ? 128 : g_tc_bn;  // pair: each CTA loads a 128-row half of the 256-row tile
   CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;
   CMX_TRY(make_plane_map(&tq_hi, Qhi, nq_pad, d_pad, TC_BM));

@@ -17,7 +17,7 @@ for N in sizes:
     while c * bench.CHUNK < N:
         x = bench.corpus_chunk(c, d, dev)
         sh.add(x[: min(bench.CHUNK, N - c * bench.CHUNK)]); del x; c += 1
-    for prec, pair, flags in (("split", 0, 3), ("split", 0, 0), ("rescore", 0, 0), ("rescore", 0, 3), ("rescore", 1, 0), ("rescore", 1, 3), ("rescore", 1, 6)):
+    for prec, pair, flags in (("rescore", 0, 1), ("rescore", 0, 2), ("rescore", 0, 3), ("rescore", 0, 4), ("rescore", 0, 8), ("split", 0, 3)):
         sh.set_precision(prec)
         _lib.check(_lib.lib().cmx_debug_set_tensor_pair(pair))
         for _ in (0,):
