@@ -352,7 +352,16 @@ def run_cmx(a) -> None:
     used_tensor = stats["path"] == 2
     per_step_score_ms = score_ms_max / a.steps
     passes = 3 if a.precision == "split" else 1
-    if used_tensor:
+    if used_tensor and nq <= 128:
+        # small batches: the tensor kernels are bound by the HBM stream of the fp16 operand plane(s)
+        alg_bytes = (4.0 if passes == 3 else 2.0) * n_local * d_pad
+        achieved = alg_bytes / (per_step_score_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "tc_score_small_kernel" if nq <= (64 if passes == 3 else 32) else "tc_score_kernel",
+                    "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                    "traffic": None, "kernel_ms_per_step": per_step_score_ms, "peak_source": peaks["source"],
+                    "note": "algorithmic bytes = fp16 operand plane(s) read once per sweep (%d B per corpus row); the measured peak is "
+                            "a copy (read+write) figure, a read-only stream can exceed it" % int(alg_bytes / n_local)}
+    elif used_tensor:
         alg_flops = 2.0 * nq * n_local * d  # per step on this rank
         executed = passes * 2.0 * nq * n_local * d_pad  # fp16 MMA passes actually issued
         achieved = executed / (per_step_score_ms / 1e3) / 1e12

@@ -329,9 +329,13 @@ static int search_device(cmx_index* ix, const float* q_d, int64_t nq, int k, flo
                          int64_t id_base, int path, cudaStream_t st) {
   if (nq == 0) return CMX_OK;
   if (ix->n == 0) return fill_empty(D_d, I_d, nq * (int64_t)k, st);
-  // measured on B200 (profiles/): the fp32 stream scorer sustains 6.7-7.3 TB/s up to 4 queries;
-  // from 5 queries on the tensor scorer (5.9 TB/s at nq=8) is faster than a second stream group
-  if (path == CMX_PATH_AUTO) path = (nq <= 4) ? CMX_PATH_STREAM : CMX_PATH_TENSOR;
+  // measured on B200 (profiles/): per 36 GB corpus sweep the fp32 stream scorer takes 4.9-5.3 ms
+  // (1-4 queries, 7.0-7.3 TB/s), the split-precision tensor kernels 5.0-5.2 ms (up to 32 queries),
+  // the one-pass tensor kernels of the rescore mode 2.5-2.8 ms (they read only the 18 GB hi plane)
+  if (path == CMX_PATH_AUTO) {
+    const bool rescore_ok = ix->precision == CMX_PRECISION_RESCORE && ix->row_norm_max > 0.f;
+    path = (rescore_ok || nq > 4) ? CMX_PATH_TENSOR : CMX_PATH_STREAM;
+  }
   if (path == CMX_PATH_STREAM && (ix->d & 3) != 0) path = CMX_PATH_TENSOR;
   ix->stats.path = path;
   for (int64_t q0 = 0; q0 < nq; q0 += kQueryChunk) {

@@ -47,7 +47,7 @@ typedef struct cmx_index cmx_index;
 #define CMX_ERR_INTERNAL 4
 
 /* scoring path selector for search */
-#define CMX_PATH_AUTO 0     /* nq <= 4: stream, else tensor                 */
+#define CMX_PATH_AUTO 0     /* tensor; stream for nq <= 4 in split precision */
 #define CMX_PATH_STREAM 1   /* CUDA-core fp32 streaming scorer (HBM-bound)  */
 #define CMX_PATH_TENSOR 2   /* tcgen05 fp16-split (hi/lo) tensor-core scorer */
 

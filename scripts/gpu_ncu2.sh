@@ -13,7 +13,7 @@ CMD1="python bench.py --rows 4420912 --steps 1 --warmup 1 --no-cpu-baseline"
 $CMD1 > gpurun_out/plain_half.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:tc_score_kernel -s 6 -c 6 -f -o gpurun_out/prof_tc2 $CMD1 > gpurun_out/ncu_tc2.log 2>&1
 echo "tc capture exit $?" >> gpurun_out/ncu_tc2.log
-CMD2="python bench.py --nq 4 --k 100 --steps 1 --warmup 1 --no-cpu-baseline"
+CMD2="python bench.py --nq 4 --k 100 --path stream --steps 1 --warmup 1 --no-cpu-baseline"
 $CMD2 > gpurun_out/plain_stream.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:stream_score -s 4 -c 3 -f -o gpurun_out/prof_stream2 $CMD2 > gpurun_out/ncu_stream2.log 2>&1
 echo "stream capture exit $?" >> gpurun_out/ncu_stream2.log
@@ -22,6 +22,6 @@ echo "compact capture exit $?" >> gpurun_out/ncu_compact2.log
 # the default bench, plain, for the record
 python bench.py > gpurun_out/bench_default.log 2>&1
 echo "bench exit $?" >> gpurun_out/bench_default.log
-python bench.py --nq 4 --k 100 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_stream_nq4.log 2>&1
-python bench.py --nq 1 --k 100 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_stream_nq1.log 2>&1
+python bench.py --nq 4 --k 100 --path stream --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_stream_nq4.log 2>&1
+python bench.py --nq 1 --k 100 --path stream --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_stream_nq1.log 2>&1
 tail -n 2 gpurun_out/bench_default.log | cut -c1-400
