@@ -255,6 +255,7 @@ def run_cmx(a) -> None:
     d, k, nq, N = a.dim, a.k, a.nq, a.rows
     _lib.set_default_precision(a.precision)
     index = ShardedIndex(d, N, device=local_rank, exchange=a.exchange)
+    index.set_precision(a.precision)
     index.path = a.path
     fill_shard(index, index.row0, index.row1, d, dev)
     assert index.local_complete()
@@ -407,7 +408,7 @@ def run_cmx(a) -> None:
         "dtype": ("f16-filter+f32-exact-rescore" if a.precision == "rescore" else "f16x3-split+f32acc") if used_tensor else "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(a), "rows": N, "dim": d, "queries": nq, "k": k, "alpha": ALPHA,
-                   "parallelism": f"corpus row shards x{world}, exchange={index.exchange_used}" if world > 1 else "single GPU",
+                   "parallelism": f"corpus row shards x{world}, exchange={index.exchange_used}, two_phase_rescore={index.two_phase_used}" if world > 1 else "single GPU",
                    "cache": "inputs_larger_than_L2 (corpus %.1f GB per GPU)" % (n_local * d * 4 / 1e9),
                    "path": "tensor" if used_tensor else "stream", "precision": a.precision if used_tensor else "fp32",
                    "slabs": stats["slabs"], "reruns": stats["reruns"]},

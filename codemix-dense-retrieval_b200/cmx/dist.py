@@ -54,6 +54,7 @@ class ShardedIndex:
         self.bounds = shard_bounds(int(ntotal_global), self.world)
         self.ntotal = int(ntotal_global)
         self.row0, self.row1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self._default_engine = engine_factory is None
         if engine_factory is None:
             from .engine import Shard
 
@@ -70,7 +71,21 @@ class ShardedIndex:
         self.exchange_used = "none" if self.world == 1 else "allgather"
         self._peer = {}
         self._device = device
+        # rescore precision + several shards: exchange approximate k-th scores before the exact rescoring
+        self.two_phase = True
+        self.two_phase_used = False
+        self.precision = "rescore"
+        self._flag = None
+        if self.world > 1 and torch is not None and torch.cuda.is_available() and self._default_engine:
+            self._flag = torch.zeros((1,), dtype=torch.float32,
+                                     device=torch.device("cuda", torch.cuda.current_device() if device is None else device))
         self._custom_engine = engine_factory is not None and not hasattr(self.local, "_h")
+
+    def set_precision(self, mode: str) -> None:
+        """'rescore' (default) or 'split' arithmetic of the tensor path (see cmx.h)."""
+        self.precision = mode
+        if hasattr(self.local, "set_precision"):
+            self.local.set_precision(mode)
 
     # ---- storage: each rank adds ITS rows, in global row order ----------------
     def reserve_local(self) -> None:
@@ -111,8 +126,9 @@ class ShardedIndex:
         dev = torch.device("cuda", torch.cuda.current_device() if self._device is None else self._device)
         grp = self.group if self.group is not None else dist.group.WORLD
         bufs = {}
-        for name, dt in (("D_loc", torch.float32), ("I_loc", torch.int64), ("D_out", torch.float32), ("I_out", torch.int64)):
-            t = symm_mem.empty((nq * k,), dtype=dt, device=dev)
+        for name, dt, numel in (("D_loc", torch.float32, nq * k), ("I_loc", torch.int64, nq * k),
+                                ("D_out", torch.float32, nq * k), ("I_out", torch.int64, nq * k), ("kth", torch.float32, nq)):
+            t = symm_mem.empty((numel,), dtype=dt, device=dev)
             hdl = symm_mem.rendezvous(t, grp)
             bufs[name] = (t, hdl, [int(p) for p in hdl.buffer_ptrs])
         self._peer = {key: bufs}  # keep one shape alive
@@ -125,7 +141,7 @@ class ShardedIndex:
             return False
         return True
 
-    def _search_p2p(self, lead_shape, k: int, run_local):
+    def _search_p2p(self, lead_shape, k: int, run_local, two_phase=None):
         import ctypes as C
 
         from . import _lib
@@ -136,7 +152,21 @@ class ShardedIndex:
         I_loc, _, I_ptrs = bufs["I_loc"]
         D_out, _, Do_ptrs = bufs["D_out"]
         I_out, _, Io_ptrs = bufs["I_out"]
-        run_local((D_loc.view(*lead_shape, k), I_loc.view(*lead_shape, k)))
+        done = False
+        if two_phase is not None:
+            # rescore precision: exchange the shards' k-th best APPROXIMATE scores first, so that each
+            # shard rescoring only touches rows that can still reach the GLOBAL top-k
+            kth, _, kth_ptrs = bufs["kth"]
+            flag = self._flag
+            flag.fill_(1.0 if two_phase(kth) else 0.0)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)  # collective fallback decision
+            hdl.barrier(channel=2)  # every rank's kth array is complete and visible
+            if float(flag.item()) == 0.0:
+                self.local.search_end(kth_ptrs, D_loc, I_loc)
+                done = True
+                self.two_phase_used = True
+        if not done:
+            run_local((D_loc.view(*lead_shape, k), I_loc.view(*lead_shape, k)))
         hdl.barrier(channel=0)  # every rank's lists are complete and visible
         G = self.world
         q0, q1 = (nq * self.rank) // G, (nq * (self.rank + 1)) // G
@@ -148,15 +178,30 @@ class ShardedIndex:
         self.exchange_used = "p2p"
         return D_out.view(*lead_shape, k), I_out.view(*lead_shape, k)
 
-    def _run(self, like, lead_shape, k: int, run_local):
+    def _run(self, like, lead_shape, k: int, run_local, two_phase=None):
         if self._p2p_ok(like):
             try:
-                return self._search_p2p(lead_shape, k, run_local)
+                return self._search_p2p(lead_shape, k, run_local, two_phase)
             except Exception as exc:  # symmetric memory unavailable: keep the NCCL exchange
                 if self.exchange == "p2p":
                     raise
                 self.exchange = "allgather"
                 self.exchange_error = repr(exc)
+        if two_phase is not None and self.world > 1 and not self._custom_engine and torch is not None \
+                and isinstance(like, torch.Tensor) and like.is_cuda:
+            nq = int(np.prod(lead_shape))
+            kth = torch.empty((nq,), dtype=torch.float32, device=like.device)
+            flag = self._flag
+            flag.fill_(1.0 if two_phase(kth) else 0.0)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            if float(flag.item()) == 0.0:
+                kth_all = torch.empty((self.world * nq,), dtype=torch.float32, device=like.device)
+                dist.all_gather_into_tensor(kth_all, kth, group=self.group)
+                D = torch.empty((*lead_shape, k), dtype=torch.float32, device=like.device)
+                I = torch.empty((*lead_shape, k), dtype=torch.int64, device=like.device)
+                self.local.search_end([kth_all.data_ptr() + 4 * nq * g for g in range(self.world)], D, I)
+                self.two_phase_used = True
+                return self._exchange_and_merge(D, I, k)
         D, I = run_local(None)
         return self._exchange_and_merge(D, I, k)
 
@@ -168,5 +213,9 @@ class ShardedIndex:
     def search_mixed(self, P, S, alphas: Sequence[float], k: int):
         k = int(k)
         lead = (len(alphas), int(P.shape[0]))
+        two_phase = None
+        if (self.two_phase and self.world > 1 and not self._custom_engine and lead[0] * lead[1] <= 8192
+                and self.path in ("auto", "tensor") and self.precision == "rescore" and self.local.ntotal > 0):
+            two_phase = lambda kth: self.local.search_mixed_begin(P, S, alphas, k, self.row0, kth)  # noqa: E731
         return self._run(P, lead, k, lambda out: self.local.search_mixed(P, S, alphas, k, id_base=self.row0, path=self.path,
-                                                                         **({"out": out} if out else {})))
+                                                                         **({"out": out} if out else {})), two_phase)

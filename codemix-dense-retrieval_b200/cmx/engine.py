@@ -175,6 +175,27 @@ class Shard:
                                           _stream(self.device)))
         return (D, I, flags) if want_flags else (D, I)
 
+    # ---- two-phase search for sharded indexes (device tensors, rescore precision) --------------
+    def search_mixed_begin(self, P, S, alphas: Sequence[float], k: int, id_base: int, kth_out) -> bool:
+        """Phase 1: fused prologue + approximate pass; writes this shard's k-th best approximate score
+        per query to ``kth_out`` [nA*nq] (CUDA float32).  Returns True when the candidate buffers
+        overflowed (every shard must then fall back to ``search_mixed``)."""
+        P = _as_f32_2d(P, self.d, "P")
+        S = _as_f32_2d(S, self.d, "S")
+        assert P.is_cuda and S.is_cuda and kth_out.is_cuda, "two-phase search works on CUDA tensors"
+        nA = len(alphas)
+        a = (C.c_double * nA)(*[float(v) for v in alphas])
+        ovf = C.c_int(0)
+        check(_lib.lib().cmx_search_mixed_begin(self._h, _ptr(P)[0], _ptr(S)[0], int(P.shape[0]), a, nA, int(k), int(id_base),
+                                                int(kth_out.data_ptr()), C.byref(ovf), _stream(self.device)))
+        return bool(ovf.value)
+
+    def search_end(self, kth_ptrs: Sequence[int], D, I) -> None:
+        """Phase 2: exact rescoring of the rows that can still reach the global top-k, given every
+        shard's k-th best approximate scores (device pointers, peer memory allowed)."""
+        arr = (C.c_void_p * len(kth_ptrs))(*[int(p) for p in kth_ptrs])
+        check(_lib.lib().cmx_search_end(self._h, arr, len(kth_ptrs), int(D.data_ptr()), int(I.data_ptr()), _stream(self.device)))
+
     def last_stats(self) -> dict:
         st = _lib.SearchStats()
         check(_lib.lib().cmx_index_last_stats(self._h, C.byref(st)))

@@ -85,6 +85,10 @@ struct cmx_index {
   uint32_t* q_absmax = nullptr;
   float* margin_buf = nullptr;
   unsigned long long* progress = nullptr;  // tile-progress counter of the tensor kernels
+  // two-phase (sharded) search state between cmx_search_mixed_begin and cmx_search_end
+  bool pending = false;
+  int64_t pend_nq = 0, pend_id_base = 0;
+  int pend_k = 0;
   float* q_scale = nullptr;  // {scale, 1/scale}
   float* D_dev = nullptr; int64_t D_cap = 0;
   int64_t* I_dev = nullptr; int64_t I_cap = 0;
@@ -224,8 +228,12 @@ static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe) {
 // rescore = true: the tensor kernels run ONE fp16 MMA pass (approximate scores), the buffers keep
 // everything within 2*eps(q) of the k-th best approximate score, and the survivors get exact fp32
 // scores at the end; rescore = false: three-pass split precision, scores final as they come
+// defer = true (two-phase sharded search): stop after the last compaction, leaving the candidate
+// superset in the workspace; cmx_search_end rescoring follows once the shards have exchanged their
+// k-th best approximate scores
 static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d,
-                       int64_t id_base, int path, bool rescore, bool safe, cudaStream_t st, bool* overflowed) {
+                       int64_t id_base, int path, bool rescore, bool safe, cudaStream_t st, bool* overflowed,
+                       bool defer = false) {
   if (path != CMX_PATH_TENSOR) rescore = false;
   const int cap = pick_cap(ix, k);
   const int64_t nq_pad = (nq + 127) / 128 * 128;
@@ -289,7 +297,7 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
     if (rescore) {
       // keep the margin band, then (after the last slab) exact fp32 scores + exact top-k
       CMX_TRY(launch_compact(ix->ws, nq, k, 0, D_d, I_d, id_base, st));
-      if (last) CMX_TRY(launch_rescore(ix->X, ix->d, q_d, ix->ws, nq, k, D_d, I_d, id_base, st));
+      if (last && !defer) CMX_TRY(launch_rescore(ix->X, ix->d, q_d, ix->ws, nq, k, D_d, I_d, id_base, RescoreCut(), st));
     } else {
       CMX_TRY(launch_compact(ix->ws, nq, k, last, D_d, I_d, id_base, st));
     }
@@ -710,6 +718,57 @@ int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int64_t nq, 
   CMX_CUDA(cudaStreamSynchronize(st));
   if (g_profiling) cudaEventElapsedTime(&ix->stats.total_ms, e0, e1);
   stats_end(ix);
+  return CMX_OK;
+}
+
+int cmx_search_mixed_begin(cmx_index* ix, const float* P, const float* S, int64_t nq, const double* alphas, int nA, int k,
+                           int64_t id_base, float* kth_out, int* overflowed, void* stream) {
+  CMX_CHECK(ix != nullptr, "null index");
+  CMX_CHECK(nq > 0 && nA > 0, "bad shape");
+  CMX_CHECK(k >= 1 && k <= CMX_MAX_K, "k=%d out of range [1, %d]", k, CMX_MAX_K);
+  CMX_CHECK(P && S && alphas && kth_out && overflowed, "null buffer");
+  const int64_t nqt = nq * (int64_t)nA;
+  CMX_CHECK(nqt <= kQueryChunk, "two-phase search handles at most %lld queries per call", (long long)kQueryChunk);
+  CMX_CHECK(ix->precision == CMX_PRECISION_RESCORE && ix->row_norm_max > 0.f && ix->n > 0,
+            "two-phase search needs the rescore precision and a non-empty index");
+  DevGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  stats_begin(ix, nqt);
+  ix->stats.path = CMX_PATH_TENSOR;
+  ix->pending = false;
+  CMX_TRY(ensure_buf(&ix->q_dev, &ix->q_cap, nqt * (int64_t)ix->d));
+  CMX_TRY(ensure_buf(&ix->flags_dev, &ix->flags_cap, nqt));
+  CMX_TRY(ensure_buf(&ix->w_dev, &ix->w_cap, 2 * (int64_t)nA));
+  CMX_TRY(ensure_buf(&ix->mode_dev, &ix->mode_cap, (int64_t)nA));
+  CMX_TRY(mix_on_device(P, S, nq, ix->d, alphas, nA, ix->q_dev, ix->flags_dev, ix->w_dev, ix->mode_dev, st));
+  bool ovf = false;
+  CMX_TRY(search_pass(ix, ix->q_dev, nqt, k, nullptr, nullptr, id_base, CMX_PATH_TENSOR, true, false, st, &ovf, true));
+  CMX_TRY(launch_kth_approx(ix->ws, nqt, kth_out, st));
+  CMX_CUDA(cudaStreamSynchronize(st));
+  *overflowed = ovf ? 1 : 0;
+  ix->pending = !ovf;
+  ix->pend_nq = nqt;
+  ix->pend_k = k;
+  ix->pend_id_base = id_base;
+  stats_end(ix);
+  return CMX_OK;
+}
+
+int cmx_search_end(cmx_index* ix, const float* const* kth_parts, int nparts, float* D, int64_t* I, void* stream) {
+  CMX_CHECK(ix != nullptr && D && I, "null argument");
+  CMX_CHECK(ix->pending, "cmx_search_end without a successful cmx_search_mixed_begin");
+  CMX_CHECK(nparts >= 0 && nparts <= CMX_MAX_PEERS && (nparts == 0 || kth_parts != nullptr), "bad kth_parts");
+  DevGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  RescoreCut cut;
+  cut.nparts = nparts;
+  for (int i = 0; i < nparts; ++i) cut.kth[i] = kth_parts[i];
+  const int launches0 = (int)g_launches.load();
+  CMX_TRY(launch_rescore(ix->X, ix->d, ix->q_dev, ix->ws, ix->pend_nq, ix->pend_k, D, I, ix->pend_id_base, cut, st));
+  CMX_CUDA(cudaStreamSynchronize(st));
+  ix->pending = false;
+  ix->stats.launches += (int)g_launches.load() - launches0;
+  ix->stats.select_launches += 1;
   return CMX_OK;
 }
 

@@ -75,8 +75,9 @@ __host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row)
 __host__ __device__ __forceinline__ float key_score(uint64_t k) { return ordered_to_f32((uint32_t)(k >> 32)); }
 __host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return 0xffffffffu - (uint32_t)(k & 0xffffffffu); }
 
-#define CMX_MAX_PEERS 16
 #define CMX_NEG_PAD (-3.402823466e+38f) /* FAISS pads IP results with lowest float */
+
+#define CMX_MAX_PEERS 16
 
 // ---- search workspace (device) ----------------------------------------------
 struct SearchWs {
@@ -133,8 +134,13 @@ int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float*
                    int64_t id_base, cudaStream_t st);
 // rescore mode: exact fp32 scores of every surviving candidate from the fp32 row store, then
 // the exact top-k (score desc, row asc) -> D, I
+struct RescoreCut {
+  int nparts = 0;                    // 0: no global cut (single shard)
+  const float* kth[CMX_MAX_PEERS];   // per shard: k-th best approximate score per query (device, maybe peer memory)
+};
+int launch_kth_approx(const SearchWs& ws, int64_t nq, float* out, cudaStream_t st);
 int launch_rescore(const float* X, int d, const float* Q, const SearchWs& ws, int64_t nq, int k, float* D,
-                   int64_t* I, int64_t id_base, cudaStream_t st);
+                   int64_t* I, int64_t id_base, const RescoreCut& cut, cudaStream_t st);
 int launch_merge(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,
                  float* D, int64_t* I, cudaStream_t st);
 

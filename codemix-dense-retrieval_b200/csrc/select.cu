@@ -251,8 +251,9 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
 // dynamic smem: cap keys | next_pow2(k) keys | d floats (the query)
 __global__ void __launch_bounds__(kSelThreads)
 rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, const uint64_t* __restrict__ cand,
-               const uint32_t* __restrict__ cnt, uint32_t* __restrict__ overflow, int cap, int k, int topn,
-               float* __restrict__ D, int64_t* __restrict__ I, int64_t id_base) {
+               const uint32_t* __restrict__ cnt, uint32_t* __restrict__ overflow, const float* __restrict__ margin,
+               const RescoreCut cut, int cap, int k, int topn, float* __restrict__ D, int64_t* __restrict__ I,
+               int64_t id_base) {
   extern __shared__ __align__(16) uint64_t keys[];
   __shared__ SelectShared sh;
   uint64_t* top = keys + cap;
@@ -266,10 +267,19 @@ rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const uint64_t* buf = cand + q * (int64_t)cap;
   const bool vec = (d & 3) == 0;
+  // sharded search: any lower bound of the GLOBAL k-th best approximate score is a valid cut --
+  // the maximum over the shards' local k-th best (read here in place from every shard's array,
+  // peer memory included) shrinks the rows this shard has to rescore by about the shard count
+  float lowest = CMX_NEG_PAD;
+  if (cut.nparts > 0) {
+    float ak = cut.kth[0][q];
+    for (int g = 1; g < cut.nparts; ++g) ak = fmaxf(ak, cut.kth[g][q]);
+    lowest = ak - (margin ? margin[q] : 0.f);
+  }
   for (int i = warp; i < n; i += nwarps) {
     const uint64_t key = buf[i];
     uint64_t out = 0ull;
-    if (key != 0ull) {
+    if (key != 0ull && key_score(key) >= lowest) {
       const uint32_t row = key_row(key);
       const float* x = X + (int64_t)row * d;
       float acc = 0.f;
@@ -331,15 +341,29 @@ int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float*
   return CMX_OK;
 }
 
+// a_k[q] = k-th best approximate score of this shard so far = tau + margin
+__global__ void kth_approx_kernel(const float* __restrict__ tau, const float* __restrict__ margin, int64_t nq,
+                                  float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) out[i] = tau[i] + (margin ? margin[i] : 0.f);
+}
+
+int launch_kth_approx(const SearchWs& ws, int64_t nq, float* out, cudaStream_t st) {
+  if (nq == 0) return CMX_OK;
+  kth_approx_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(ws.tau, ws.margin, nq, out);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
 int launch_rescore(const float* X, int d, const float* Q, const SearchWs& ws, int64_t nq, int k, float* D,
-                   int64_t* I, int64_t id_base, cudaStream_t st) {
+                   int64_t* I, int64_t id_base, const RescoreCut& cut, cudaStream_t st) {
   if (nq == 0) return CMX_OK;
   const int topn = pow2_at_least(k);
   const size_t smem = ((size_t)ws.cap + topn) * sizeof(uint64_t) + (size_t)d * sizeof(float);
   CMX_CHECK(smem <= 220 * 1024, "rescore: d=%d too large for the shared-memory query copy", d);
   CMX_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rescore_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(X, d, Q, ws.cand, ws.cnt, ws.overflow, ws.cap, k, topn, D, I,
-                                                          id_base);
+  rescore_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(X, d, Q, ws.cand, ws.cnt, ws.overflow, ws.margin, cut, ws.cap, k,
+                                                          topn, D, I, id_base);
   CMX_LAUNCHED();
   return CMX_OK;
 }

@@ -126,6 +126,22 @@ CMX_API int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int6
                      const double* alphas, int nA, int k, float* D, int64_t* I, uint8_t* flags,
                      int io_on_device, int64_t id_base, int path, void* stream);
 
+/* ---- two-phase search for row-sharded indexes (rescore precision, device buffers) -------------
+ * A shard that rescored its own k best would do G times the necessary exact work.  Phase 1
+ * (begin) runs the fused prologue and the approximate pass and writes the shard's k-th best
+ * APPROXIMATE score per query to kth_out [nA*nq] (device).  The caller makes every shard's array
+ * visible to the others (all_gather, or peer-mapped memory) and phase 2 (end) rescoring uses
+ * max over shards as a lower bound of the global k-th best: only rows with
+ * approx >= that bound - 2*eps(q) get an exact score.  D, I [nA*nq,k] then hold the shard's exact
+ * hits that can still belong to the global top-k (fewer than k: padded with -1), ready for
+ * cmx_merge_topk(_peers).  *overflowed = 1: the approximate pass overflowed its buffers; every
+ * shard must then use cmx_search_mixed instead (decide collectively).  nA*nq <= 8192. */
+CMX_API int cmx_search_mixed_begin(cmx_index* ix, const float* P, const float* S, int64_t nq,
+                                   const double* alphas, int nA, int k, int64_t id_base,
+                                   float* kth_out, int* overflowed, void* stream);
+CMX_API int cmx_search_end(cmx_index* ix, const float* const* kth_parts, int nparts, float* D,
+                           int64_t* I, void* stream);
+
 /* ---- k-way merge of per-shard results (multi-GPU) ---------------------------
  * new capability (BASELINE north_star (4)); the reference never shards.
  * D_parts [nparts,nq,k], I_parts [nparts,nq,k] -> D [nq,k], I [nq,k]; order:

@@ -19,22 +19,28 @@ X[200_000:200_500] = X[100:600]  # ties across shards
 P = torch.nn.functional.normalize(torch.randn((nq, d), generator=g, device=dev), dim=1)
 S = torch.nn.functional.normalize(torch.randn((nq, d), generator=g, device=dev), dim=1)
 res = {}
-for mode in ("allgather", "p2p"):
+for mode, prec in (("allgather", "rescore"), ("p2p", "rescore"), ("allgather", "split"), ("p2p", "split")):
     idx = ShardedIndex(d, N, device=lr, exchange=mode)
+    idx.set_precision(prec)
     idx.add_local(X[idx.row0:idx.row1].contiguous())
     D, I = idx.search_mixed(P, S, [0.0, 0.5], k)
     D2, I2 = idx.search(P[:5].contiguous(), k)
-    res[mode] = (D.clone(), I.clone(), D2.clone(), I2.clone(), idx.exchange_used)
+    res[(mode, prec)] = (D.clone(), I.clone(), D2.clone(), I2.clone(), idx.exchange_used, idx.two_phase_used)
     del idx
-ok = all(torch.equal(a, b) for a, b in zip(res["allgather"][:4], res["p2p"][:4]))
-single = Shard(d, lr)
-single.add(X)
-Ds, Is = single.search_mixed(P, S, [0.0, 0.5], k)
-ok1 = torch.equal(Ds, res["p2p"][0]) and torch.equal(Is, res["p2p"][1])
+ok = True
+ok1 = True
+for prec in ("rescore", "split"):
+    ok = ok and all(torch.equal(a, b) for a, b in zip(res[("allgather", prec)][:4], res[("p2p", prec)][:4]))
+    single = Shard(d, lr)
+    single.set_precision(prec)
+    single.add(X)
+    Ds, Is = single.search_mixed(P, S, [0.0, 0.5], k)
+    ok1 = ok1 and torch.equal(Ds, res[("p2p", prec)][0]) and torch.equal(Is, res[("p2p", prec)][1])
+    del single
 flag = torch.tensor([int(ok and ok1)], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("check_dist:", "OK" if int(flag) == 1 else "MISMATCH", "exchange modes used:", res["allgather"][4], res["p2p"][4],
+    print("check_dist:", "OK" if int(flag) == 1 else "MISMATCH", "modes used:", {k: v[4:] for k, v in res.items()},
           "p2p==allgather", ok, "sharded==single", ok1, flush=True)
 dist.destroy_process_group()
 sys.exit(0 if int(flag) == 1 else 1)
