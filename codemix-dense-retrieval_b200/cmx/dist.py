@@ -160,21 +160,21 @@ class ShardedIndex:
             flag = self._flag
             flag.fill_(1.0 if two_phase(kth) else 0.0)
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)  # collective fallback decision
-            hdl.barrier(channel=2)  # every rank's kth array is complete and visible
+            hdl.barrier(channel=0)  # every rank's kth array is complete and visible
             if float(flag.item()) == 0.0:
                 self.local.search_end(kth_ptrs, D_loc, I_loc)
                 done = True
                 self.two_phase_used = True
         if not done:
             run_local((D_loc.view(*lead_shape, k), I_loc.view(*lead_shape, k)))
-        hdl.barrier(channel=0)  # every rank's lists are complete and visible
+        hdl.barrier(channel=1)  # every rank's lists are complete and visible
         G = self.world
         q0, q1 = (nq * self.rank) // G, (nq * (self.rank + 1)) // G
         arr = lambda ptrs: (C.c_void_p * G)(*ptrs)  # noqa: E731
         stream = int(torch.cuda.current_stream().cuda_stream)
         _lib.check(_lib.lib().cmx_merge_topk_peers(arr(D_ptrs), arr(I_ptrs), G, nq, k, q0, q1, arr(Do_ptrs), arr(Io_ptrs), G,
                                                    D_out.device.index, stream))
-        hdl.barrier(channel=1)  # every rank's slice has landed in every output buffer
+        hdl.barrier(channel=0)  # every rank's slice has landed in every output buffer
         self.exchange_used = "p2p"
         return D_out.view(*lead_shape, k), I_out.view(*lead_shape, k)
 
