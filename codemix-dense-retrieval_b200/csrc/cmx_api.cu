@@ -4,6 +4,7 @@
 // kernels of prologue.cu / stream_score.cu / tc_score.cu / select.cu.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -318,6 +319,8 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
       cudaEventElapsedTime(&b, ix->ev[4 * s + 1], ix->ev[4 * s + 2]);
       ix->stats.score_ms += a;
       ix->stats.select_ms += b;
+      if (getenv("CMX_DEBUG_SLABS"))
+        fprintf(stderr, "[cmx] slab %d rows %lld score %.3f ms select %.3f ms\n", s, (long long)pl.rows[s], a, b);
     }
   }
   return CMX_OK;

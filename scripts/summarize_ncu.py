@@ -5,6 +5,7 @@ import collections, csv, json, pathlib, subprocess, sys
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 OUT, PROF = ROOT / "gpurun_out", ROOT / "profiles"
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+names = sys.argv[2].split(",") if len(sys.argv) > 2 else ["prof_tc2", "prof_stream2", "prof_compact2"]
 KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__bytes_read.sum.per_second',
@@ -30,7 +31,7 @@ def raw_page(rep):
 
 
 traffic = {}
-for name in ("prof_tc2", "prof_stream2", "prof_compact2"):
+for name in names:
     rep = OUT / f"{name}.ncu-rep"
     if not rep.exists():
         continue
