@@ -222,6 +222,7 @@ __device__ __forceinline__ void epilogue_filter_tile_two_pass(const TcParams& p,
     if (n) chunk_bits |= 1u << c;
   }
   if (!__any_sync(0xffffffffu, total != 0)) return;
+  if (p.flags & 8) return;  // timing experiment: filter only
   uint32_t pos = 0;
   if (total) pos = atomicAdd(&p.cnt[q], total);
   uint64_t* qcand = p.cand + q * (int64_t)p.cap;
@@ -260,6 +261,7 @@ struct EpiStage {
 __device__ __forceinline__ void epilogue_flush(const TcParams& p, const EpiStage& st, int& nst, int64_t q, float inv,
                                                int64_t tile_row0) {
   if (nst == 0) return;
+  if (p.flags & 8) { nst = 0; return; }  // timing experiment: filter only
   const uint32_t pos = atomicAdd(&p.cnt[q], (uint32_t)nst);
   uint64_t* qcand = p.cand + q * (int64_t)p.cap;
   for (int i = 0; i < nst; ++i) {
@@ -1017,6 +1019,8 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   // more than ~6 expected survivors per row and tile (slab right after the dense one): the staging
   // area would be flushed several times per tile with the TMEM buffer held
   p.two_pass = (!dense && expected_pass_rate * 256.0 > 6.0) ? 1 : 0;
+  if (g_tc_flags & 16) p.two_pass = 1;
+  if (g_tc_flags & 32) p.two_pass = 0;
   // corpus-as-M kernel: up to 64 queries with three passes, up to 32 with one pass (measured: at
   // 64 queries and one pass the padded 128-row kernel is faster, 2.7 vs 3.9 ms per sweep)
   if (g_tc_small && nq <= (split ? 64 : 32)) {

@@ -16,11 +16,16 @@ for N in [int(v) for v in sys.argv[1].split(",")]:
     while c * bench.CHUNK < N:
         x = bench.corpus_chunk(c, d, dev)
         sh.add(x[: min(bench.CHUNK, N - c * bench.CHUNK)]); del x; c += 1
-    for prec in ("rescore", "split"):
+    for prec, flags in (("rescore", 0), ("rescore", 16), ("rescore", 32), ("rescore", 8)):
         sh.set_precision(prec)
+        _lib.check(_lib.lib().cmx_debug_set_tensor_flags(flags))
         for _ in range(2):
-            sys.stderr.write(f"--- N={N} {prec}\n"); sys.stderr.flush()
-            sh.search_mixed(P, S, [0.5], 1000)
+            sys.stderr.write(f"--- N={N} {prec} flags={flags}\n"); sys.stderr.flush()
+            try:
+                sh.search_mixed(P, S, [0.5], 1000)
+            except Exception as e:
+                sys.stderr.write(f"error {e}\n")
         st = sh.last_stats()
-        print(N, prec, st, flush=True)
+        print(N, prec, flags, st, flush=True)
+    _lib.check(_lib.lib().cmx_debug_set_tensor_flags(0))
     del sh; torch.cuda.empty_cache()
