@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "allgather"],
                     help="multi-GPU merge: fused peer-memory kernel (p2p) or NCCL all_gather + merge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-times", action="store_true", help="after the timed runs, print a per-stage breakdown (extra syncs)")
     ap.add_argument("--cpu-sample-queries", type=int, default=512)
     return ap.parse_args()
 
@@ -333,6 +334,15 @@ def run_cmx(a) -> None:
         launches = int(tsum[2])
     else:
         t_e2e_ms, score_ms_max = t_e2e * 1e3, score_ms
+
+    if a.stage_times and world > 1:
+        index.profile = True
+        index.timing = {}
+        for _ in range(a.steps):
+            step_device()
+        if rank == 0:
+            print("stage_ms_per_step", {k2: round(v / a.steps, 3) for k2, v in index.timing.items()}, index.local.last_stats(), file=sys.stderr)
+        index.profile = False
 
     # light self-check of the timed result (full parity lives in tests/)
     ok = bool((D[0, :, 1:] <= D[0, :, :-1]).all()) and int(I.min()) >= 0 and int(I.max()) < N

@@ -74,12 +74,24 @@ class ShardedIndex:
         # rescore precision + several shards: exchange approximate k-th scores before the exact rescoring
         self.two_phase = True
         self.two_phase_used = False
+        self.profile = False
+        self.timing = {}
+        self._t_last = 0.0
         self.precision = "rescore"
         self._flag = None
         if self.world > 1 and torch is not None and torch.cuda.is_available() and self._default_engine:
             self._flag = torch.zeros((1,), dtype=torch.float32,
                                      device=torch.device("cuda", torch.cuda.current_device() if device is None else device))
         self._custom_engine = engine_factory is not None and not hasattr(self.local, "_h")
+
+    def _tick(self, name: str) -> None:
+        import time
+
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if name != "start":
+            self.timing[name] = self.timing.get(name, 0.0) + (now - self._t_last) * 1e3
+        self._t_last = now
 
     def set_precision(self, mode: str) -> None:
         """'rescore' (default) or 'split' arithmetic of the tensor path (see cmx.h)."""
@@ -153,18 +165,24 @@ class ShardedIndex:
         D_out, _, Do_ptrs = bufs["D_out"]
         I_out, _, Io_ptrs = bufs["I_out"]
         done = False
+        tm = self._tick if self.profile else (lambda name: None)
+        tm("start")
         if two_phase is not None:
             # rescore precision: exchange the shards' k-th best APPROXIMATE scores first, so that each
             # shard rescoring only touches rows that can still reach the GLOBAL top-k
             kth, _, kth_ptrs = bufs["kth"]
             flag = self._flag
             flag.fill_(1.0 if two_phase(kth) else 0.0)
+            tm("begin")
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)  # collective fallback decision
             hdl.barrier(channel=0)  # every rank's kth array is complete and visible
-            if float(flag.item()) == 0.0:
+            ok = float(flag.item()) == 0.0
+            tm("flag+barrier")
+            if ok:
                 self.local.search_end(kth_ptrs, D_loc, I_loc)
                 done = True
                 self.two_phase_used = True
+                tm("rescore")
         if not done:
             run_local((D_loc.view(*lead_shape, k), I_loc.view(*lead_shape, k)))
         hdl.barrier(channel=1)  # every rank's lists are complete and visible
@@ -175,6 +193,7 @@ class ShardedIndex:
         _lib.check(_lib.lib().cmx_merge_topk_peers(arr(D_ptrs), arr(I_ptrs), G, nq, k, q0, q1, arr(Do_ptrs), arr(Io_ptrs), G,
                                                    D_out.device.index, stream))
         hdl.barrier(channel=0)  # every rank's slice has landed in every output buffer
+        tm("merge")
         self.exchange_used = "p2p"
         return D_out.view(*lead_shape, k), I_out.view(*lead_shape, k)
 
