@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
     L.cmx_search_mixed.argtypes = [vp, f32p, f32p, i64, C.POINTER(C.c_double), i32, i32, f32p, vp, vp, i32, i64, i32, vp]
     L.cmx_search_mixed_begin.argtypes = [vp, f32p, f32p, i64, C.POINTER(C.c_double), i32, i32, i64, vp, C.POINTER(i32), vp]
     L.cmx_search_end.argtypes = [vp, vp, i32, f32p, vp, vp]
+    L.cmx_union_kth.argtypes = [vp, i32, i64, i32, i64, i64, vp, i32, i32, vp]
     L.cmx_merge_topk.argtypes = [f32p, vp, i32, i64, i32, f32p, vp, i32, i32, vp]
     L.cmx_merge_topk_peers.argtypes = [vp, vp, i32, i64, i32, i64, i64, vp, vp, i32, i32, vp]
     cpp, i64p = C.POINTER(C.c_char_p), C.POINTER(i64)
@@ -94,7 +95,7 @@ def lib() -> C.CDLL:
     for name in (
         "cmx_device_count cmx_index_create cmx_index_free cmx_index_reserve cmx_index_add cmx_index_reset "
         "cmx_index_ntotal cmx_index_dim cmx_index_device cmx_index_reconstruct cmx_index_data cmx_index_search "
-        "cmx_mix_normalize cmx_search_mixed cmx_search_mixed_begin cmx_search_end cmx_merge_topk cmx_merge_topk_peers cmx_trec_mono cmx_trec_bilingual cmx_index_last_stats cmx_set_profiling "
+        "cmx_mix_normalize cmx_search_mixed cmx_search_mixed_begin cmx_search_end cmx_union_kth cmx_merge_topk cmx_merge_topk_peers cmx_trec_mono cmx_trec_bilingual cmx_index_last_stats cmx_set_profiling "
         "cmx_index_set_cand_capacity cmx_index_set_precision cmx_set_default_precision cmx_debug_set_tensor_tile cmx_debug_set_stream_variant cmx_debug_set_tensor_flags cmx_debug_set_tensor_pair cmx_debug_set_tensor_small cmx_debug_set_tensor_window"
     ).split():
         getattr(L, name).restype = i32

@@ -139,7 +139,8 @@ class ShardedIndex:
         grp = self.group if self.group is not None else dist.group.WORLD
         bufs = {}
         for name, dt, numel in (("D_loc", torch.float32, nq * k), ("I_loc", torch.int64, nq * k),
-                                ("D_out", torch.float32, nq * k), ("I_out", torch.int64, nq * k), ("kth", torch.float32, nq)):
+                                ("D_out", torch.float32, nq * k), ("I_out", torch.int64, nq * k),
+                                ("ascore", torch.float32, nq * k), ("kth", torch.float32, nq)):
             t = symm_mem.empty((numel,), dtype=dt, device=dev)
             hdl = symm_mem.rendezvous(t, grp)
             bufs[name] = (t, hdl, [int(p) for p in hdl.buffer_ptrs])
@@ -170,29 +171,38 @@ class ShardedIndex:
         if two_phase is not None:
             # rescore precision: exchange the shards' k-th best APPROXIMATE scores first, so that each
             # shard rescoring only touches rows that can still reach the GLOBAL top-k
+            from .engine import union_kth
+
+            ascore, _, as_ptrs = bufs["ascore"]
             kth, _, kth_ptrs = bufs["kth"]
             flag = self._flag
-            flag.fill_(1.0 if two_phase(kth) else 0.0)
+            flag.fill_(1.0 if two_phase(ascore) else 0.0)
             tm("begin")
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)  # collective fallback decision
-            hdl.barrier(channel=0)  # every rank's kth array is complete and visible
+            hdl.barrier(channel=0)  # every rank's approximate top-k scores are complete and visible
             ok = float(flag.item()) == 0.0
             tm("flag+barrier")
             if ok:
-                self.local.search_end(kth_ptrs, D_loc, I_loc)
+                # global k-th best approximate score of MY slice of the queries, from all shards' lists
+                # (peer reads), written into every shard's kth array (peer stores)
+                G = self.world
+                union_kth(as_ptrs, nq, k, (nq * self.rank) // G, (nq * (self.rank + 1)) // G, kth_ptrs, kth.device.index)
+                hdl.barrier(channel=1)
+                tm("union_kth")
+                self.local.search_end([kth_ptrs[self.rank]], D_loc, I_loc)
                 done = True
                 self.two_phase_used = True
                 tm("rescore")
         if not done:
             run_local((D_loc.view(*lead_shape, k), I_loc.view(*lead_shape, k)))
-        hdl.barrier(channel=1)  # every rank's lists are complete and visible
+        hdl.barrier(channel=0)  # every rank's lists are complete and visible
         G = self.world
         q0, q1 = (nq * self.rank) // G, (nq * (self.rank + 1)) // G
         arr = lambda ptrs: (C.c_void_p * G)(*ptrs)  # noqa: E731
         stream = int(torch.cuda.current_stream().cuda_stream)
         _lib.check(_lib.lib().cmx_merge_topk_peers(arr(D_ptrs), arr(I_ptrs), G, nq, k, q0, q1, arr(Do_ptrs), arr(Io_ptrs), G,
                                                    D_out.device.index, stream))
-        hdl.barrier(channel=0)  # every rank's slice has landed in every output buffer
+        hdl.barrier(channel=1)  # every rank's slice has landed in every output buffer
         tm("merge")
         self.exchange_used = "p2p"
         return D_out.view(*lead_shape, k), I_out.view(*lead_shape, k)
@@ -208,17 +218,22 @@ class ShardedIndex:
                 self.exchange_error = repr(exc)
         if two_phase is not None and self.world > 1 and not self._custom_engine and torch is not None \
                 and isinstance(like, torch.Tensor) and like.is_cuda:
+            from .engine import union_kth
+
             nq = int(np.prod(lead_shape))
-            kth = torch.empty((nq,), dtype=torch.float32, device=like.device)
+            ascore = torch.empty((nq * k,), dtype=torch.float32, device=like.device)
             flag = self._flag
-            flag.fill_(1.0 if two_phase(kth) else 0.0)
+            flag.fill_(1.0 if two_phase(ascore) else 0.0)
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
             if float(flag.item()) == 0.0:
-                kth_all = torch.empty((self.world * nq,), dtype=torch.float32, device=like.device)
-                dist.all_gather_into_tensor(kth_all, kth, group=self.group)
+                as_all = torch.empty((self.world * nq * k,), dtype=torch.float32, device=like.device)
+                dist.all_gather_into_tensor(as_all, ascore, group=self.group)
+                kth = torch.empty((nq,), dtype=torch.float32, device=like.device)
+                union_kth([as_all.data_ptr() + 4 * nq * k * g for g in range(self.world)], nq, k, 0, nq, [kth.data_ptr()],
+                          like.device.index)
                 D = torch.empty((*lead_shape, k), dtype=torch.float32, device=like.device)
                 I = torch.empty((*lead_shape, k), dtype=torch.int64, device=like.device)
-                self.local.search_end([kth_all.data_ptr() + 4 * nq * g for g in range(self.world)], D, I)
+                self.local.search_end([kth.data_ptr()], D, I)
                 self.two_phase_used = True
                 return self._exchange_and_merge(D, I, k)
         D, I = run_local(None)

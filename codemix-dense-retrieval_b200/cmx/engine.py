@@ -177,9 +177,9 @@ class Shard:
 
     # ---- two-phase search for sharded indexes (device tensors, rescore precision) --------------
     def search_mixed_begin(self, P, S, alphas: Sequence[float], k: int, id_base: int, kth_out) -> bool:
-        """Phase 1: fused prologue + approximate pass; writes this shard's k-th best approximate score
-        per query to ``kth_out`` [nA*nq] (CUDA float32).  Returns True when the candidate buffers
-        overflowed (every shard must then fall back to ``search_mixed``)."""
+        """Phase 1: fused prologue + approximate pass; writes this shard's k best approximate scores
+        per query to ``kth_out`` [nA*nq*k] (CUDA float32, order arbitrary).  Returns True when the
+        candidate buffers overflowed (every shard must then fall back to ``search_mixed``)."""
         P = _as_f32_2d(P, self.d, "P")
         S = _as_f32_2d(S, self.d, "S")
         assert P.is_cuda and S.is_cuda and kth_out.is_cuda, "two-phase search works on CUDA tensors"
@@ -227,6 +227,15 @@ def mix_normalize(P, S, alphas: Sequence[float], device: int = 0, want_flags: bo
     check(_lib.lib().cmx_mix_normalize(_ptr(P)[0], _ptr(S)[0], nq, d, a, nA, _ptr(out)[0], _ptr(flags)[0],
                                        1 if on_dev else 0, int(device), _stream(device)))
     return (out, flags) if want_flags else out
+
+
+def union_kth(score_ptrs: Sequence[int], nq: int, k: int, q0: int, q1: int, out_ptrs: Sequence[int], device: int) -> None:
+    """Global k-th best approximate score of queries [q0, q1) over all shards' exported lists
+    (device pointers, peer memory allowed), written to every ``out_ptrs[o][q]``.  Asynchronous."""
+    parts = (C.c_void_p * len(score_ptrs))(*[int(p) for p in score_ptrs])
+    outs = (C.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
+    check(_lib.lib().cmx_union_kth(parts, len(score_ptrs), int(nq), int(k), int(q0), int(q1), outs, len(out_ptrs), int(device),
+                                   _stream(device)))
 
 
 def merge_topk(D_parts, I_parts, k: Optional[int] = None, device: int = 0):

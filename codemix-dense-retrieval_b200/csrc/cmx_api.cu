@@ -725,11 +725,11 @@ int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int64_t nq, 
 }
 
 int cmx_search_mixed_begin(cmx_index* ix, const float* P, const float* S, int64_t nq, const double* alphas, int nA, int k,
-                           int64_t id_base, float* kth_out, int* overflowed, void* stream) {
+                           int64_t id_base, float* scores_out, int* overflowed, void* stream) {
   CMX_CHECK(ix != nullptr, "null index");
   CMX_CHECK(nq > 0 && nA > 0, "bad shape");
   CMX_CHECK(k >= 1 && k <= CMX_MAX_K, "k=%d out of range [1, %d]", k, CMX_MAX_K);
-  CMX_CHECK(P && S && alphas && kth_out && overflowed, "null buffer");
+  CMX_CHECK(P && S && alphas && scores_out && overflowed, "null buffer");
   const int64_t nqt = nq * (int64_t)nA;
   CMX_CHECK(nqt <= kQueryChunk, "two-phase search handles at most %lld queries per call", (long long)kQueryChunk);
   CMX_CHECK(ix->precision == CMX_PRECISION_RESCORE && ix->row_norm_max > 0.f && ix->n > 0,
@@ -746,7 +746,7 @@ int cmx_search_mixed_begin(cmx_index* ix, const float* P, const float* S, int64_
   CMX_TRY(mix_on_device(P, S, nq, ix->d, alphas, nA, ix->q_dev, ix->flags_dev, ix->w_dev, ix->mode_dev, st));
   bool ovf = false;
   CMX_TRY(search_pass(ix, ix->q_dev, nqt, k, nullptr, nullptr, id_base, CMX_PATH_TENSOR, true, false, st, &ovf, true));
-  CMX_TRY(launch_kth_approx(ix->ws, nqt, kth_out, st));
+  CMX_TRY(launch_export_scores(ix->ws, nqt, k, scores_out, st));
   CMX_CUDA(cudaStreamSynchronize(st));
   *overflowed = ovf ? 1 : 0;
   ix->pending = !ovf;
@@ -755,6 +755,18 @@ int cmx_search_mixed_begin(cmx_index* ix, const float* P, const float* S, int64_
   ix->pend_id_base = id_base;
   stats_end(ix);
   return CMX_OK;
+}
+
+int cmx_union_kth(const float* const* score_parts, int nparts, int64_t nq, int k, int64_t q0, int64_t q1,
+                  float* const* kth_outs, int nouts, int device, void* stream) {
+  CMX_CHECK(score_parts && kth_outs, "null pointer table");
+  CMX_CHECK(k >= 1 && k <= CMX_MAX_K, "k=%d out of range [1, %d]", k, CMX_MAX_K);
+  CMX_CHECK(q0 >= 0 && q0 <= q1 && q1 <= nq, "bad query slice");
+  int ndev = 0;
+  CMX_TRY(cmx_device_count(&ndev));
+  CMX_CHECK(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+  DevGuard g(device);
+  return launch_union_kth(score_parts, nparts, k, q0, q1, kth_outs, nouts, (cudaStream_t)stream);
 }
 
 int cmx_search_end(cmx_index* ix, const float* const* kth_parts, int nparts, float* D, int64_t* I, void* stream) {

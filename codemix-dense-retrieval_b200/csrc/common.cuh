@@ -139,6 +139,9 @@ struct RescoreCut {
   const float* kth[CMX_MAX_PEERS];   // per shard: k-th best approximate score per query (device, maybe peer memory)
 };
 int launch_kth_approx(const SearchWs& ws, int64_t nq, float* out, cudaStream_t st);
+int launch_export_scores(const SearchWs& ws, int64_t nq, int k, float* out, cudaStream_t st);
+int launch_union_kth(const float* const* parts, int nparts, int k, int64_t q0, int64_t q1, float* const* outs, int nouts,
+                     cudaStream_t st);
 int launch_rescore(const float* X, int d, const float* Q, const SearchWs& ws, int64_t nq, int k, float* D,
                    int64_t* I, int64_t id_base, const RescoreCut& cut, cudaStream_t st);
 int launch_merge(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,

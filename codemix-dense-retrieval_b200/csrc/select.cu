@@ -348,6 +348,93 @@ __global__ void kth_approx_kernel(const float* __restrict__ tau, const float* __
   if (i < nq) out[i] = tau[i] + (margin ? margin[i] : 0.f);
 }
 
+// Export the shard's k best APPROXIMATE scores per query (order arbitrary, short lists padded with
+// lowest-float) so that the shards can find the GLOBAL k-th best approximate score together.
+__global__ void __launch_bounds__(256)
+export_scores_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, const float* __restrict__ tau,
+                     const float* __restrict__ margin, int cap, int k, float* __restrict__ out) {
+  __shared__ uint32_t s_n;
+  const int64_t q = blockIdx.x;
+  const int n = (int)min(cnt[q], (uint32_t)cap);
+  const float ak = tau[q] + (margin ? margin[q] : 0.f);  // local k-th best approximate score (or lower)
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const uint64_t* buf = cand + q * (int64_t)cap;
+  float* o = out + q * (int64_t)k;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t key = buf[i];
+    if (key != 0ull) {
+      const float s = key_score(key);
+      if (s >= ak) {
+        const uint32_t pos = atomicAdd(&s_n, 1u);
+        if (pos < (uint32_t)k) o[pos] = s;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = (int)min(s_n, (uint32_t)k) + threadIdx.x; i < k; i += blockDim.x) o[i] = CMX_NEG_PAD;
+}
+
+int launch_export_scores(const SearchWs& ws, int64_t nq, int k, float* out, cudaStream_t st) {
+  if (nq == 0) return CMX_OK;
+  export_scores_kernel<<<(unsigned)nq, 256, 0, st>>>(ws.cand, ws.cnt, ws.tau, ws.margin, ws.cap, k, out);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+// GLOBAL k-th best approximate score of queries [q0, q1): the k-th largest of the union of every
+// shard's exported list, read in place (peer memory), written into every shard's kth array.
+struct UnionArgs {
+  const float* parts[CMX_MAX_PEERS];
+  float* outs[CMX_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(kSelThreads)
+union_kth_kernel(const UnionArgs a, int nparts, int nouts, int64_t q0, int k) {
+  extern __shared__ __align__(16) uint64_t keys[];
+  __shared__ SelectShared sh;
+  const int64_t q = q0 + blockIdx.x;
+  const int n_all = nparts * k;
+  for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+    const int g = i / k, pos = i - g * k;
+    keys[i] = make_key(a.parts[g][q * k + pos], (uint32_t)i);  // distinct keys; padding sorts last
+  }
+  __syncthreads();
+  float v;
+  if (n_all > k) v = key_score(block_kth_largest(keys, n_all, k, sh));
+  else {
+    // single part: the k-th best is the minimum of the list
+    float m = __int_as_float(0x7f800000);
+    for (int i = threadIdx.x; i < n_all; i += blockDim.x) m = fminf(m, key_score(keys[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float red[32];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fminf(m, red[w]);
+    v = m;
+  }
+  if (threadIdx.x == 0)
+    for (int o = 0; o < nouts; ++o) a.outs[o][q] = v;
+}
+
+int launch_union_kth(const float* const* parts, int nparts, int k, int64_t q0, int64_t q1, float* const* outs, int nouts,
+                     cudaStream_t st) {
+  if (q1 <= q0) return CMX_OK;
+  CMX_CHECK(nparts >= 1 && nparts <= CMX_MAX_PEERS && nouts >= 1 && nouts <= CMX_MAX_PEERS, "union_kth: at most %d parts",
+            CMX_MAX_PEERS);
+  const size_t smem = (size_t)nparts * k * sizeof(uint64_t);
+  CMX_CHECK(smem <= 200 * 1024, "union_kth: nparts*k = %d too large", nparts * k);
+  UnionArgs a;
+  for (int g = 0; g < nparts; ++g) a.parts[g] = parts[g];
+  for (int o = 0; o < nouts; ++o) a.outs[o] = outs[o];
+  CMX_CUDA(cudaFuncSetAttribute(union_kth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  union_kth_kernel<<<(unsigned)(q1 - q0), kSelThreads, smem, st>>>(a, nparts, nouts, q0, k);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
 int launch_kth_approx(const SearchWs& ws, int64_t nq, float* out, cudaStream_t st) {
   if (nq == 0) return CMX_OK;
   kth_approx_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(ws.tau, ws.margin, nq, out);

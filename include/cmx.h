@@ -127,18 +127,22 @@ CMX_API int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int6
                      int io_on_device, int64_t id_base, int path, void* stream);
 
 /* ---- two-phase search for row-sharded indexes (rescore precision, device buffers) -------------
- * A shard that rescored its own k best would do G times the necessary exact work.  Phase 1
- * (begin) runs the fused prologue and the approximate pass and writes the shard's k-th best
- * APPROXIMATE score per query to kth_out [nA*nq] (device).  The caller makes every shard's array
- * visible to the others (all_gather, or peer-mapped memory) and phase 2 (end) rescoring uses
- * max over shards as a lower bound of the global k-th best: only rows with
- * approx >= that bound - 2*eps(q) get an exact score.  D, I [nA*nq,k] then hold the shard's exact
- * hits that can still belong to the global top-k (fewer than k: padded with -1), ready for
- * cmx_merge_topk(_peers).  *overflowed = 1: the approximate pass overflowed its buffers; every
- * shard must then use cmx_search_mixed instead (decide collectively).  nA*nq <= 8192. */
+ * A shard that rescored its own k best would do G times the necessary exact work.
+ *  1. cmx_search_mixed_begin: fused prologue + approximate pass; writes the shard's k best
+ *     APPROXIMATE scores per query to scores_out [nA*nq, k] (order arbitrary, short lists padded
+ *     with lowest-float).  *overflowed = 1: the approximate pass overflowed its buffers; every
+ *     shard must then use cmx_search_mixed instead (decide collectively).  nA*nq <= 8192.
+ *  2. cmx_union_kth: the GLOBAL k-th best approximate score of queries [q0, q1) = k-th largest of
+ *     the union of all shards' lists, read in place (score_parts[g] may be peer memory) and
+ *     written to every kth_outs[o][q] (local or peer).  Asynchronous on `stream`.
+ *  3. cmx_search_end: exact fp32 rescoring of the rows with approx >= max_p kth_parts[p][q] -
+ *     2*eps(q) only; D, I [nA*nq,k] then hold the shard's exact hits that can still belong to the
+ *     global top-k (fewer than k: padded with -1), ready for cmx_merge_topk(_peers). */
 CMX_API int cmx_search_mixed_begin(cmx_index* ix, const float* P, const float* S, int64_t nq,
                                    const double* alphas, int nA, int k, int64_t id_base,
-                                   float* kth_out, int* overflowed, void* stream);
+                                   float* scores_out, int* overflowed, void* stream);
+CMX_API int cmx_union_kth(const float* const* score_parts, int nparts, int64_t nq, int k, int64_t q0,
+                          int64_t q1, float* const* kth_outs, int nouts, int device, void* stream);
 CMX_API int cmx_search_end(cmx_index* ix, const float* const* kth_parts, int nparts, float* D,
                            int64_t* I, void* stream);
 
