@@ -50,6 +50,11 @@ def parse_args():
                     help="tensor-path arithmetic: one fp16 MMA pass + exact fp32 rescoring (default) or 3-pass split precision")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "allgather"],
                     help="multi-GPU merge: fused peer-memory kernel (p2p) or NCCL all_gather + merge")
+    ap.add_argument("--data", default="iid", choices=["iid", "aniso", "shift"],
+                    help="synthetic corpus: iid = normalize(N(0,I)) (default, SURVEY 8d); aniso = normalize(g + 1.5 sqrt(d) u), "
+                         "one shared direction u, scores ~0.7 like real embedding cosines (SURVEY 8d variant); shift = iid "
+                         "first half, second half and all queries leaning towards one direction (EN rows then ZH rows of "
+                         "the bilingual index: not stationary in file order)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-times", action="store_true", help="after the timed runs, print a per-stage breakdown (extra syncs)")
     ap.add_argument("--cpu-sample-queries", type=int, default=512)
@@ -59,7 +64,20 @@ def parse_args():
 def workload_name(a) -> str:
     full = (a.rows, a.dim, a.nq, a.k) == (N_FULL, D_FULL, NQ_FULL, K_FULL)
     base = "C2 (BASELINE configs[1]): EN monolingual full mMARCO shape" if full else "REDUCED development shape"
-    return f"{base}: {a.rows} x {a.dim} fp32 flat-IP, {a.nq} queries, alpha={ALPHA}, k={a.k}"
+    var = "" if a.data == "iid" else f", data variant {a.data}"
+    return f"{base}: {a.rows} x {a.dim} fp32 flat-IP, {a.nq} queries, alpha={ALPHA}, k={a.k}{var}"
+
+
+DATA = "iid"      # set from --data
+ROWS_TOTAL = N_FULL
+
+
+def _direction(d: int, device):
+    import torch
+
+    g = torch.Generator(device="cpu").manual_seed(7)
+    u = torch.nn.functional.normalize(torch.randn((1, d), generator=g), dim=1)
+    return u.to(device)
 
 
 def make_queries(nq: int, d: int, device):
@@ -67,7 +85,12 @@ def make_queries(nq: int, d: int, device):
 
     g1 = torch.Generator(device=device).manual_seed(42)
     g2 = torch.Generator(device=device).manual_seed(43)
-    P = torch.nn.functional.normalize(torch.randn((nq, d), generator=g1, device=device), dim=1)
+    P = torch.randn((nq, d), generator=g1, device=device)
+    if DATA == "aniso":
+        P = P + 1.5 * (d ** 0.5) * _direction(d, device)
+    elif DATA == "shift":
+        P = P + 0.5 * (d ** 0.5) * _direction(d, device)
+    P = torch.nn.functional.normalize(P, dim=1)
     G = torch.nn.functional.normalize(torch.randn((nq, d), generator=g2, device=device), dim=1)
     S = torch.nn.functional.normalize(0.8 * P + 0.6 * G, dim=1)
     return P.contiguous(), S.contiguous()
@@ -79,6 +102,11 @@ def corpus_chunk(c: int, d: int, device):
 
     g = torch.Generator(device=device).manual_seed(1234 + c)
     x = torch.randn((CHUNK, d), generator=g, device=device)
+    if DATA == "aniso":
+        x += 1.5 * (d ** 0.5) * _direction(d, device)
+    elif DATA == "shift":  # rows of the second half of the corpus lean towards u
+        rows = torch.arange(c * CHUNK, (c + 1) * CHUNK, device=device)
+        x += (rows >= ROWS_TOTAL // 2).to(x.dtype)[:, None] * (0.5 * (d ** 0.5)) * _direction(d, device)
     return torch.nn.functional.normalize(x, dim=1)
 
 
@@ -223,7 +251,7 @@ def run_reference(a) -> None:
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * a.nq / qps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic" if DATA == "iid" else f"synthetic ({DATA})",
         "config": {"workload": workload_name(a), "cache": "inputs_larger_than_L2"},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "cpu_count": os.cpu_count()},
@@ -416,7 +444,7 @@ def run_cmx(a) -> None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": ("f16-filter+f32-exact-rescore" if a.precision == "rescore" else "f16x3-split+f32acc") if used_tensor else "f32",
-        "data": "synthetic",
+        "data": "synthetic" if DATA == "iid" else f"synthetic ({DATA})",
         "config": {"workload": workload_name(a), "rows": N, "dim": d, "queries": nq, "k": k, "alpha": ALPHA,
                    "parallelism": f"corpus row shards x{world}, exchange={index.exchange_used}, two_phase_rescore={index.two_phase_used}" if world > 1 else "single GPU",
                    "cache": "inputs_larger_than_L2 (corpus %.1f GB per GPU)" % (n_local * d * 4 / 1e9),
@@ -438,6 +466,8 @@ def run_cmx(a) -> None:
 
 def main():
     a = parse_args()
+    global DATA, ROWS_TOTAL
+    DATA, ROWS_TOTAL = a.data, a.rows
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -239,6 +239,14 @@ class ShardedIndex:
         D, I = run_local(None)
         return self._exchange_and_merge(D, I, k)
 
+    def _sync_error_bounds(self) -> None:
+        """Two-phase search cuts every shard's candidates at (global k-th approximate score - margin):
+        the margin must come from the corpus maxima over ALL shards (include/cmx.h)."""
+        b = torch.tensor(self.local.error_bounds(), dtype=torch.float32, device=self._flag.device)
+        dist.all_reduce(b, op=dist.ReduceOp.MAX, group=self.group)
+        nmax, rmax = (float(v) for v in b.tolist())
+        self.local.raise_error_bounds(nmax, rmax)
+
     def search(self, x, k: int):
         k = int(k)
         nq = int(x.shape[0]) if hasattr(x, "shape") and len(x.shape) == 2 else 1
@@ -250,6 +258,7 @@ class ShardedIndex:
         two_phase = None
         if (self.two_phase and self.world > 1 and not self._custom_engine and lead[0] * lead[1] <= 8192
                 and self.path in ("auto", "tensor") and self.precision == "rescore" and self.local.ntotal > 0):
+            self._sync_error_bounds()
             two_phase = lambda kth: self.local.search_mixed_begin(P, S, alphas, k, self.row0, kth)  # noqa: E731
         return self._run(P, lead, k, lambda out: self.local.search_mixed(P, S, alphas, k, id_base=self.row0, path=self.path,
                                                                          **({"out": out} if out else {})), two_phase)

@@ -73,6 +73,8 @@ struct cmx_index {
   uint32_t absmax_bits = 0;  // max |x| over all finite stored elements
   uint32_t* absmax_dev = nullptr;   // [2]: absmax bits, max row norm bits
   float row_norm_max = 0.f;  // max ||row||_2 over finite rows (rescore-mode error bound)
+  float row_resid_max = 0.f;  // max ||row - hi plane row||_2 over the rows split so far
+  float norm_floor = 0.f, resid_floor = 0.f;  // lower limits set from outside (maxima over all shards)
   int precision = CMX_PRECISION_RESCORE;  // set from the process default at creation
   // search workspace
   SearchWs ws;
@@ -145,6 +147,7 @@ static int ensure_planes(cmx_index* ix, bool need_lo, cudaStream_t st) {
     ix->plane_rows = 0;
     ix->lo_rows = 0;
     ix->plane_scale = want_scale;
+    ix->row_resid_max = 0.f;
   }
   if (ix->plane_cap < ix->cap_rows || !ix->Bhi) {
     if (ix->Bhi) { cudaFree(ix->Bhi); ix->Bhi = nullptr; }
@@ -177,6 +180,14 @@ static int ensure_planes(cmx_index* ix, bool need_lo, cudaStream_t st) {
   if (r0 < ix->n) {
     CMX_TRY(launch_split_planes(ix->X + r0 * ix->d, ix->n - r0, ix->d, ix->d_pad, nullptr, ix->plane_scale,
                                 ix->Bhi + r0 * ix->d_pad, need_lo ? ix->Blo + r0 * ix->d_pad : nullptr, st));
+    // what the hi plane alone loses of each new row (error bound of the one-pass scorer)
+    CMX_CUDA(cudaMemsetAsync(ix->absmax_dev + 1, 0, sizeof(uint32_t), st));
+    CMX_TRY(launch_row_resid_max(ix->X + r0 * ix->d, ix->Bhi + r0 * ix->d_pad, ix->n - r0, ix->d, ix->d_pad,
+                                 1.0f / ix->plane_scale, ix->absmax_dev + 1, st));
+    float res = 0.f;
+    CMX_CUDA(cudaMemcpyAsync(&res, ix->absmax_dev + 1, sizeof(float), cudaMemcpyDeviceToHost, st));
+    CMX_CUDA(cudaStreamSynchronize(st));
+    ix->row_resid_max = std::max(ix->row_resid_max, res);
     ix->plane_rows = ix->n;
     if (need_lo) ix->lo_rows = ix->n;
   }
@@ -225,6 +236,21 @@ static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe) {
   return pl;
 }
 
+// Block multiplier of the tensor path's processing order (TcParams::perm): the odd-or-not integer
+// nearest to nblk / golden ratio that is coprime to nblk.  j -> (j * perm) mod nblk is then a
+// permutation of the blocks whose every prefix is spread evenly over the corpus (three-distance
+// theorem), so thresholds learnt on the first slabs hold for a corpus that is not stationary in
+// file order (EN rows then ZH rows in the bilingual index; passages grouped by source document).
+static int g_block_order = 1;  // 0: file order (experiments / adversarial tests)
+static uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
+static uint64_t pick_perm(int64_t nblk) {
+  if (!g_block_order || nblk < 3) return 1;
+  uint64_t p = (uint64_t)((double)nblk * 0.6180339887498949);
+  if (p < 1) p = 1;
+  while (gcd_u64(p, (uint64_t)nblk) != 1) ++p;  // nblk - 1 is always coprime, so this ends below nblk
+  return p;
+}
+
 // one pass over the corpus for queries q_d[0..nq) (nq <= kQueryChunk)
 // rescore = true: the tensor kernels run ONE fp16 MMA pass (approximate scores), the buffers keep
 // everything within 2*eps(q) of the k-th best approximate score, and the survivors get exact fp32
@@ -263,12 +289,12 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
     }
     CMX_TRY(launch_split_planes(q_d, nq, ix->d, ix->d_pad, ix->q_scale, 1.0f, ix->Qhi, rescore ? nullptr : ix->Qlo, st));
     if (rescore) {
-      // |approx - exact| <= eps(q) = c_d * ||q|| * max_row ||x||:  2^-10 (1+2^-11) bounds the fp16 rounding
-      // of both operands (Cauchy-Schwarz over the element-wise relative errors), 2*d*2^-23 the fp32
-      // accumulation error of the tensor core and of the exact rescoring chain.  margin = 2 * eps.
-      const float c_d = 1.06f * 0.0009765625f + 2.0f * (float)ix->d * 1.1920929e-07f;
+      // |approx - exact| <= eps(q), margin = 2 eps(q): see query_margin_kernel.  gamma = 2*d*2^-23 bounds
+      // the fp32 accumulation error of the tensor core plus that of the exact rescoring chain.
+      const float gamma = 2.0f * (float)ix->d * 1.1920929e-07f;
       CMX_TRY(ensure_buf(&ix->margin_buf, &ix->margin_cap, nq_pad));
-      CMX_TRY(launch_query_margin(q_d, nq, ix->d, 2.0f * c_d * ix->row_norm_max, ix->margin_buf, st));
+      CMX_TRY(launch_query_margin(q_d, ix->Qhi, nq, ix->d, ix->d_pad, ix->q_scale, std::max(ix->row_norm_max, ix->norm_floor),
+                                  std::max(ix->row_resid_max, ix->resid_floor), gamma, ix->margin_buf, st));
       ix->ws.margin = ix->margin_buf;
     }
   }
@@ -276,7 +302,11 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
   const int align = (path == CMX_PATH_TENSOR) ? 256 : 32;
   // rescore mode keeps the margin band on top of the k best: plan for ~4/3 k resident candidates
   const int k_plan = rescore ? std::min(cap / 2, k + k / 3 + 8) : k;
-  SlabPlan pl = plan_slabs(ix->n, k_plan, cap, align, safe);
+  // tensor path: whole 256-row blocks in permuted order (the tail block's padding rows yield null keys)
+  const int64_t nblk = (ix->n + 255) / 256;
+  const uint64_t perm = pick_perm(nblk);
+  const int64_t n_plan = (path == CMX_PATH_TENSOR) ? nblk * 256 : ix->n;
+  SlabPlan pl = plan_slabs(n_plan, k_plan, cap, align, safe);
   const bool prof = g_profiling && !safe && (int)pl.rows.size() <= kMaxSlabEvents;
   if (prof) CMX_TRY(ensure_events(ix));
   int64_t seen = 0;
@@ -287,7 +317,7 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
     if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 0], st));
     if (path == CMX_PATH_TENSOR) {
       CMX_TRY(launch_tensor_score(ix->Bhi, ix->Blo, ix->n, seen, rows, ix->d_pad, ix->Qhi, ix->Qlo, nq, nq_pad,
-                                  ix->q_scale + 1, 1.0f / ix->plane_scale, ix->ws, dense, seen, rescore ? 1 : 3,
+                                  ix->q_scale + 1, 1.0f / ix->plane_scale, ix->ws, dense, perm, rescore ? 1 : 3,
                                   seen > 0 ? (double)k_plan / (double)seen : 1.0, ix->progress, st, ix->sm_count));
     } else {
       CMX_TRY(launch_stream_score(ix->X, seen, rows, ix->d, q_d, (int)nq, ix->ws, 0, dense, seen, st, ix->sm_count));
@@ -351,22 +381,22 @@ static int search_device(cmx_index* ix, const float* q_d, int64_t nq, int k, flo
   ix->stats.path = path;
   for (int64_t q0 = 0; q0 < nq; q0 += kQueryChunk) {
     const int64_t nqc = std::min<int64_t>(kQueryChunk, nq - q0);
-    bool ovf = false;
-    bool rescore = ix->precision == CMX_PRECISION_RESCORE && ix->row_norm_max > 0.f;
-    CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, rescore, false, st, &ovf));
-    if (ovf) {
-      // some query's candidate buffer overflowed (rows arrived in an adversarial order for the
-      // stale threshold); redo this chunk with the worst-case-safe slab schedule
-      ix->stats.reruns = 1;
-      CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, rescore, true, st, &ovf));
-      if (ovf && rescore && path == CMX_PATH_TENSOR) {
-        // more than `cap` rows inside the margin band of one query (e.g. thousands of near-duplicate
-        // rows): the approximate pass cannot separate them -- use the split-precision scorer
-        ix->stats.reruns = 2;
-        CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, false, true, st, &ovf));
-      }
-      if (ovf) { set_error("internal: candidate buffer overflow in safe mode"); return CMX_ERR_INTERNAL; }
+    const bool rescore = path == CMX_PATH_TENSOR && ix->precision == CMX_PRECISION_RESCORE && ix->row_norm_max > 0.f;
+    // attempts, cheapest first; stats.reruns = how many of them overflowed a candidate buffer
+    //   rescore, planned slabs : one fp16 pass + exact rescoring of the margin band
+    //   split,   planned slabs : the band of some query outgrew its buffer (thousands of rows within
+    //                            2*eps of the k-th score, e.g. near-duplicates) -- exact scores have no band
+    //   split,   safe slabs    : rows arrive in an order that is adversarial even for the sampled
+    //                            thresholds; slabs so small that no buffer can overflow
+    struct Attempt { bool rescore, safe; };
+    const Attempt chain[3] = {{true, false}, {false, false}, {false, true}};
+    bool ovf = true;
+    for (int a = rescore ? 0 : 1; a < 3 && ovf; ++a) {
+      ix->stats.reruns = std::max(ix->stats.reruns, a - (rescore ? 0 : 1));
+      CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, chain[a].rescore,
+                          chain[a].safe, st, &ovf));
     }
+    if (ovf) { set_error("internal: candidate buffer overflow in safe mode"); return CMX_ERR_INTERNAL; }
   }
   return CMX_OK;
 }
@@ -482,6 +512,25 @@ int cmx_index_reset(cmx_index* ix) {
   ix->lo_rows = 0;
   ix->absmax_bits = 0;
   ix->row_norm_max = 0.f;
+  ix->row_resid_max = 0.f;
+  ix->norm_floor = ix->resid_floor = 0.f;
+  return CMX_OK;
+}
+
+int cmx_index_error_bounds(cmx_index* ix, float* out2) {
+  CMX_CHECK(ix && out2, "null argument");
+  DevGuard g(ix->device);
+  if (ix->n > 0) CMX_TRY(ensure_planes(ix, false, 0));
+  out2[0] = std::max(ix->row_norm_max, ix->norm_floor);
+  out2[1] = std::max(ix->row_resid_max, ix->resid_floor);
+  return CMX_OK;
+}
+
+int cmx_index_raise_error_bounds(cmx_index* ix, const float* in2) {
+  CMX_CHECK(ix && in2, "null argument");
+  CMX_CHECK(in2[0] >= 0.f && in2[1] >= 0.f, "error bounds must be finite and non-negative");  // NaN fails too
+  ix->norm_floor = std::max(ix->norm_floor, in2[0]);
+  ix->resid_floor = std::max(ix->resid_floor, in2[1]);
   return CMX_OK;
 }
 
@@ -841,6 +890,7 @@ int cmx_merge_topk_peers(const float* const* D_parts, const int64_t* const* I_pa
 
 /* test hook (not in cmx.h): tensor tile width 256 / 128 */
 CMX_API int cmx_debug_set_tensor_tile(int bn) { set_tensor_tile(bn); return CMX_OK; }
+CMX_API int cmx_debug_set_block_order(int on) { g_block_order = on ? 1 : 0; return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_window(int w) { set_tensor_window(w); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_small(int on) { set_tensor_small(on); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_pair(int on) { set_tensor_pair(on); return CMX_OK; }

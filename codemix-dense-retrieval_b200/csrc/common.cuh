@@ -105,8 +105,12 @@ int launch_scale_from_absmax(const uint32_t* absmax_bits, float* scale_out, cuda
 float host_scale_for_absmax_bits(uint32_t bits);
 // max over rows of ||x||_2 (finite rows only), as float bits via atomicMax
 int launch_row_norm_max(const float* x, int64_t rows, int d, uint32_t* max_bits, cudaStream_t st);
-// margin[q] = coef * ||Q[q]||_2   (coef = 2 * c_d * max corpus row norm)
-int launch_query_margin(const float* Q, int64_t nq, int d, float coef, float* margin, cudaStream_t st);
+// max over rows of ||x - hi / scale||_2 (finite rows only), as float bits via atomicMax
+int launch_row_resid_max(const float* x, const __half* hi, int64_t rows, int d, int d_pad, float inv_scale,
+                         uint32_t* max_bits, cudaStream_t st);
+// margin[q] = 2 eps(q), eps(q) = ||q - qh|| xmax + (||q|| + ||q - qh||) xres + gamma ||q|| xmax
+int launch_query_margin(const float* Q, const __half* Qhi, int64_t nq, int d, int d_pad, const float* q_scale,
+                        float xmax, float xres, float gamma, float* margin, cudaStream_t st);
 
 int launch_stream_score(const float* X, int64_t row0, int64_t nrows, int d, const float* Q,
                         int nq, const SearchWs& ws, int64_t q0, int dense, int64_t dense_row0,
@@ -120,10 +124,12 @@ void set_tensor_small(int on);  // corpus-as-M kernel for nq <= 64
 void set_tensor_pair(int on);  // CTA-pair (cta_group::2) scorer for nq > 128
 // passes = 3: split precision (hi*hi + hi*lo + lo*hi, fp32-faithful scores);
 // passes = 1: hi*hi only (approximate filter scores; Blo/Qlo may be NULL) for the rescore mode
+// row0 / nrows are row POSITIONS in processing order (whole 256-row blocks); position block j is
+// corpus block (j * perm) mod ceil(plane_rows / 256) -- perm = 1 is file order
 int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
                         int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,
                         int64_t nq, int64_t nq_pad, const float* q_inv_scale_dev, float b_inv_scale,
-                        const SearchWs& ws, int dense, int64_t dense_row0, int passes, double expected_pass_rate,
+                        const SearchWs& ws, int dense, uint64_t perm, int passes, double expected_pass_rate,
                         unsigned long long* progress, cudaStream_t st, int sm_count);
 void set_tensor_window(int w);  // progress throttle slack in round-robin iterations (0 = off)
 

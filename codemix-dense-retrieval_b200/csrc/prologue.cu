@@ -194,23 +194,76 @@ int launch_row_norm_max(const float* x, int64_t rows, int d, uint32_t* max_bits,
   return CMX_OK;
 }
 
+// max over rows of || x - hi / scale ||_2: what the one-pass scorer loses of a corpus row (fp16
+// rounding, underflow of tiny elements -- whatever the cause, this is the true residual)
 __global__ void __launch_bounds__(256)
-query_margin_kernel(const float* __restrict__ Q, int64_t nq, int d, float coef, float* __restrict__ margin) {
+row_resid_max_kernel(const float* __restrict__ x, const __half* __restrict__ hi, int64_t rows, int d, int d_pad,
+                     float inv_scale, uint32_t* __restrict__ max_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float best = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    const float* row = x + r * d;
+    const __half* hrow = hi + r * d_pad;
+    float ss = 0.f;
+    for (int i = lane; i < d; i += 32) {
+      const float v = row[i] - __half2float(hrow[i]) * inv_scale;  // exact: scale is a power of two
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    if (is_finite_f(nrm)) best = fmaxf(best, nrm);
+  }
+  if (lane == 0 && best > 0.f) atomicMax(max_bits, __float_as_uint(best));
+}
+
+int launch_row_resid_max(const float* x, const __half* hi, int64_t rows, int d, int d_pad, float inv_scale,
+                         uint32_t* max_bits, cudaStream_t st) {
+  if (rows == 0) return CMX_OK;
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  row_resid_max_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, hi, rows, d, d_pad, inv_scale, max_bits);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+// Rescore-mode margin.  With q = qh + ql and x = xh + xl (qh, xh the fp16 planes in true units):
+//   q.x - qh.xh = ql.x + qh.xl,   |ql.x + qh.xl| <= ||ql|| ||x|| + ||qh|| ||xl||     (Cauchy-Schwarz)
+// and the fp32 accumulation of the tensor core plus that of the exact rescoring chain adds at
+// most gamma ||q|| ||x||.  eps(q) = ||ql|| X + (||q|| + ||ql||) R + gamma ||q|| X with X, R the
+// corpus maxima of ||x|| and ||xl||; margin = 2 eps.  The residual norms are measured, not
+// bounded by 2^-11 ||.||: typical fp16 rounding loses ~0.4 of the worst case.
+__global__ void __launch_bounds__(256)
+query_margin_kernel(const float* __restrict__ Q, const __half* __restrict__ Qhi, int64_t nq, int d, int d_pad,
+                    const float* __restrict__ q_scale, float xmax, float xres, float gamma,
+                    float* __restrict__ margin) {
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq) return;
   const float* row = Q + q * d;
-  float ss = 0.f;
-  for (int i = lane; i < d; i += 32) { const float v = row[i]; ss = fmaf(v, v, ss); }
+  const __half* hrow = Qhi + q * d_pad;
+  const float inv_scale = q_scale[1];
+  float ss = 0.f, rr = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float v = row[i];
+    const float r = v - __half2float(hrow[i]) * inv_scale;
+    ss = fmaf(v, v, ss);
+    rr = fmaf(r, r, rr);
+  }
   ss = warp_sum(ss);
-  // a non-finite query norm gives a non-finite margin: every score passes the filter, the
-  // buffers overflow and the search falls back to the split-precision path
-  if (lane == 0) margin[q] = coef * sqrtf(ss) * 1.0001f;
+  rr = warp_sum(rr);
+  // a non-finite query gives a non-finite margin: every score passes the filter, the buffers
+  // overflow and the search falls back to the split-precision path
+  if (lane == 0) {
+    const float nq2 = sqrtf(ss) * 1.001f, rq = sqrtf(rr) * 1.001f;  // 1.001: rounding of these very sums
+    margin[q] = 2.0f * (rq * xmax + (nq2 + rq) * xres + gamma * nq2 * xmax) * 1.001f;
+  }
 }
 
-int launch_query_margin(const float* Q, int64_t nq, int d, float coef, float* margin, cudaStream_t st) {
+int launch_query_margin(const float* Q, const __half* Qhi, int64_t nq, int d, int d_pad, const float* q_scale,
+                        float xmax, float xres, float gamma, float* margin, cudaStream_t st) {
   if (nq == 0) return CMX_OK;
-  query_margin_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(Q, nq, d, coef, margin);
+  query_margin_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(Q, Qhi, nq, d, d_pad, q_scale, xmax, xres, gamma, margin);
   CMX_LAUNCHED();
   return CMX_OK;
 }

@@ -141,8 +141,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 struct TcParams {
-  int64_t row0;        // first corpus row of the slab (plane row index)
-  int64_t nrows;       // rows in the slab
+  int64_t row0;        // first row POSITION of the slab in processing order (multiple of 256)
+  int64_t nrows;       // row positions in the slab (multiple of 256)
+  // Processing order (perm_row below): the corpus is cut into blocks of 256 rows and block
+  // position j is corpus block (j * perm) mod nblk, with perm ~ 0.618 * nblk coprime to nblk.
+  // Every prefix of that order is spread evenly over the whole corpus, so the thresholds the
+  // first slabs establish are estimates for ALL rows -- not just for the head of the file.
+  // (A combined EN+ZH index stores one language after the other: in file order the thresholds
+  // learnt on the first language would let the second one overflow the candidate buffers.)
+  int64_t nblk;        // ceil(ntotal / 256)
+  uint64_t perm;       // block multiplier, 1 = file order
+  int64_t nvalid;      // ntotal: rows at or beyond it are padding
   int kblocks;         // d_pad / 64
   int mtiles;          // ceil(nq / 128)
   int64_t ntiles;      // mtiles * ceil(nrows / BN)
@@ -154,7 +163,6 @@ struct TcParams {
   uint64_t* cand;
   int cap;
   int dense;
-  int64_t dense_row0;
   int flags;  // bit0: Q tiles evict_last, bit1: corpus tiles evict_first, bit2: streaming (.cs) appends
   // Progress throttle: tiles are assigned round-robin (m fastest) so that CTAs running at the
   // same time share corpus tiles through L2 -- but in a long launch CTAs drift apart (they are
@@ -166,12 +174,19 @@ struct TcParams {
   int two_pass;  // 1: count-then-store epilogue (dense early slabs), 0: staged epilogue
 };
 
+// corpus row of row position `pos_row` (see TcParams::perm)
+__device__ __forceinline__ int64_t perm_row(const TcParams& p, int64_t pos_row) {
+  const uint64_t pos = (uint64_t)pos_row >> 8;
+  const uint64_t blk = (pos * p.perm) % (uint64_t)p.nblk;  // pos, perm < 2^24
+  return (int64_t)(blk << 8) + (pos_row & 255);
+}
+
 // Dense epilogue (first slab): every column of the calling thread's query row becomes a
-// candidate, written at its own position of the query's buffer.
+// candidate, written at its own position of the query's buffer (padding rows: null keys).
 template <int BN>
 __device__ __forceinline__ void epilogue_dense_tile(const TcParams& p, uint32_t taddr_row, int64_t q, bool qvalid,
-                                                    float inv, int64_t tile_row0, int64_t cols_valid) {
-  uint64_t* qcand = p.cand + q * (int64_t)p.cap;
+                                                    float inv, int64_t tile_row0, int64_t cols_valid, int64_t slot0) {
+  uint64_t* qcand = p.cand + q * (int64_t)p.cap + slot0;
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
     uint32_t v[32];
@@ -181,11 +196,8 @@ __device__ __forceinline__ void epilogue_dense_tile(const TcParams& p, uint32_t 
     if (qvalid) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (j < jmax) {
-          const float s = __uint_as_float(v[j]) * inv;
-          const int64_t grow = tile_row0 + c * 32 + j;
-          qcand[grow - p.dense_row0] = (s > CMX_NEG_PAD) ? make_key(s, (uint32_t)grow) : 0ull;
-        }
+        const float s = __uint_as_float(v[j]) * inv;
+        qcand[c * 32 + j] = (j < jmax && s > CMX_NEG_PAD) ? make_key(s, (uint32_t)(tile_row0 + c * 32 + j)) : 0ull;
       }
     }
   }
@@ -380,7 +392,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
         const int m = (int)(t % mtiles);
         const int64_t n = t / mtiles;
         const int32_t qrow = m * TC_BM;
-        const int32_t brow = (int32_t)(p.row0 + n * BN);
+        const int32_t brow = (int32_t)perm_row(p, p.row0 + n * BN);
         throttle_wait(p.done, t, p.window);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -450,8 +462,8 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       const int m = (int)(t % mtiles);
       const int64_t n = t / mtiles;
       const int64_t q = (int64_t)m * TC_BM + lane_base + lane;
-      const int64_t tile_row0 = p.row0 + n * BN;
-      int64_t cols_valid = p.row0 + p.nrows - tile_row0;
+      const int64_t tile_row0 = perm_row(p, p.row0 + n * BN);
+      int64_t cols_valid = p.nvalid - tile_row0;  // <= 0 for a padding tile
       if (cols_valid > BN) cols_valid = BN;
       const bool qvalid = q < p.nq;
       // compare raw accumulators against tau expressed in accumulator units
@@ -459,7 +471,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
-      if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid);
+      if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid, n * BN);
       else if (p.two_pass) epilogue_filter_tile_two_pass<BN>(p, taddr_row, q, tau_raw, inv, tile_row0, cols_valid);
       else epilogue_filter_tile<BN>(p, taddr_row, stg, nst, q, tau_raw, inv, tile_row0, cols_valid);
       tc_fence_before();
@@ -590,7 +602,7 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
         const int m = (int)(t % mtiles);
         const int64_t n = t / mtiles;
         const int32_t qrow = m * 256 + (int32_t)rank * 128;
-        const int32_t brow = (int32_t)(p.row0 + n * BN) + (int32_t)rank * 128;
+        const int32_t brow = (int32_t)perm_row(p, p.row0 + n * BN) + (int32_t)rank * 128;
         throttle_wait(p.done, t, p.window);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -661,15 +673,15 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
       const int m = (int)(t % mtiles);
       const int64_t n = t / mtiles;
       const int64_t q = (int64_t)m * 256 + (int64_t)rank * 128 + lane_base + lane;
-      const int64_t tile_row0 = p.row0 + n * BN;
-      int64_t cols_valid = p.row0 + p.nrows - tile_row0;
+      const int64_t tile_row0 = perm_row(p, p.row0 + n * BN);
+      int64_t cols_valid = p.nvalid - tile_row0;  // <= 0 for a padding tile
       if (cols_valid > BN) cols_valid = BN;
       const bool qvalid = q < p.nq;
       const float tau_raw = qvalid ? p.tau[q] * fwd : __int_as_float(0x7f800000);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
-      if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid);
+      if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid, n * BN);
       else if (p.two_pass) epilogue_filter_tile_two_pass<BN>(p, taddr_row, q, tau_raw, inv, tile_row0, cols_valid);
       else epilogue_filter_tile<BN>(p, taddr_row, stg, nst, q, tau_raw, inv, tile_row0, cols_valid);
       tc_fence_before();
@@ -769,7 +781,7 @@ tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        const int32_t brow = (int32_t)(p.row0 + t * 128);
+        const int32_t brow = (int32_t)perm_row(p, p.row0 + t * 128);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
@@ -829,8 +841,9 @@ tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-      const int64_t grow = p.row0 + t * 128 + lane_base + lane;
-      const bool rvalid = grow < p.row0 + p.nrows;
+      const int64_t grow = perm_row(p, p.row0 + t * 128) + lane_base + lane;
+      const bool rvalid = grow < p.nvalid;
+      const int64_t slot = t * 128 + lane_base + lane;  // dense slab: position in the query's buffer
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * NQ);
@@ -847,10 +860,8 @@ tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_co
           if (qj < p.nq) {  // warp-uniform
             const float raw = __uint_as_float(v[j]);
             if (p.dense) {
-              if (rvalid) {
-                const float s = raw * inv;
-                p.cand[(int64_t)qj * p.cap + (grow - p.dense_row0)] = (s > CMX_NEG_PAD) ? make_key(s, (uint32_t)grow) : 0ull;
-              }
+              const float s = raw * inv;
+              p.cand[(int64_t)qj * p.cap + slot] = (rvalid && s > CMX_NEG_PAD) ? make_key(s, (uint32_t)grow) : 0ull;
             } else {
               const bool pass = rvalid && raw > tau_s[qj];
               const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
@@ -991,7 +1002,7 @@ void set_tensor_small(int on) { g_tc_small = on ? 1 : 0; }
 int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows, int64_t row0,
                         int64_t nrows, int d_pad, const __half* Qhi, const __half* Qlo,
                         int64_t nq, int64_t nq_pad, const float* q_inv_scale_dev, float b_inv_scale,
-                        const SearchWs& ws, int dense, int64_t dense_row0, int passes, double expected_pass_rate,
+                        const SearchWs& ws, int dense, uint64_t perm, int passes, double expected_pass_rate,
                         unsigned long long* progress, cudaStream_t st, int sm_count) {
   if (nrows <= 0 || nq <= 0) return CMX_OK;
   CMX_CHECK(passes == 1 || passes == 3, "tensor path: passes must be 1 or 3");
@@ -999,8 +1010,13 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   CMX_CHECK(plane_rows < (int64_t)0x7fffffff, "tensor path: more than 2^31 rows per shard");
   const bool split = passes == 3;
   TcParams p;
+  CMX_CHECK((row0 & 255) == 0 && (nrows & 255) == 0, "tensor path: slabs are whole 256-row blocks");
   p.row0 = row0;
   p.nrows = nrows;
+  p.nblk = (plane_rows + 255) / 256;
+  p.perm = perm % (uint64_t)p.nblk;
+  if (p.perm == 0) p.perm = 1;
+  p.nvalid = plane_rows;
   p.kblocks = d_pad / TC_BK;
   p.nq = nq;
   p.q_inv_scale = q_inv_scale_dev;
@@ -1010,7 +1026,6 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   p.cand = ws.cand;
   p.cap = ws.cap;
   p.dense = dense;
-  p.dense_row0 = dense_row0;
   p.flags = g_tc_flags;
   p.mtiles = 1;
   p.ntiles = 0;

@@ -190,9 +190,9 @@ CMX_API void cmx_free_text(char* p);
 typedef struct cmx_search_stats {
   int32_t path;            /* CMX_PATH_STREAM / CMX_PATH_TENSOR actually used       */
   int32_t slabs;           /* corpus slabs (score launches) of the last search      */
-  int32_t reruns;          /* 1 if the candidate buffers overflowed and the search
-                              was repeated with worst-case-safe slabs; 2 if the
-                              rescore mode additionally fell back to split precision */
+  int32_t reruns;          /* attempts that overflowed a candidate buffer and were
+                              repeated: rescore -> split precision with the planned
+                              slabs -> split precision with worst-case-safe slabs    */
   int32_t launches;        /* kernels launched by the last search                   */
   int64_t nq, ntotal;      /* shape of the last search                              */
   float score_ms;          /* CUDA-event time inside the scoring kernels (0 unless
@@ -207,6 +207,13 @@ CMX_API int cmx_index_last_stats(const cmx_index* ix, cmx_search_stats* out);
 CMX_API int cmx_set_profiling(int on);
 /* arithmetic of the tensor path: CMX_PRECISION_RESCORE (default) or CMX_PRECISION_SPLIT. */
 CMX_API int cmx_index_set_precision(cmx_index* ix, int mode);
+/* Rescore precision, sharded corpus: the filter margin of every shard must be derived from the
+ * maxima over ALL shards of the corpus row norm (out2[0]) and of the norm of what the fp16 plane
+ * loses of a row (out2[1]).  cmx_index_error_bounds builds the plane if needed and reports this
+ * shard's values; after a max-reduction over the shards cmx_index_raise_error_bounds installs
+ * the global ones (values only ever grow; cmx_index_reset clears them). */
+CMX_API int cmx_index_error_bounds(cmx_index* ix, float* out2);
+CMX_API int cmx_index_raise_error_bounds(cmx_index* ix, const float* in2);
 /* precision given to indexes created afterwards (process-wide default: CMX_PRECISION_RESCORE). */
 CMX_API int cmx_set_default_precision(int mode);
 /* tuning knob (tests): candidate-buffer capacity per query (0 = automatic). */
