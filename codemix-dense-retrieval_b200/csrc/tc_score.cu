@@ -203,6 +203,40 @@ __device__ __forceinline__ void epilogue_dense_tile(const TcParams& p, uint32_t 
   }
 }
 
+// ---- branch-free survivor extraction ------------------------------------------------
+// Each epilogue warp is alone on its SM sub-partition, so nothing hides the latency of a
+// dependent branch: 32 "if (score > tau) {...}" blocks per 32-column chunk cost ~60 cycles
+// each whenever ANY lane of the warp has a survivor in the chunk (measured: the early slabs
+// ran at half the MMA rate).  Instead: a 32-bit survivor mask per thread (independent
+// compares), and for each set bit the value is fetched with a 31-select tree -- registers
+// cannot be indexed dynamically.
+__device__ __forceinline__ uint32_t survivor_mask(const uint32_t (&v)[32], float tau_raw, int jmax) {
+  uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;  // four chains instead of one 32-deep dependency
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m0 |= (__uint_as_float(v[j]) > tau_raw) ? (1u << j) : 0u;
+    m1 |= (__uint_as_float(v[8 + j]) > tau_raw) ? (1u << (8 + j)) : 0u;
+    m2 |= (__uint_as_float(v[16 + j]) > tau_raw) ? (1u << (16 + j)) : 0u;
+    m3 |= (__uint_as_float(v[24 + j]) > tau_raw) ? (1u << (24 + j)) : 0u;
+  }
+  uint32_t m = (m0 | m1) | (m2 | m3);
+  if (jmax < 32) m &= (jmax <= 0) ? 0u : ((1u << jmax) - 1u);  // columns past the corpus end
+  return m;
+}
+
+__device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int j) {
+  const bool b0 = j & 1, b1 = j & 2, b2 = j & 4, b3 = j & 8, b4 = j & 16;
+  uint32_t a[16], b[8], c[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = b0 ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = b1 ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = b2 ? b[2 * i + 1] : b[2 * i];
+  const uint32_t d0 = b3 ? c[1] : c[0], d1 = b3 ? c[3] : c[2];
+  return b4 ? d1 : d0;
+}
+
 // Filter epilogue of one 128 x BN accumulator tile for the calling thread's query row.
 // ONE pass over the row in TMEM: columns that beat the threshold are parked in a small
 // per-thread staging area in shared memory (value + column).  The caller then releases the
@@ -227,9 +261,7 @@ __device__ __forceinline__ void epilogue_filter_tile_two_pass(const TcParams& p,
     tmem_ld_x32(taddr_row + (uint32_t)(c * 32), v);
     tmem_ld_wait();
     const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
-    uint32_t n = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) n += (j < jmax && __uint_as_float(v[j]) > tau_raw) ? 1u : 0u;
+    const uint32_t n = (uint32_t)__popc(survivor_mask(v, tau_raw, jmax));
     total += n;
     if (n) chunk_bits |= 1u << c;
   }
@@ -248,13 +280,13 @@ __device__ __forceinline__ void epilogue_filter_tile_two_pass(const TcParams& p,
     tmem_ld_wait();
     if (mine) {
       const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float raw = __uint_as_float(v[j]);
-        if (j < jmax && raw > tau_raw) {
-          if (pos < (uint32_t)p.cap) qcand[pos] = make_key(raw * inv, (uint32_t)(tile_row0 + c * 32 + j));
-          ++pos;
-        }
+      uint32_t mask = survivor_mask(v, tau_raw, jmax);
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        const float raw = __uint_as_float(select32(v, j));
+        if (pos < (uint32_t)p.cap) qcand[pos] = make_key(raw * inv, (uint32_t)(tile_row0 + c * 32 + j));
+        ++pos;
       }
     }
   }
@@ -311,23 +343,18 @@ __device__ __forceinline__ void epilogue_filter_tile(const TcParams& p, uint32_t
     tmem_ld_x32(taddr_row + (uint32_t)(c * 32), v);
     tmem_ld_wait();
     const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
-    float mx = __int_as_float(0xff800000);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (j < jmax) ? __uint_as_float(v[j]) : mx);
-    if (mx > tau_raw) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float raw = __uint_as_float(v[j]);
-        if (j < jmax && raw > tau_raw) {
-          if (nst == TC_STAGE_SLOTS) {
-            epilogue_flush_full(&p.cnt[q], p.cand + q * (int64_t)p.cap, p.cap, st.val + st.e, st.col + st.e, inv, tile_row0);
-            nst = 0;
-          }
-          st.val[nst * TC_EPI_THREADS + st.e] = raw;
-          st.col[nst * TC_EPI_THREADS + st.e] = c * 32 + j;
-          ++nst;
-        }
+    uint32_t mask = survivor_mask(v, tau_raw, jmax);
+    while (mask) {  // lanes without a survivor skip; the warp runs max-popcount iterations
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      const uint32_t raw = select32(v, j);
+      if (nst == TC_STAGE_SLOTS) {
+        epilogue_flush_full(&p.cnt[q], p.cand + q * (int64_t)p.cap, p.cap, st.val + st.e, st.col + st.e, inv, tile_row0);
+        nst = 0;
       }
+      st.val[nst * TC_EPI_THREADS + st.e] = __uint_as_float(raw);
+      st.col[nst * TC_EPI_THREADS + st.e] = c * 32 + j;
+      ++nst;
     }
   }
 }
