@@ -223,8 +223,9 @@ static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe) {
       rows = round_dn(cap);
       if (rows > cap) rows = cap;  // align > cap cannot happen (cap >= 256)
     } else if (safe) {
-      rows = round_dn(room);
-      if (rows > room) rows = room;
+      // no more rows than a buffer has room for; a room smaller than the alignment unit is served
+      // in pieces that never straddle a unit (the tensor kernels address whole 256-row blocks)
+      rows = room >= align ? room / align * align : std::min<int64_t>(room, align - seen % align);
     } else {
       const double g = (double)seen * (double)room / (2.0 * (double)k);
       rows = round_dn((int64_t)std::min<double>(g, 4e18));

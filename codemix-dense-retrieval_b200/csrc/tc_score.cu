@@ -141,8 +141,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 struct TcParams {
-  int64_t row0;        // first row POSITION of the slab in processing order (multiple of 256)
-  int64_t nrows;       // row positions in the slab (multiple of 256)
+  int64_t row0;        // first row POSITION of the slab in processing order
+  int64_t nrows;       // row positions in the slab (whole 256-row blocks, or a piece of one block)
   // Processing order (perm_row below): the corpus is cut into blocks of 256 rows and block
   // position j is corpus block (j * perm) mod nblk, with perm ~ 0.618 * nblk coprime to nblk.
   // Every prefix of that order is spread evenly over the whole corpus, so the thresholds the
@@ -491,6 +491,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       const int64_t q = (int64_t)m * TC_BM + lane_base + lane;
       const int64_t tile_row0 = perm_row(p, p.row0 + n * BN);
       int64_t cols_valid = p.nvalid - tile_row0;  // <= 0 for a padding tile
+      if (cols_valid > p.nrows - n * BN) cols_valid = p.nrows - n * BN;  // slab ends inside the tile (safe slabs)
       if (cols_valid > BN) cols_valid = BN;
       const bool qvalid = q < p.nq;
       // compare raw accumulators against tau expressed in accumulator units
@@ -702,6 +703,7 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
       const int64_t q = (int64_t)m * 256 + (int64_t)rank * 128 + lane_base + lane;
       const int64_t tile_row0 = perm_row(p, p.row0 + n * BN);
       int64_t cols_valid = p.nvalid - tile_row0;  // <= 0 for a padding tile
+      if (cols_valid > p.nrows - n * BN) cols_valid = p.nrows - n * BN;  // slab ends inside the tile (safe slabs)
       if (cols_valid > BN) cols_valid = BN;
       const bool qvalid = q < p.nq;
       const float tau_raw = qvalid ? p.tau[q] * fwd : __int_as_float(0x7f800000);
@@ -869,7 +871,7 @@ tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_co
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
       const int64_t grow = perm_row(p, p.row0 + t * 128) + lane_base + lane;
-      const bool rvalid = grow < p.nvalid;
+      const bool rvalid = grow < p.nvalid && t * 128 + lane_base + lane < p.nrows;
       const int64_t slot = t * 128 + lane_base + lane;  // dense slab: position in the query's buffer
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -1037,7 +1039,9 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   CMX_CHECK(plane_rows < (int64_t)0x7fffffff, "tensor path: more than 2^31 rows per shard");
   const bool split = passes == 3;
   TcParams p;
-  CMX_CHECK((row0 & 255) == 0 && (nrows & 255) == 0, "tensor path: slabs are whole 256-row blocks");
+  // a slab is a run of whole 256-row blocks, or (worst-case-safe slabs of a tiny candidate buffer) a piece of one block
+  CMX_CHECK(((row0 & 255) == 0 && (nrows & 255) == 0) || ((row0 & 255) + nrows <= 256),
+            "tensor path: slab [%lld, +%lld) straddles 256-row blocks", (long long)row0, (long long)nrows);
   p.row0 = row0;
   p.nrows = nrows;
   p.nblk = (plane_rows + 255) / 256;
