@@ -405,11 +405,13 @@ def run_cmx(a) -> None:
         executed = passes * 2.0 * nq * n_local * d_pad  # fp16 MMA passes actually issued
         achieved = executed / (per_step_score_ms / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-        traffic, per_row = ncu_traffic("tc_score_kernel", n_local, d)
+        traffic, per_row = ncu_traffic("tc_score_kernel" if passes == 3 else "tc_score_kernel_1pass", n_local, d)
+        alg_row = 4096 if passes == 3 else 2048
         roofline = {"bound": "tensor", "kernel": "tc_score_kernel", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_note": f"DRAM bytes of the step's scoring launches = {per_row} B per corpus row (ncu capture, "
-                                    "profiles/ncu_traffic.json) x rows; algorithmic = 4096 B per row (fp16 hi+lo planes read once)",
+                                    f"profiles/ncu_traffic.json) x rows of this rank, summed over the step's launches; algorithmic = {alg_row} B per row "
+                                    f"(fp16 {'hi+lo planes' if passes == 3 else 'hi plane'} read once)",
                     "passes": passes,
                     "achieved_alg_fp32_equiv": alg_flops / (per_step_score_ms / 1e3) / 1e12,
                     "kernel_ms_per_step": per_step_score_ms, "launches_per_step": score_launches / a.steps,
