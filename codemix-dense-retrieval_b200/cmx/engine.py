@@ -120,13 +120,13 @@ class Shard:
     def error_bounds(self):
         """(max row norm, max norm of what the fp16 plane loses of a row) of this shard -- the two corpus
         quantities behind the rescore-mode filter margin (builds the fp16 plane if needed)."""
-        out = (ctypes.c_float * 2)()
+        out = (C.c_float * 2)()
         check(_lib.lib().cmx_index_error_bounds(self._h, out))
         return float(out[0]), float(out[1])
 
     def raise_error_bounds(self, norm_max: float, resid_max: float) -> None:
         """Install the maxima over ALL shards (sharded search; see include/cmx.h)."""
-        check(_lib.lib().cmx_index_raise_error_bounds(self._h, (ctypes.c_float * 2)(norm_max, resid_max)))
+        check(_lib.lib().cmx_index_raise_error_bounds(self._h, (C.c_float * 2)(norm_max, resid_max)))
 
     def set_cand_capacity(self, cap: int) -> None:
         check(_lib.lib().cmx_index_set_cand_capacity(self._h, int(cap)))

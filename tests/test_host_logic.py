@@ -191,3 +191,39 @@ def test_no_gpu_fails_loudly():
         idx.search(np.zeros((1, 8), np.float32), 2)
     with pytest.raises(RuntimeError):
         engine.mix_normalize(np.zeros((2, 8), np.float32), np.zeros((2, 8), np.float32), [0.5])
+
+
+def test_no_undefined_globals_in_host_modules():
+    """Every global name a function of the host package (and of bench.py / __graft_entry__.py) loads is
+    defined at module level or is a builtin -- GPU-only code paths cannot be executed here, but a
+    misspelt module alias in one of them must not wait for a GPU box to be found."""
+    import builtins
+    import dis
+    import types
+
+    files = sorted((ROOT / "codemix-dense-retrieval_b200" / "cmx").glob("*.py")) + [ROOT / "bench.py", ROOT / "__graft_entry__.py"]
+    assert len(files) >= 8
+    problems = []
+    for f in files:
+        code = compile(f.read_text(), str(f), "exec")
+        defined = set(dir(builtins)) | {"__file__", "__name__", "__doc__", "__package__", "__spec__", "__builtins__", "__annotations__"}
+        loads = []
+
+        def walk(co):
+            for ins in dis.get_instructions(co):
+                if ins.opname in ("STORE_NAME", "STORE_GLOBAL") and co is code:
+                    defined.add(ins.argval)
+                if ins.opname in ("STORE_GLOBAL",):
+                    defined.add(ins.argval)
+                if ins.opname == "LOAD_GLOBAL" or (ins.opname == "LOAD_NAME" and co is code):
+                    loads.append((ins.argval, co.co_name))
+            for c in co.co_consts:
+                if isinstance(c, types.CodeType):
+                    walk(c)
+
+        walk(code)
+        # names bound at module level by `import a.b as c`, `from x import y`, def and class are STORE_NAMEs
+        for name, where in loads:
+            if name not in defined:
+                problems.append(f"{f.name}: {name} (in {where})")
+    assert not problems, problems
