@@ -220,6 +220,9 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
     if (threadIdx.x == 0) {
       cnt[q] = (uint32_t)kk;
       if (kth != 0ull) tau[q] = new_tau;
+      // rescore mode: the k best plus their margin band must fit half of the buffer (the other half
+      // is the room the slab plan counts on, and rescore_kernel holds at most cap/2 keys)
+      if (m > 0.f && kk > cap / 2) atomicExch(overflow, 1u);
     }
   } else if (final_pass) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) top[i] = keys[i];
@@ -245,10 +248,23 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
 
 // Rescore mode, last step.  One CTA per query: every surviving candidate (a superset of the
 // exact top-k, selected on approximate fp16 tensor-core scores) gets its EXACT fp32 score
-// from the fp32 row store -- one warp per candidate row, 128-bit coalesced loads, fp32 FMA
-// chain + shuffle reduction, deterministic for a given (query, row) -- then the exact top-k
-// under (score desc, row asc) is selected, sorted and written to D / I.
-// dynamic smem: cap keys | next_pow2(k) keys | d floats (the query)
+// from the fp32 row store, then the exact top-k under (score desc, row asc) is selected,
+// sorted and written to D / I.
+//  1. the candidates that pass the cut are gathered into shared memory (sharded search: the
+//     cut is the GLOBAL k-th best approximate score minus the margin, so a shard keeps ~1/G
+//     of its local band);
+//  2. one warp per TWO candidate rows at a time (16 independent 128-bit loads in flight per
+//     lane), fp32 FMA chain + shuffle reduction -- deterministic for a given (query, row);
+//  3. radix select + bitonic sort of the k best exact keys.
+// dynamic smem: cap/2 keys | next_pow2(k) keys | d floats (the query): 44 KB at k = 1000,
+// d = 1024, so four 512-thread CTAs share an SM and the row gathers of one hide the select
+// phase of another.
+__device__ __forceinline__ float dot_row_pair_reduce(float acc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
 __global__ void __launch_bounds__(kSelThreads)
 rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, const uint64_t* __restrict__ cand,
                const uint32_t* __restrict__ cnt, uint32_t* __restrict__ overflow, const float* __restrict__ margin,
@@ -256,56 +272,85 @@ rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, 
                int64_t id_base) {
   extern __shared__ __align__(16) uint64_t keys[];
   __shared__ SelectShared sh;
-  uint64_t* top = keys + cap;
+  __shared__ uint32_t s_m;
+  const int half = cap >> 1;
+  uint64_t* top = keys + half;
   float* qv = reinterpret_cast<float*>(top + topn);
   const int64_t q = blockIdx.x;
   const uint32_t n_raw = cnt[q];
-  if (n_raw > (uint32_t)cap && threadIdx.x == 0) atomicExch(overflow, 1u);
+  if (threadIdx.x == 0) {
+    s_m = 0;
+    if (n_raw > (uint32_t)cap) atomicExch(overflow, 1u);
+  }
   const int n = (int)min(n_raw, (uint32_t)cap);
   for (int i = threadIdx.x; i < d; i += blockDim.x) qv[i] = Q[q * (int64_t)d + i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const uint64_t* buf = cand + q * (int64_t)cap;
-  const bool vec = (d & 3) == 0;
-  // sharded search: any lower bound of the GLOBAL k-th best approximate score is a valid cut --
-  // the maximum over the shards' local k-th best (read here in place from every shard's array,
-  // peer memory included) shrinks the rows this shard has to rescore by about the shard count
+  // sharded search: any lower bound of the GLOBAL k-th best approximate score is a valid cut
   float lowest = CMX_NEG_PAD;
   if (cut.nparts > 0) {
     float ak = cut.kth[0][q];
     for (int g = 1; g < cut.nparts; ++g) ak = fmaxf(ak, cut.kth[g][q]);
     lowest = ak - (margin ? margin[q] : 0.f);
   }
-  for (int i = warp; i < n; i += nwarps) {
-    const uint64_t key = buf[i];
-    uint64_t out = 0ull;
-    if (key != 0ull && key_score(key) >= lowest) {
-      const uint32_t row = key_row(key);
-      const float* x = X + (int64_t)row * d;
-      float acc = 0.f;
-      if (vec) {
-        const float4* x4 = reinterpret_cast<const float4*>(x);
-        const float4* q4 = reinterpret_cast<const float4*>(qv);
-        for (int j = lane; j < (d >> 2); j += 32) {
-          const float4 a = x4[j], b = q4[j];
-          acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
-        }
-      } else {
-        for (int j = lane; j < d; j += 32) acc = fmaf(x[j], qv[j], acc);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (acc > CMX_NEG_PAD) out = make_key(acc, row);
-    }
-    if (lane == 0) keys[i] = out;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint64_t* buf = cand + q * (int64_t)cap;
+  // 1. gather (order is irrelevant: exact keys are distinct and the selection is a total order)
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const uint64_t key = i < n ? buf[i] : 0ull;
+    const bool valid = key != 0ull && key_score(key) >= lowest;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, valid);
+    uint32_t wbase = 0;
+    if (lane == 0 && ballot) wbase = atomicAdd(&s_m, (uint32_t)__popc(ballot));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    const uint32_t pos = wbase + __popc(ballot & ((1u << lane) - 1u));
+    if (valid && pos < (uint32_t)half) keys[pos] = key;
   }
   __syncthreads();
-  int kk = n;
-  if (n > k) {
-    const uint64_t kth = block_kth_largest(keys, n, k, sh);
-    kk = block_partition(keys, n, kth, top, sh);
+  if (s_m > (uint32_t)half && threadIdx.x == 0) atomicExch(overflow, 1u);  // compact_kernel flags this first
+  const int m = (int)min(s_m, (uint32_t)half);
+  // 2. exact scores, two rows per warp and iteration
+  const bool vec = (d & 3) == 0;
+  for (int i = 2 * warp; i < m; i += 2 * nwarps) {
+    const bool two = i + 1 < m;
+    const uint32_t row0 = key_row(keys[i]);
+    const uint32_t row1 = two ? key_row(keys[i + 1]) : row0;
+    const float* x0 = X + (int64_t)row0 * d;
+    const float* x1 = X + (int64_t)row1 * d;
+    float acc0 = 0.f, acc1 = 0.f;
+    if (vec) {
+      const float4* a4 = reinterpret_cast<const float4*>(x0);
+      const float4* b4 = reinterpret_cast<const float4*>(x1);
+      const float4* q4 = reinterpret_cast<const float4*>(qv);
+#pragma unroll 4
+      for (int j = lane; j < (d >> 2); j += 32) {
+        const float4 a = a4[j], b = b4[j], c = q4[j];
+        acc0 = fmaf(a.x, c.x, acc0); acc0 = fmaf(a.y, c.y, acc0); acc0 = fmaf(a.z, c.z, acc0); acc0 = fmaf(a.w, c.w, acc0);
+        acc1 = fmaf(b.x, c.x, acc1); acc1 = fmaf(b.y, c.y, acc1); acc1 = fmaf(b.z, c.z, acc1); acc1 = fmaf(b.w, c.w, acc1);
+      }
+    } else {
+      for (int j = lane; j < d; j += 32) {
+        const float c = qv[j];
+        acc0 = fmaf(x0[j], c, acc0);
+        acc1 = fmaf(x1[j], c, acc1);
+      }
+    }
+    acc0 = dot_row_pair_reduce(acc0);
+    acc1 = dot_row_pair_reduce(acc1);
+    __syncwarp();
+    if (lane == 0) {
+      keys[i] = acc0 > CMX_NEG_PAD ? make_key(acc0, row0) : 0ull;
+      if (two) keys[i + 1] = acc1 > CMX_NEG_PAD ? make_key(acc1, row1) : 0ull;
+    }
+  }
+  __syncthreads();
+  // 3. exact top-k
+  int kk = m;
+  if (m > k) {
+    const uint64_t kth = block_kth_largest(keys, m, k, sh);
+    kk = block_partition(keys, m, kth, top, sh);
   } else {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) top[i] = keys[i];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) top[i] = keys[i];
     __syncthreads();
   }
   const int P = next_pow2(max(kk, 2));
@@ -446,7 +491,7 @@ int launch_rescore(const float* X, int d, const float* Q, const SearchWs& ws, in
                    int64_t* I, int64_t id_base, const RescoreCut& cut, cudaStream_t st) {
   if (nq == 0) return CMX_OK;
   const int topn = pow2_at_least(k);
-  const size_t smem = ((size_t)ws.cap + topn) * sizeof(uint64_t) + (size_t)d * sizeof(float);
+  const size_t smem = ((size_t)(ws.cap >> 1) + topn) * sizeof(uint64_t) + (size_t)d * sizeof(float);
   CMX_CHECK(smem <= 220 * 1024, "rescore: d=%d too large for the shared-memory query copy", d);
   CMX_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rescore_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(X, d, Q, ws.cand, ws.cnt, ws.overflow, ws.margin, cut, ws.cap, k,

@@ -616,3 +616,75 @@ def test_rescore_scores_are_exact_fp32_and_near_duplicates_fall_back():
     D2, I2 = sh2.search(Qd, 50, path="tensor")
     assert sh2.last_stats()["reruns"] == 1  # rescore band overflow -> split precision, planned slabs
     _check(D2, I2, Xd, Qd, 50)
+
+
+def test_union_kth_matches_numpy():
+    """cmx_union_kth: global k-th best of several per-shard score lists (padding = lowest float)."""
+    import torch
+    from cmx.engine import union_kth
+
+    rng = np.random.default_rng(77)
+    nq, k, G = 37, 50, 3
+    parts = rng.standard_normal((G, nq, k)).astype(np.float32)
+    parts[1, 5, 10:] = np.finfo(np.float32).min  # a short list
+    parts[:, 7, :] = np.finfo(np.float32).min     # nothing anywhere
+    parts[:, 9, :] = 0.25                          # all equal
+    t = [torch.from_numpy(parts[g].reshape(-1).copy()).cuda() for g in range(G)]
+    outs = [torch.full((nq,), 123.0, dtype=torch.float32, device="cuda") for _ in range(2)]
+    union_kth([x.data_ptr() for x in t], nq, k, 3, 30, [o.data_ptr() for o in outs], 0)
+    torch.cuda.synchronize()
+    flat = np.sort(parts.transpose(1, 0, 2).reshape(nq, G * k), axis=1)[:, ::-1]
+    want = flat[:, k - 1]
+    for o in outs:
+        got = o.cpu().numpy()
+        assert (got[:3] == 123.0).all() and (got[30:] == 123.0).all()  # only the slice is written
+        sl = slice(3, 30)
+        lowest = np.finfo(np.float32).min
+        ok = (got[sl] == want[sl]) | ((want[sl] == lowest) & (got[sl] <= lowest))
+        assert ok.all(), (got[sl][~ok], want[sl][~ok])
+
+
+@pytest.mark.parametrize("G", [2, 5])
+def test_two_phase_sharded_search_on_one_gpu(G):
+    """The three-step sharded rescore search (begin / union_kth / end + merge), with the shards emulated
+    as G indexes on one GPU: equals the single-index result exactly, and every shard rescored only its
+    part of the global band."""
+    import torch
+    from cmx.engine import Shard, merge_topk, union_kth
+
+    rng = np.random.default_rng(78)
+    d, N, nq, k = 128, 30000, 64, 200
+    X = _aniso(rng, N, d)
+    X[1000:1040] *= 3.0  # unequal row norms across shards: the margin must use the GLOBAL maxima
+    P, S = _aniso(rng, nq, d), _aniso(rng, nq, d)
+    alphas = [0.0, 0.35, 1.0]
+    one = Shard(d, 0)
+    one.set_precision("rescore")
+    one.add(X)
+    Pt, St = torch.from_numpy(P).cuda(), torch.from_numpy(S).cuda()
+    D1, I1 = one.search_mixed(Pt, St, alphas, k, path="tensor")
+    bounds = np.linspace(0, N, G + 1).astype(int)
+    shards = []
+    for g in range(G):
+        sh = Shard(d, 0)
+        sh.set_precision("rescore")
+        sh.add(X[bounds[g]:bounds[g + 1]])
+        shards.append(sh)
+    eb = np.array([sh.error_bounds() for sh in shards]).max(axis=0)
+    for sh in shards:
+        sh.raise_error_bounds(float(eb[0]), float(eb[1]))
+    nqt = len(alphas) * nq
+    asc = [torch.empty((nqt * k,), dtype=torch.float32, device="cuda") for _ in range(G)]
+    for g, sh in enumerate(shards):
+        assert not sh.search_mixed_begin(Pt, St, alphas, k, int(bounds[g]), asc[g])
+    kth = torch.empty((nqt,), dtype=torch.float32, device="cuda")
+    union_kth([a.data_ptr() for a in asc], nqt, k, 0, nqt, [kth.data_ptr()], 0)
+    Dp = torch.empty((G, nqt, k), dtype=torch.float32, device="cuda")
+    Ip = torch.empty((G, nqt, k), dtype=torch.int64, device="cuda")
+    for g, sh in enumerate(shards):
+        sh.search_end([kth.data_ptr()], Dp[g], Ip[g])
+    Dm, Im = merge_topk(Dp, Ip)
+    assert torch.equal(Im.view(len(alphas), nq, k), I1) and torch.equal(Dm.view(len(alphas), nq, k), D1)
+    # each shard returned only rows inside the global band: far fewer than k valid entries per query
+    valid = (Ip >= 0).sum(dim=2).float().mean(dim=1).cpu().numpy()
+    assert valid.sum() < 1.6 * k and (valid < 0.9 * k).all(), valid
