@@ -159,7 +159,7 @@ def mono_trec_bytes(qids: Sequence[str], D, I, docs, tag: str = "onepass-cm", nt
     if nq == 0:
         return b""
     docs = docs if isinstance(docs, DocTable) else DocTable(docs)
-    q = StrTable(qids)
+    q = qids if isinstance(qids, StrTable) else StrTable(qids)
     assert q.n == nq
     out, n = C.c_void_p(), C.c_int64(0)
     keys_ptr = None if docs.keys is None else docs.keys.ctypes.data
@@ -167,6 +167,41 @@ def mono_trec_bytes(qids: Sequence[str], D, I, docs, tag: str = "onepass-cm", nt
                                         docs.table.off.ctypes.data, keys_ptr, docs.table.n, tag.encode("utf-8"),
                                         int(nthreads), C.byref(out), C.byref(n)))
     return _take_bytes(out, n)
+
+
+def _tmp_name(path: pathlib.Path) -> pathlib.Path:
+    return path.with_name(path.name + f".tmp{os.getpid()}")
+
+
+def write_mono_trec(path, qids: Sequence[str], D, I, docs, tag: str = "onepass-cm", nthreads: int = 0) -> int:
+    """``mono_trec_bytes`` written to ``path`` without assembling the text in memory: the C
+    formatter's threads pwrite their parts into a temporary file that is then renamed over
+    ``path`` (all-or-nothing, like the reference's single write_text).  Returns the file size."""
+    import ctypes as C
+
+    from . import _lib
+
+    path = pathlib.Path(path)
+    D, I = _host_f32_i64(D, I)
+    nq, k = D.shape
+    if nq == 0:
+        _atomic_write(path, b"")
+        return 0
+    docs = docs if isinstance(docs, DocTable) else DocTable(docs)
+    q = qids if isinstance(qids, StrTable) else StrTable(qids)
+    assert q.n == nq
+    n = C.c_int64(0)
+    keys_ptr = None if docs.keys is None else docs.keys.ctypes.data
+    tmp = _tmp_name(path)
+    try:
+        _lib.check(_lib.lib().cmx_trec_mono_file(D.ctypes.data, I.ctypes.data, nq, k, q.buf, q.off.ctypes.data, docs.table.buf,
+                                                 docs.table.off.ctypes.data, keys_ptr, docs.table.n, tag.encode("utf-8"),
+                                                 int(nthreads), os.fsencode(tmp), C.byref(n)))
+        os.replace(tmp, path)
+    finally:
+        if tmp.exists():
+            tmp.unlink()
+    return int(n.value)
 
 
 class BaseTable:
@@ -219,6 +254,40 @@ def bilingual_bytes(qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int =
                                              bt.bases.off.ctypes.data, bt.bases.n, tag.encode("utf-8"), int(nthreads),
                                              C.byref(raw), C.byref(nraw), C.byref(col), C.byref(ncol)))
     return _take_bytes(raw, nraw), _take_bytes(col, ncol)
+
+
+def write_bilingual_trec(raw_path, col_path, qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int = 0):
+    """``bilingual_bytes`` written straight to the raw and the collapsed run file (temporary
+    names, then renamed).  Returns the two file sizes."""
+    import ctypes as C
+
+    from . import _lib
+
+    raw_path, col_path = pathlib.Path(raw_path), pathlib.Path(col_path)
+    D, I = _host_f32_i64(D, I)
+    nq, k = D.shape
+    qids = list(qids)
+    if nq == 0 or len(set(qids)) != len(qids):  # repeated qids: the exact (slow) Python path
+        raw, col = bilingual_bytes(qids, D, I, id2doc, tag, nthreads)
+        _atomic_write(raw_path, raw)
+        _atomic_write(col_path, col)
+        return len(raw), len(col)
+    bt = id2doc if isinstance(id2doc, BaseTable) else BaseTable(id2doc)
+    q = StrTable(qids)
+    nraw, ncol = C.c_int64(0), C.c_int64(0)
+    t_raw, t_col = _tmp_name(raw_path), _tmp_name(col_path)
+    try:
+        _lib.check(_lib.lib().cmx_trec_bilingual_file(D.ctypes.data, I.ctypes.data, nq, k, q.buf, q.off.ctypes.data, bt.docs.buf,
+                                                      bt.docs.off.ctypes.data, bt.docs.n, bt.codes.ctypes.data, bt.bases.buf,
+                                                      bt.bases.off.ctypes.data, bt.bases.n, tag.encode("utf-8"), int(nthreads),
+                                                      os.fsencode(t_raw), os.fsencode(t_col), C.byref(nraw), C.byref(ncol)))
+        os.replace(t_raw, raw_path)
+        os.replace(t_col, col_path)
+    finally:
+        for t in (t_raw, t_col):
+            if t.exists():
+                t.unlink()
+    return int(nraw.value), int(ncol.value)
 
 
 def bilingual_raw_text(qids, D, I, id2doc, tag: str) -> str:
@@ -293,25 +362,39 @@ def run_alpha_sweep(index, id_lookup, qids: Sequence[str], P, S, alphas: Sequenc
     accepted for CLI compatibility: searches are independent per query, so the whole alpha
     batch is issued in one call.  ``alpha_batch`` alphas share one fused launch sequence.
     """
+    from concurrent.futures import ThreadPoolExecutor
+
     outdir = pathlib.Path(outdir)
     outdir.mkdir(parents=True, exist_ok=True)
     docs = DocTable(id_lookup)
-    qids = list(qids)
+    qtab = StrTable(list(qids))
     written: List[pathlib.Path] = []
     alphas = [float(a) for a in alphas]
-    for a0 in range(0, len(alphas), max(1, alpha_batch)):
-        group = alphas[a0 : a0 + max(1, alpha_batch)]
-        t0 = time.perf_counter()
-        D, I = index.search_mixed(P, S, group, k)
-        D, I = _to_host(D), _to_host(I)
-        t1 = time.perf_counter()
-        for gi, alpha in enumerate(group):
-            label = format_alpha(alpha)
-            run_path = outdir / f"cm-alpha-{label}.trec"
-            _atomic_write(run_path, mono_trec_bytes(qids, D[gi], I[gi], docs, tag))
-            written.append(run_path)
-            if log:
-                log(f"Run saved: {run_path}  ({len(qids)} queries, alpha={label}, search {t1 - t0:.3f}s)")
+    # two-stage pipeline: while the formatter threads (C, GIL released) turn alpha i into text and
+    # write its file, the GPU already searches alpha i+1
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        pending = None
+        for a0 in range(0, len(alphas), max(1, alpha_batch)):
+            group = alphas[a0 : a0 + max(1, alpha_batch)]
+            t0 = time.perf_counter()
+            D, I = index.search_mixed(P, S, group, k)
+            D, I = _to_host(D), _to_host(I)
+            t1 = time.perf_counter()
+            if pending is not None:
+                pending.result()
+
+            def emit(group=group, D=D, I=I, dt=t1 - t0):
+                for gi, alpha in enumerate(group):
+                    label = format_alpha(alpha)
+                    run_path = outdir / f"cm-alpha-{label}.trec"
+                    write_mono_trec(run_path, qtab, D[gi], I[gi], docs, tag)
+                    written.append(run_path)
+                    if log:
+                        log(f"Run saved: {run_path}  ({qtab.n} queries, alpha={label}, search {dt:.3f}s)")
+
+            pending = pool.submit(emit)
+        if pending is not None:
+            pending.result()
     return written
 
 
@@ -321,30 +404,41 @@ def run_alpha_sweep_bilingual(index, id2doc: Sequence[str], qids: Sequence[str],
     """Bilingual sweep: per alpha write ``cm-alpha-<label>_raw.trec`` (derived ``base#lang``
     ids), the collapsed ``cm-alpha-<label>.trec`` (max over languages) and
     ``cm-alpha-<label>_meta.json``."""
+    from concurrent.futures import ThreadPoolExecutor
+
     outdir = pathlib.Path(outdir)
     outdir.mkdir(parents=True, exist_ok=True)
     qids = list(qids)
     table = BaseTable(id2doc)
     written: List[pathlib.Path] = []
     alphas = [float(a) for a in alphas]
-    for a0 in range(0, len(alphas), max(1, alpha_batch)):
-        group = alphas[a0 : a0 + max(1, alpha_batch)]
-        D, I = index.search_mixed(P, S, group, topk)
-        D, I = _to_host(D), _to_host(I)
-        for gi, alpha in enumerate(group):
-            label = format_alpha(alpha)
-            set_name = f"cm-alpha-{label}"
-            run_raw = outdir / f"{set_name}_raw.trec"
-            run_base = outdir / f"{set_name}.trec"
-            raw_text, collapsed = bilingual_bytes(qids, D[gi], I[gi], table, tag)
-            _atomic_write(run_raw, raw_text)
-            _atomic_write(run_base, collapsed)
-            m = dict(meta or {})
-            m.update({"alpha": label, "runs": {"raw": str(run_raw), "base": str(run_base)},
-                      "index": {"type": "IndexIDMap(IndexFlatIP)", "size": int(index.ntotal), "dim": int(index.d)},
-                      "topk": int(topk), "qblock": int(qblock)})
-            _atomic_write(outdir / f"{set_name}_meta.json", json.dumps(m, indent=2))
-            written.append(run_base)
-            if log:
-                log(f"Completed set '{set_name}' -> {run_raw.name} , {run_base.name}")
+    ntotal, dim = int(index.ntotal), int(index.d)
+    with ThreadPoolExecutor(max_workers=1) as pool:  # text of alpha i overlaps the search of alpha i+1
+        pending = None
+        for a0 in range(0, len(alphas), max(1, alpha_batch)):
+            group = alphas[a0 : a0 + max(1, alpha_batch)]
+            D, I = index.search_mixed(P, S, group, topk)
+            D, I = _to_host(D), _to_host(I)
+            if pending is not None:
+                pending.result()
+
+            def emit(group=group, D=D, I=I):
+                for gi, alpha in enumerate(group):
+                    label = format_alpha(alpha)
+                    set_name = f"cm-alpha-{label}"
+                    run_raw = outdir / f"{set_name}_raw.trec"
+                    run_base = outdir / f"{set_name}.trec"
+                    write_bilingual_trec(run_raw, run_base, qids, D[gi], I[gi], table, tag)
+                    m = dict(meta or {})
+                    m.update({"alpha": label, "runs": {"raw": str(run_raw), "base": str(run_base)},
+                              "index": {"type": "IndexIDMap(IndexFlatIP)", "size": ntotal, "dim": dim},
+                              "topk": int(topk), "qblock": int(qblock)})
+                    _atomic_write(outdir / f"{set_name}_meta.json", json.dumps(m, indent=2))
+                    written.append(run_base)
+                    if log:
+                        log(f"Completed set '{set_name}' -> {run_raw.name} , {run_base.name}")
+
+            pending = pool.submit(emit)
+        if pending is not None:
+            pending.result()
     return written

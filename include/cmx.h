@@ -185,6 +185,22 @@ CMX_API int cmx_trec_bilingual(const float* D, const int64_t* I, int64_t nq, int
                                const int64_t* base_off, int64_t nbases, const char* tag, int nthreads,
                                char** raw_out, int64_t* raw_len, char** col_out, int64_t* col_len);
 CMX_API void cmx_free_text(char* p);
+/* The same text written straight to files (created / truncated): every formatting thread
+ * pwrites its part at its final offset, so the run file (300 MB at 6980 x 1000 hits) is never
+ * assembled in memory.  *_len receive the file sizes.  Replaces the reference's
+ * write_text("\n".join(lines)) (onepass_dense_mix_run_custom_lang.py:889) and the raw / collapsed
+ * writers (onepass_bilingual_mix_hub_custom_lang.py:942-962); callers that want the reference's
+ * all-or-nothing files write to a temporary name and rename. */
+CMX_API int cmx_trec_mono_file(const float* D, const int64_t* I, int64_t nq, int k, const char* qids,
+                               const int64_t* qid_off, const char* docs, const int64_t* doc_off,
+                               const int64_t* doc_keys, int64_t ndocs, const char* tag, int nthreads,
+                               const char* path, int64_t* out_len);
+CMX_API int cmx_trec_bilingual_file(const float* D, const int64_t* I, int64_t nq, int k, const char* qids,
+                                    const int64_t* qid_off, const char* docs, const int64_t* doc_off,
+                                    int64_t ndocs, const int32_t* base_code, const char* bases,
+                                    const int64_t* base_off, int64_t nbases, const char* tag, int nthreads,
+                                    const char* raw_path, const char* col_path, int64_t* raw_len,
+                                    int64_t* col_len);
 
 /* ---- instrumentation --------------------------------------------------------*/
 typedef struct cmx_search_stats {

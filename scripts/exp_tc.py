@@ -17,9 +17,12 @@ for N in sizes:
     while c * bench.CHUNK < N:
         x = bench.corpus_chunk(c, d, dev)
         sh.add(x[: min(bench.CHUNK, N - c * bench.CHUNK)]); del x; c += 1
-    for prec, pair, flags in (("rescore", 0, 1), ("rescore", 0, 2), ("rescore", 0, 3), ("rescore", 0, 4), ("rescore", 0, 8), ("split", 0, 3)):
+    for prec, pair, flags, bn in (("rescore", 0, 3, 256), ("rescore", 0, 2, 256), ("rescore", 0, 4, 256), ("rescore", 0, 6, 256),
+                                  ("rescore", 0, 0, 256), ("rescore", 1, 3, 256), ("rescore", 1, 2, 256), ("rescore", 0, 3, 128),
+                                  ("rescore", 0, 3, 256)):
         sh.set_precision(prec)
         _lib.check(_lib.lib().cmx_debug_set_tensor_pair(pair))
+        _lib.check(_lib.lib().cmx_debug_set_tensor_tile(bn))
         for _ in (0,):
             _lib.check(_lib.lib().cmx_debug_set_tensor_window(flags))
             for _ in range(2):
@@ -30,7 +33,7 @@ for N in sizes:
                 sh.search_mixed(P, S, [0.5], 1000, path="tensor"); st = sh.last_stats()
                 sc += st["score_ms"]; se += st["select_ms"]; tot += st["total_ms"]
             tf = (3 if prec == "split" else 1) * 2.0 * 6980 * N * d / (sc / reps / 1e3) / 1e12
-            print(json.dumps({"N": N, "precision": prec, "pair": pair, "window": flags, "reruns": st["reruns"], "qps": round(6980 / (tot / reps / 1e3)), "score_ms": round(sc / reps, 2), "select_ms": round(se / reps, 2),
+            print(json.dumps({"N": N, "precision": prec, "pair": pair, "window": flags, "bn": bn, "reruns": st["reruns"], "qps": round(6980 / (tot / reps / 1e3)), "score_ms": round(sc / reps, 2), "select_ms": round(se / reps, 2),
                               "total_ms": round(tot / reps, 2), "exec_TFLOPs": round(tf, 1)}), flush=True)
     del sh
     torch.cuda.empty_cache()

@@ -74,6 +74,60 @@ def test_bilingual_raw_and_collapse_equal_oracle():
     assert runloop.collapse_by_base(qids, D, I, id2doc) == want
 
 
+class _OracleIndex:
+    """Stands in for a cmx.faiss index in the sweep loops (CPU): search_mixed through the oracle."""
+
+    def __init__(self, X):
+        self.X, self.ntotal, self.d = X, X.shape[0], X.shape[1]
+
+    def search_mixed(self, P, S, alphas, k):
+        Q, _ = oracle.mix_normalize(P, S, list(alphas))
+        out = [oracle.flat_ip_search(self.X, Q[a], k) for a in range(len(alphas))]
+        return np.stack([o[0] for o in out]), np.stack([o[1] for o in out])
+
+
+def test_file_writers_and_pipelined_sweeps_equal_oracle_text(tmp_path):
+    """cmx_trec_mono_file / cmx_trec_bilingual_file (parallel pwrite, no assembled text) and the
+    pipelined sweep loops write exactly the bytes the reference loops would."""
+    rng = np.random.default_rng(61)
+    n, d, nq, k = 3000, 32, 157, 40  # more queries than formatter threads, ragged thread ranges
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    P = rng.standard_normal((nq, d)).astype(np.float32)
+    S = rng.standard_normal((nq, d)).astype(np.float32)
+    qids = [str(9000 + 3 * i) for i in range(nq)]
+    lookup = {i: f"D{i:07d}" for i in range(n - 5)}  # the last ids print as numbers
+    alphas = [0.0, 0.25, 0.5, 1.0]
+    idx = _OracleIndex(X)
+    files = runloop.run_alpha_sweep(idx, lookup, qids, P, S, alphas, tmp_path / "mono", k=k)
+    assert [f.name for f in files] == ["cm-alpha-0.trec", "cm-alpha-0.25.trec", "cm-alpha-0.5.trec", "cm-alpha-1.trec"]
+    for a, f in zip(alphas, files):
+        D, I = idx.search_mixed(P, S, [a], k)
+        want = "\n".join(oracle.mono_trec_lines(qids, D[0], I[0], lookup))
+        assert f.read_bytes() == want.encode("utf-8")
+        assert runloop.mono_trec_bytes(qids, D[0], I[0], lookup) == want.encode("utf-8")
+    assert not list((tmp_path / "mono").glob("*.tmp*"))
+    # one thread / many threads give the same file
+    sz = runloop.write_mono_trec(tmp_path / "one.trec", qids, D[0], I[0], lookup, nthreads=1)
+    assert (tmp_path / "one.trec").read_bytes() == files[-1].read_bytes() and sz == files[-1].stat().st_size
+    runloop.write_mono_trec(tmp_path / "many.trec", qids, D[0], I[0], lookup, nthreads=64)
+    assert (tmp_path / "many.trec").read_bytes() == files[-1].read_bytes()
+    # bilingual: raw + collapsed
+    id2doc = [f"{i // 2}#{'en' if i % 2 == 0 else 'zh'}" for i in range(n)]
+    bfiles = runloop.run_alpha_sweep_bilingual(idx, id2doc, qids, P, S, [0.5, 0.75], tmp_path / "bi", topk=k, tag="bilingual-mix-en-zh")
+    for a, f in zip([0.5, 0.75], bfiles):
+        D, I = idx.search_mixed(P, S, [a], k)
+        raw_lines = oracle.bilingual_raw_lines(qids, D[0], I[0], id2doc, "bilingual-mix-en-zh")
+        raw = f.with_name(f.stem + "_raw.trec")
+        assert raw.read_text() == "".join(raw_lines)
+        assert f.read_text() == oracle.collapse_run_max_text(raw_lines)
+        meta = json.loads(f.with_name(f.stem + "_meta.json").read_text())
+        assert meta["topk"] == k and meta["index"]["size"] == n
+    # empty result set
+    assert runloop.write_mono_trec(tmp_path / "empty.trec", [], np.zeros((0, 5), np.float32), np.zeros((0, 5), np.int64), lookup) == 0
+    assert (tmp_path / "empty.trec").read_bytes() == b""
+
+
 def test_collapse_text_form_matches_golden(golden_dir, tmp_path):
     g = json.loads((golden_dir / "text_golden.json").read_text())
     pin, pout = tmp_path / "x_raw.trec", tmp_path / "x.trec"
