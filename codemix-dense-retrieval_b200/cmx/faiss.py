@@ -212,16 +212,17 @@ class IndexFlatIP(_Searchable):
         return self._promote().search_mixed(P, S, alphas, k)
 
 
-def _map_ids(I, id_map: np.ndarray):
-    """I = id_map[I], -1 stays -1 (faiss IndexIDMap::search)."""
+def _map_ids(I, id_map_ext, dev_cache: dict):
+    """I = id_map[I], -1 stays -1 (faiss IndexIDMap::search).  ``id_map_ext`` is the map with a
+    trailing -1, so that one gather does both (index -1 wraps to the sentinel)."""
     if _is_torch(I):
         if I.is_cuda:
-            idm = torch.from_numpy(id_map).to(I.device)
-            return torch.where(I >= 0, idm[I.clamp_min(0)], I)
-        I = I.numpy()
-        out = np.where(I >= 0, id_map[np.clip(I, 0, None)], -1)
-        return torch.from_numpy(out)
-    return np.where(I >= 0, id_map[np.clip(I, 0, None)], -1)
+            idm = dev_cache.get(I.device)
+            if idm is None:  # uploaded once per device, not per search
+                idm = dev_cache[I.device] = torch.from_numpy(id_map_ext).to(I.device)
+            return idm[I]
+        return torch.from_numpy(id_map_ext[I.numpy()])
+    return id_map_ext[I]
 
 
 class IndexIDMap(_Searchable):
@@ -235,11 +236,40 @@ class IndexIDMap(_Searchable):
             raise RuntimeError("IndexIDMap: index must be empty on input")
         self.index = index
         self.d = index.d
-        self._ids: List[np.ndarray] = []
+        self._version = 0
+        self._ids = []            # list of int64 arrays (property: every assignment bumps _version)
+        self._map_sig = None      # _version the cached translation state below was built from
+        self._map_identity = True
+        self._map_ext = None
+        self._map_dev: dict = {}
 
     @property
     def ntotal(self) -> int:
         return self.index.ntotal
+
+    @property
+    def _ids(self) -> List[np.ndarray]:
+        return self._id_parts
+
+    @_ids.setter
+    def _ids(self, parts) -> None:
+        self._id_parts = parts
+        self._version += 1
+
+    def _translate(self, I):
+        """User ids of the rows in I.  The common map of the reference -- ids 0..n-1 in row order
+        (``add_with_ids(x, np.arange(start, start + n))``) -- is recognised once and costs nothing
+        per search; any other map is one gather (on the device for device results)."""
+        if self._version != self._map_sig:
+            idm = self.id_map
+            self._map_identity = bool(idm.shape[0] == 0 or (idm[0] == 0 and idm[-1] == idm.shape[0] - 1
+                                                            and np.array_equal(idm, np.arange(idm.shape[0], dtype=np.int64))))
+            self._map_ext = None if self._map_identity else np.concatenate([idm, np.array([-1], dtype=np.int64)])
+            self._map_dev = {}
+            self._map_sig = self._version
+        if self._map_identity:
+            return I
+        return _map_ids(I, self._map_ext, self._map_dev)
 
     @property
     def id_map(self) -> np.ndarray:
@@ -256,6 +286,7 @@ class IndexIDMap(_Searchable):
         assert ids.shape[0] == n, "add_with_ids: one id per row"
         self.index.add(x)
         self._ids.append(ids.copy())
+        self._version += 1
 
     def reset(self) -> None:
         self.index.reset()
@@ -264,12 +295,12 @@ class IndexIDMap(_Searchable):
     def search(self, x, k: int):
         self.index.path = self.path
         D, I = self.index.search(x, k)
-        return D, _map_ids(I, self.id_map)
+        return D, self._translate(I)
 
     def search_mixed(self, P, S, alphas, k: int):
         self.index.path = self.path
         D, I = self.index.search_mixed(P, S, alphas, k)
-        return D, _map_ids(I, self.id_map)
+        return D, self._translate(I)
 
     def reconstruct(self, key, out=None):
         # faiss: only IndexIDMap2 can reconstruct by user id; the reference probes the

@@ -351,6 +351,59 @@ def _to_host(a):
 
 
 # ---- the sweeps -------------------------------------------------------------------
+def _gpu_of(index) -> Optional[int]:
+    """CUDA device of a single-GPU cmx.faiss index (through IndexIDMap wrappers), else None."""
+    seen = 0
+    while index is not None and seen < 4:
+        if hasattr(index, "getDevice"):
+            try:
+                return int(index.getDevice())
+            except Exception:
+                return None
+        index = getattr(index, "index", None)
+        seen += 1
+    return None
+
+
+class _SweepIO:
+    """Host<->device traffic of a sweep.  On a single-GPU index the cached query matrices are
+    uploaded ONCE (the reference re-uploads a 4 KB row per query and alpha: safe_mix), every
+    alpha's (D, I) lands in one of two pinned host slots (full PCIe rate, no per-alpha
+    allocation), and the slot of alpha i is being formatted while alpha i+1 is searched.
+    Any other index (sharded, host) gets the arrays as they are."""
+
+    def __init__(self, index, P, S):
+        self.P, self.S, self.slots, self.turn, self.torch = P, S, [None, None], 0, None
+        dev = _gpu_of(index)
+        if dev is None:
+            return
+        try:
+            import torch
+        except Exception:
+            return
+        if not torch.cuda.is_available():
+            return
+        self.torch = torch
+        self.dev = torch.device("cuda", dev)
+        self.P = torch.as_tensor(np.ascontiguousarray(_to_host(P), dtype=np.float32)).to(self.dev)
+        self.S = torch.as_tensor(np.ascontiguousarray(_to_host(S), dtype=np.float32)).to(self.dev)
+
+    def to_host(self, D, I):
+        torch = self.torch
+        if torch is None or not (hasattr(D, "is_cuda") and D.is_cuda):
+            return _to_host(D), _to_host(I)
+        slot = self.slots[self.turn]
+        if slot is None or tuple(slot[0].shape) != tuple(D.shape):
+            slot = (torch.empty(tuple(D.shape), dtype=torch.float32).pin_memory(),
+                    torch.empty(tuple(I.shape), dtype=torch.int64).pin_memory())
+            self.slots[self.turn] = slot
+        self.turn ^= 1
+        slot[0].copy_(D, non_blocking=True)
+        slot[1].copy_(I, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return slot[0].numpy(), slot[1].numpy()
+
+
 def run_alpha_sweep(index, id_lookup, qids: Sequence[str], P, S, alphas: Sequence[float], outdir,
                     k: int = 100, qblock: int = 256, tag: str = "onepass-cm", alpha_batch: int = 1,
                     log=None) -> List[pathlib.Path]:
@@ -372,16 +425,17 @@ def run_alpha_sweep(index, id_lookup, qids: Sequence[str], P, S, alphas: Sequenc
     alphas = [float(a) for a in alphas]
     # two-stage pipeline: while the formatter threads (C, GIL released) turn alpha i into text and
     # write its file, the GPU already searches alpha i+1
+    sio = _SweepIO(index, P, S)
     with ThreadPoolExecutor(max_workers=1) as pool:
         pending = None
         for a0 in range(0, len(alphas), max(1, alpha_batch)):
             group = alphas[a0 : a0 + max(1, alpha_batch)]
             t0 = time.perf_counter()
-            D, I = index.search_mixed(P, S, group, k)
-            D, I = _to_host(D), _to_host(I)
-            t1 = time.perf_counter()
-            if pending is not None:
+            D, I = index.search_mixed(sio.P, sio.S, group, k)
+            if pending is not None:  # the slot about to be overwritten belongs to the alpha before the pending one
                 pending.result()
+            D, I = sio.to_host(D, I)
+            t1 = time.perf_counter()
 
             def emit(group=group, D=D, I=I, dt=t1 - t0):
                 for gi, alpha in enumerate(group):
@@ -413,14 +467,15 @@ def run_alpha_sweep_bilingual(index, id2doc: Sequence[str], qids: Sequence[str],
     written: List[pathlib.Path] = []
     alphas = [float(a) for a in alphas]
     ntotal, dim = int(index.ntotal), int(index.d)
+    sio = _SweepIO(index, P, S)
     with ThreadPoolExecutor(max_workers=1) as pool:  # text of alpha i overlaps the search of alpha i+1
         pending = None
         for a0 in range(0, len(alphas), max(1, alpha_batch)):
             group = alphas[a0 : a0 + max(1, alpha_batch)]
-            D, I = index.search_mixed(P, S, group, topk)
-            D, I = _to_host(D), _to_host(I)
+            D, I = index.search_mixed(sio.P, sio.S, group, topk)
             if pending is not None:
                 pending.result()
+            D, I = sio.to_host(D, I)
 
             def emit(group=group, D=D, I=I):
                 for gi, alpha in enumerate(group):
