@@ -4,17 +4,21 @@
 // (reference call sites onepass_dense_mix_run_custom_lang.py:878,
 // onepass_bilingual_mix_hub_custom_lang.py:950).
 //
-// Arithmetic: split precision with fp32 accumulation.  Every operand element x is
-// stored as two fp16 numbers hi = f16(x*2^e), lo = f16(x*2^e - hi) (prologue.cu), so
-// x*2^e = hi + lo up to 2^-22 relative; a score is accumulated by three tcgen05
-// kind::f16 MMAs per k-step into one fp32 TMEM accumulator
+// Arithmetic, PASSES = 1 (default "rescore" precision): ONE tcgen05 kind::f16 MMA pass over the
+// fp16 hi planes, hi = f16(x*2^e) (prologue.cu), fp32 accumulation in TMEM.  The scores are
+// approximate with a rigorous per-query error bound; the selection keeps a margin band and
+// select.cu:rescore_kernel computes exact fp32 scores for the survivors.
+// PASSES = 3 ("split" precision): every operand element is two fp16 numbers hi, lo =
+// f16(x*2^e - hi), x*2^e = hi + lo up to 2^-22 relative, and a score is accumulated by three
+// MMAs per k-step into one accumulator
 //        D += Qlo*Bhi ;  D += Qhi*Blo ;  D += Qhi*Bhi
-// (products of fp16 pairs are exact in fp32; only lo*lo ~ 2^-22 is dropped) and
-// rescaled by the exact power of two 2^-(eq+eb) in the epilogue.
+// (products of fp16 pairs are exact in fp32; only lo*lo ~ 2^-22 is dropped).  Either way the
+// accumulator is rescaled by the exact power of two 2^-(eq+eb) in the epilogue.
 //
 // Structure (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 0    TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of Qhi/Qlo
-//             [128 x 64] and Bhi/Blo [BN x 64] into a ring of smem stages
+//   warp 0    TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of Qhi(/Qlo)
+//             [128 x 64] and Bhi(/Blo) [BN x 64] into a ring of smem stages; corpus tiles
+//             are visited in a golden-ratio block order (TcParams::perm)
 //   warp 1    TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16)
 //   warps 2-5 epilogue: tcgen05.ld the 128 x BN fp32 accumulator (one query row per
 //             thread), compare with the row's threshold tau and append survivors
