@@ -85,3 +85,79 @@ def test_config_c5_ablation_dims(d):
     assert oracle.compare_topk(D[0], I[0], Dr, Ir, rtol=RTOL, atol=ATOL)["ok"]
     Ds, Is = sh.search(Q[0][:4], k, path="stream")
     assert oracle.compare_topk(Ds, Is, Dr[:4], Ir[:4], rtol=RTOL, atol=ATOL)["ok"]
+
+
+def test_config_c2_full_size_sampled_parity():
+    """configs[1] at FULL size (8 841 823 x 1024, 6980 queries, k = 1000, the bench's synthetic corpus):
+    * 96 sampled queries against an independent brute force (cuBLAS fp32 GEMM over the regenerated
+      corpus chunks + running torch.topk) with the tie-aware comparison of the oracle;
+    * every list sorted, ids in range and distinct;
+    * the returned score of sampled (query, id) pairs equals an fp64 recomputation."""
+    import sys
+    import pathlib
+
+    import torch
+
+    root = pathlib.Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root))
+    import bench
+    from cmx.engine import Shard, mix_normalize
+
+    free, _total = torch.cuda.mem_get_info()
+    if free < 70e9:
+        pytest.skip("needs ~65 GB of free HBM")
+    N, d, nq, k = bench.N_FULL, bench.D_FULL, bench.NQ_FULL, bench.K_FULL
+    dev = torch.device("cuda", 0)
+    bench.DATA, bench.ROWS_TOTAL = "iid", N
+    sh = Shard(d, 0)
+    sh.reserve(N)
+    c = 0
+    while c * bench.CHUNK < N:
+        x = bench.corpus_chunk(c, d, dev)
+        sh.add(x[: min(bench.CHUNK, N - c * bench.CHUNK)])
+        del x
+        c += 1
+    P, S = bench.make_queries(nq, d, dev)
+    D, I = sh.search_mixed(P, S, [0.5], k)
+    assert sh.last_stats()["reruns"] == 0 and sh.last_stats()["path"] == 2
+    D, I = D[0], I[0]
+    assert bool((D[:, 1:] <= D[:, :-1]).all()) and int(I.min()) >= 0 and int(I.max()) < N
+    srt = torch.sort(I, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    # independent brute force for a sample of the queries
+    Q = mix_normalize(P, S, [0.5])[0]
+    sel = torch.arange(0, nq, 73, device=dev)[:96]
+    Qs = Q[sel]
+    best_d = torch.full((len(sel), k), -float("inf"), device=dev)
+    best_i = torch.full((len(sel), k), -1, dtype=torch.int64, device=dev)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        c = 0
+        while c * bench.CHUNK < N:
+            x = bench.corpus_chunk(c, d, dev)[: min(bench.CHUNK, N - c * bench.CHUNK)]
+            sc = Qs @ x.T
+            dd, ii = torch.topk(sc, k, dim=1)
+            cat_d = torch.cat([best_d, dd], dim=1)
+            cat_i = torch.cat([best_i, ii + c * bench.CHUNK], dim=1)
+            best_d, pos = torch.topk(cat_d, k, dim=1)
+            best_i = torch.gather(cat_i, 1, pos)
+            if c == 3:  # fp64 recomputation of returned scores whose rows live in this chunk
+                lo, hi = c * bench.CHUNK, c * bench.CHUNK + x.shape[0]
+                Is, Ds = I[sel], D[sel]
+                m = (Is >= lo) & (Is < hi)
+                qi, pi = m.nonzero(as_tuple=True)
+                rows = x[Is[qi, pi] - lo].double()
+                exact = (rows * Qs[qi].double()).sum(dim=1)
+                err = (Ds[qi, pi].double() - exact).abs().max().item()
+                assert len(qi) > 1000 and err < 2e-7, (len(qi), err)
+            del x, sc
+            c += 1
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    rep = oracle.compare_topk(D[sel].cpu().numpy(), I[sel].cpu().numpy(), best_d.cpu().numpy(), best_i.cpu().numpy(),
+                              rtol=RTOL, atol=ATOL)
+    del sh
+    torch.cuda.empty_cache()
+    assert rep["ok"], rep
+    assert rep["id_exact_frac"] > 0.995, rep
