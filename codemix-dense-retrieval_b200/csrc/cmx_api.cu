@@ -206,18 +206,43 @@ static int pick_cap(const cmx_index* ix, int k) {
 
 struct SlabPlan {
   std::vector<int64_t> rows;  // slab sizes, in order; slab 0 is the dense one
+  int spec_slab = -1;         // >= 1: this (last) slab runs under a speculative threshold ...
+  int spec_rank = 0;          // ... the spec_rank-th best score after the slab before it
 };
 
 // Geometric slab schedule: slab 0 fills the (empty) candidate buffers densely, every
 // later slab is sized so that, for rows arriving in exchangeable order, the expected
 // number of rows beating the stale threshold is half of the free room (cap - k).
 // safe = worst-case schedule (every row may pass): rows <= cap - k per slab.
-static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe) {
+//
+// Speculative last slab (spec = true; tensor path, whose block order makes every prefix a uniform
+// sample): once `seen` rows are in, the k-th best of the WHOLE corpus is expected near the
+// (k seen/N)-th best so far.  When that rank is >= kSpecMinRank the rest of the corpus is scored in
+// ONE slab filtered at the 3x deeper rank: ~3k survivors per query (+-3k/sqrt(rank), far inside the
+// buffer), while the chance that fewer than k rows clear it is P(Poisson(r) >= 3r) < 1e-12.  The
+// compaction after that slab VERIFIES the guess per query (k-th best >= threshold + margin); a miss
+// only costs a rerun with spec = false.  This replaces the last 2-3 geometric slabs and their
+// compactions, which is what a small shard of a multi-GPU search spends a fifth of its time on.
+constexpr double kSpecMinRank = 24.0;
+static int g_speculate = 1;  // 0: planned geometric slabs only (experiments)
+
+static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe, bool spec = false, int k_out = 0) {
   SlabPlan pl;
   int64_t seen = 0;
   const int64_t room = cap - k;
   auto round_dn = [&](int64_t v) { return std::max<int64_t>(align, v / align * align); };
   while (seen < N) {
+    if (spec && !safe && g_speculate && seen > 0) {
+      const double r0 = (double)k * (double)seen / (double)N;  // expected rank of the final k-th best
+      const double g = (double)seen * (double)room / (2.0 * (double)k);
+      // worth it only if the geometric plan still needs two or more slabs
+      if (r0 >= kSpecMinRank && std::ceil(3.0 * r0) < (double)k_out && 3.0 * r0 < 0.75 * k && (double)(N - seen) > g) {
+        pl.spec_slab = (int)pl.rows.size();
+        pl.spec_rank = (int)std::ceil(3.0 * r0);
+        pl.rows.push_back(N - seen);
+        break;
+      }
+    }
     int64_t rows;
     if (seen == 0) {
       rows = round_dn(cap);
@@ -260,12 +285,13 @@ static uint64_t pick_perm(int64_t nblk) {
 // superset in the workspace; cmx_search_end rescoring follows once the shards have exchanged their
 // k-th best approximate scores
 static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d,
-                       int64_t id_base, int path, bool rescore, bool safe, cudaStream_t st, bool* overflowed,
-                       bool defer = false) {
+                       int64_t id_base, int path, bool rescore, bool safe, bool speculate, cudaStream_t st,
+                       unsigned* overflowed, bool defer = false) {
   if (path != CMX_PATH_TENSOR) rescore = false;
   const int cap = pick_cap(ix, k);
   const int64_t nq_pad = (nq + 127) / 128 * 128;
-  CMX_TRY(ensure_buf(&ix->ws.tau, &ix->tau_cap, nq_pad));
+  CMX_TRY(ensure_buf(&ix->ws.tau, &ix->tau_cap, 2 * nq_pad));
+  ix->ws.spec = ix->ws.tau + nq_pad;
   CMX_TRY(ensure_buf(&ix->ws.cnt, &ix->cnt_cap, nq_pad));
   CMX_TRY(ensure_buf(&ix->ws.cand, &ix->cand_cap_elems, nq * (int64_t)cap));
   if (!ix->ws.overflow) CMX_CUDA(cudaMalloc((void**)&ix->ws.overflow, sizeof(uint32_t)));
@@ -307,7 +333,7 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
   const int64_t nblk = (ix->n + 255) / 256;
   const uint64_t perm = pick_perm(nblk);
   const int64_t n_plan = (path == CMX_PATH_TENSOR) ? nblk * 256 : ix->n;
-  SlabPlan pl = plan_slabs(n_plan, k_plan, cap, align, safe);
+  SlabPlan pl = plan_slabs(n_plan, k_plan, cap, align, safe, speculate && path == CMX_PATH_TENSOR, k);
   const bool prof = g_profiling && !safe && (int)pl.rows.size() <= kMaxSlabEvents;
   if (prof) CMX_TRY(ensure_events(ix));
   int64_t seen = 0;
@@ -319,19 +345,22 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
     if (path == CMX_PATH_TENSOR) {
       CMX_TRY(launch_tensor_score(ix->Bhi, ix->Blo, ix->n, seen, rows, ix->d_pad, ix->Qhi, ix->Qlo, nq, nq_pad,
                                   ix->q_scale + 1, 1.0f / ix->plane_scale, ix->ws, dense, perm, rescore ? 1 : 3,
-                                  seen > 0 ? (double)k_plan / (double)seen : 1.0, ix->progress, st, ix->sm_count));
+                                  seen > 0 ? (double)(s == pl.spec_slab ? pl.spec_rank : k_plan) / (double)seen : 1.0,
+                                  ix->progress, st, ix->sm_count));
     } else {
       CMX_TRY(launch_stream_score(ix->X, seen, rows, ix->d, q_d, (int)nq, ix->ws, 0, dense, seen, st, ix->sm_count));
     }
     if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 1], st));
     if (dense) CMX_TRY(launch_set_counts(ix->ws, nq, (uint32_t)rows, st));
     const int last = (s == nslabs - 1) ? 1 : 0;
+    const int spec_rank = (s + 1 == pl.spec_slab) ? pl.spec_rank : 0;  // publish the guess for the next slab
+    const int verify = (s == pl.spec_slab) ? 1 : 0;                    // this slab ran under a guess
     if (rescore) {
       // keep the margin band, then (after the last slab) exact fp32 scores + exact top-k
-      CMX_TRY(launch_compact(ix->ws, nq, k, 0, D_d, I_d, id_base, st));
+      CMX_TRY(launch_compact(ix->ws, nq, k, 0, D_d, I_d, id_base, st, spec_rank, verify));
       if (last && !defer) CMX_TRY(launch_rescore(ix->X, ix->d, q_d, ix->ws, nq, k, D_d, I_d, id_base, RescoreCut(), st));
     } else {
-      CMX_TRY(launch_compact(ix->ws, nq, k, last, D_d, I_d, id_base, st));
+      CMX_TRY(launch_compact(ix->ws, nq, k, last, D_d, I_d, id_base, st, spec_rank, verify));
     }
     if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 2], st));
     seen += rows;
@@ -339,7 +368,7 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
   uint32_t ovf = 0;
   CMX_CUDA(cudaMemcpyAsync(&ovf, ix->ws.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CMX_CUDA(cudaStreamSynchronize(st));
-  *overflowed = (ovf != 0);
+  *overflowed = ovf;
   ix->stats.slabs += nslabs;
   ix->stats.score_launches += nslabs * ((path == CMX_PATH_TENSOR) ? 1 : (int)((nq + 7) / 8));
   ix->stats.select_launches += nslabs + (rescore ? 1 : 0);
@@ -383,19 +412,25 @@ static int search_device(cmx_index* ix, const float* q_d, int64_t nq, int k, flo
   for (int64_t q0 = 0; q0 < nq; q0 += kQueryChunk) {
     const int64_t nqc = std::min<int64_t>(kQueryChunk, nq - q0);
     const bool rescore = path == CMX_PATH_TENSOR && ix->precision == CMX_PRECISION_RESCORE && ix->row_norm_max > 0.f;
-    // attempts, cheapest first; stats.reruns = how many of them overflowed a candidate buffer
-    //   rescore, planned slabs : one fp16 pass + exact rescoring of the margin band
-    //   split,   planned slabs : the band of some query outgrew its buffer (thousands of rows within
-    //                            2*eps of the k-th score, e.g. near-duplicates) -- exact scores have no band
-    //   split,   safe slabs    : rows arrive in an order that is adversarial even for the sampled
-    //                            thresholds; slabs so small that no buffer can overflow
-    struct Attempt { bool rescore, safe; };
-    const Attempt chain[3] = {{true, false}, {false, false}, {false, true}};
-    bool ovf = true;
-    for (int a = rescore ? 0 : 1; a < 3 && ovf; ++a) {
-      ix->stats.reruns = std::max(ix->stats.reruns, a - (rescore ? 0 : 1));
-      CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, chain[a].rescore,
-                          chain[a].safe, st, &ovf));
+    // Attempts, cheapest first; stats.reruns = how many of them had to be repeated.  An attempt is a
+    // precision (rescore: one fp16 pass + exact rescoring of the margin band; split: exact scores, no
+    // band) and a slab schedule (0 = geometric slabs with a speculative last slab, 1 = geometric
+    // slabs, 2 = worst-case-safe slabs: so small that no buffer can overflow, split precision only).
+    //   band of some query wider than half its buffer (thousands of rows within 2*eps of the k-th
+    //   score, e.g. near-duplicates)            -> same schedule in split precision
+    //   buffer overflow / speculation not cleared -> next schedule (rows arrive in an order that is
+    //   adversarial for thresholds learnt on a sample); rescore gives way to split before schedule 2
+    bool resc = rescore;
+    int sched = (path == CMX_PATH_TENSOR && g_speculate) ? 0 : 1;  // the stream scorer walks the file in order: no guesses
+    unsigned ovf = 1;
+    for (int attempt = 0; attempt < 6 && ovf; ++attempt) {
+      ix->stats.reruns = std::max(ix->stats.reruns, attempt);
+      CMX_TRY(search_pass(ix, q_d + q0 * ix->d, nqc, k, D_d + q0 * k, I_d + q0 * k, id_base, path, resc, sched == 2,
+                          sched == 0, st, &ovf));
+      if (!ovf) break;
+      if (resc && ((ovf & CMX_OVF_BAND) || sched >= 1)) resc = false;  // split precision, same schedule
+      else if (sched < 2) ++sched;
+      else break;
     }
     if (ovf) { set_error("internal: candidate buffer overflow in safe mode"); return CMX_ERR_INTERNAL; }
   }
@@ -794,8 +829,8 @@ int cmx_search_mixed_begin(cmx_index* ix, const float* P, const float* S, int64_
   CMX_TRY(ensure_buf(&ix->w_dev, &ix->w_cap, 2 * (int64_t)nA));
   CMX_TRY(ensure_buf(&ix->mode_dev, &ix->mode_cap, (int64_t)nA));
   CMX_TRY(mix_on_device(P, S, nq, ix->d, alphas, nA, ix->q_dev, ix->flags_dev, ix->w_dev, ix->mode_dev, st));
-  bool ovf = false;
-  CMX_TRY(search_pass(ix, ix->q_dev, nqt, k, nullptr, nullptr, id_base, CMX_PATH_TENSOR, true, false, st, &ovf, true));
+  unsigned ovf = 0;
+  CMX_TRY(search_pass(ix, ix->q_dev, nqt, k, nullptr, nullptr, id_base, CMX_PATH_TENSOR, true, false, true, st, &ovf, true));
   CMX_TRY(launch_export_scores(ix->ws, nqt, k, scores_out, st));
   CMX_CUDA(cudaStreamSynchronize(st));
   *overflowed = ovf ? 1 : 0;
@@ -892,6 +927,7 @@ int cmx_merge_topk_peers(const float* const* D_parts, const int64_t* const* I_pa
 /* test hook (not in cmx.h): tensor tile width 256 / 128 */
 CMX_API int cmx_debug_set_tensor_tile(int bn) { set_tensor_tile(bn); return CMX_OK; }
 CMX_API int cmx_debug_set_block_order(int on) { g_block_order = on ? 1 : 0; return CMX_OK; }
+CMX_API int cmx_debug_set_speculate(int on) { g_speculate = on ? 1 : 0; return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_window(int w) { set_tensor_window(w); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_small(int on) { set_tensor_small(on); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_pair(int on) { set_tensor_pair(on); return CMX_OK; }

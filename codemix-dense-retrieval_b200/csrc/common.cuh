@@ -80,6 +80,11 @@ __host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return 0xffff
 #define CMX_MAX_PEERS 16
 
 // ---- search workspace (device) ----------------------------------------------
+// bits of SearchWs::overflow[0]: why an attempt has to be repeated
+constexpr unsigned CMX_OVF_BUFFER = 1u;  // more survivors than a candidate buffer holds (row order / bad guess)
+constexpr unsigned CMX_OVF_BAND = 2u;    // rescore mode: the margin band of some query outgrew cap/2
+constexpr unsigned CMX_OVF_SPEC = 4u;    // a speculative threshold was not cleared by the k-th best
+
 struct SearchWs {
   float* tau = nullptr;        // [nq_pad] running k-th best score per query (filter threshold)
   uint32_t* cnt = nullptr;     // [nq_pad] candidates appended per query (may exceed cap)
@@ -87,6 +92,7 @@ struct SearchWs {
   uint32_t* overflow = nullptr;// [1] set when some query's buffer overflowed
   float* margin = nullptr;     // [nq_pad] rescore mode: 2*eps(q), the slack kept below the k-th best
                                // APPROXIMATE score so that the exact top-k is provably contained; else 0
+  float* spec = nullptr;       // [nq_pad] speculative threshold in force for the last slab (lowest-float = none)
   int cap = 0;
   int64_t nq_cap = 0;
 };
@@ -136,8 +142,11 @@ void set_tensor_window(int w);  // progress throttle slack in round-robin iterat
 int launch_ws_init(const SearchWs& ws, int64_t nq, int64_t nq_pad, cudaStream_t st);
 int launch_set_counts(const SearchWs& ws, int64_t nq, uint32_t value, cudaStream_t st);
 // sort candidates, keep top-k, refresh tau; final=1 also writes D/I (+id_base, padded)
+// spec_rank > 0: additionally publish the speculative threshold of the remaining corpus (the
+// spec_rank-th best score so far, minus the margin); verify = 1: the slab just compacted ran under a
+// speculative threshold -- flag `overflow` for any query whose k-th best does not clear it
 int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float* D, int64_t* I,
-                   int64_t id_base, cudaStream_t st);
+                   int64_t id_base, cudaStream_t st, int spec_rank = 0, int verify = 0);
 // rescore mode: exact fp32 scores of every surviving candidate from the fp32 row store, then
 // the exact top-k (score desc, row asc) -> D, I
 struct RescoreCut {

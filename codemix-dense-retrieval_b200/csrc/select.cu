@@ -18,13 +18,14 @@ namespace cmx {
 
 constexpr int kSelThreads = 512;
 
-__global__ void ws_init_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, int64_t nq, int64_t nq_pad) {
+__global__ void ws_init_kernel(float* tau, float* spec, uint32_t* cnt, uint32_t* overflow, int64_t nq, int64_t nq_pad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) overflow[0] = 0;
   if (i < nq_pad) {
     // FAISS's IP heap starts at lowest-float and admits only strictly larger scores;
     // padded (non-existent) queries get +inf so nothing ever passes the filter.
     tau[i] = (i < nq) ? CMX_NEG_PAD : __int_as_float(0x7f800000);
+    if (spec) spec[i] = CMX_NEG_PAD;
     cnt[i] = 0;
   }
 }
@@ -32,7 +33,7 @@ __global__ void ws_init_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, in
 int launch_ws_init(const SearchWs& ws, int64_t nq, int64_t nq_pad, cudaStream_t st) {
   int64_t blocks = (nq_pad + 255) / 256;
   if (blocks < 1) blocks = 1;
-  ws_init_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws.tau, ws.cnt, ws.overflow, nq, nq_pad);
+  ws_init_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws.tau, ws.spec, ws.cnt, ws.overflow, nq, nq_pad);
   CMX_LAUNCHED();
   return CMX_OK;
 }
@@ -190,14 +191,25 @@ __device__ int block_partition(const uint64_t* keys, int n, uint64_t kth, uint64
 // dynamic smem: cap keys, then next_pow2(k) keys for the final sort
 __global__ void __launch_bounds__(kSelThreads)
 compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* __restrict__ tau,
-               uint32_t* __restrict__ overflow, const float* __restrict__ margin, int cap, int k, int final_pass,
-               float* __restrict__ D, int64_t* __restrict__ I, int64_t id_base) {
+               uint32_t* __restrict__ overflow, const float* __restrict__ margin, float* __restrict__ spec, int cap,
+               int k, int final_pass, int spec_rank, int verify, float* __restrict__ D, int64_t* __restrict__ I,
+               int64_t id_base) {
   extern __shared__ __align__(16) uint64_t keys[];
   __shared__ SelectShared sh;
   const int64_t q = blockIdx.x;
   const uint32_t n_raw = cnt[q];
-  if (n_raw > (uint32_t)cap && threadIdx.x == 0) atomicExch(overflow, 1u);
+  if (n_raw > (uint32_t)cap && threadIdx.x == 0) atomicOr(overflow, CMX_OVF_BUFFER);
   const int n = (int)min(n_raw, (uint32_t)cap);
+  // Speculative threshold (see plan_slabs): the slab just scored was filtered with spec[q] > the
+  // provably safe threshold.  That was valid iff the k-th best now clears it by the margin --
+  // then everything within the margin band of the k-th best was above the filter.
+  const float spec_old = (verify && spec) ? spec[q] : CMX_NEG_PAD;
+  if (spec_old > CMX_NEG_PAD && n <= k && threadIdx.x == 0) {
+    // a speculation is only published over >= k kept candidates, so n <= k means nothing new cleared
+    // it: count that as a failed guess (conservative; the chunk is redone with the planned slabs)
+    atomicOr(overflow, CMX_OVF_SPEC);
+    spec[q] = CMX_NEG_PAD;
+  }
   if (!final_pass && n <= k) return;  // nothing to drop yet; tau stays
   uint64_t* buf = cand + q * (int64_t)cap;
   for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = buf[i];
@@ -216,13 +228,30 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
       new_tau = key_score(kth) - m;
       thr = make_key(new_tau, 0xffffffffu);  // smallest key carrying that score
     }
+    if (spec_old > CMX_NEG_PAD && threadIdx.x == 0) {
+      const bool cleared = kth != 0ull && (m > 0.f ? key_score(kth) >= spec_old + m : key_score(kth) > spec_old);
+      if (!cleared) atomicOr(overflow, CMX_OVF_SPEC);
+      spec[q] = CMX_NEG_PAD;
+    }
+    float spec_tau = CMX_NEG_PAD;
+    if (spec_rank > 0 && spec_rank < k && kth != 0ull) {
+      // the spec_rank-th best so far estimates (with a 3x safety factor, plan_slabs) where the k-th
+      // best of the WHOLE corpus will be; `keys` still holds all n candidates
+      __syncthreads();
+      const uint64_t rth = block_kth_largest(keys, n, spec_rank, sh);
+      if (rth != 0ull) spec_tau = key_score(rth) - m;
+    }
     kk = block_partition(keys, n, thr, final_pass ? top : buf, sh);
     if (threadIdx.x == 0) {
       cnt[q] = (uint32_t)kk;
       if (kth != 0ull) tau[q] = new_tau;
+      if (spec_tau > new_tau && kth != 0ull) {  // only a threshold above the safe one is a speculation
+        tau[q] = spec_tau;
+        spec[q] = spec_tau;
+      }
       // rescore mode: the k best plus their margin band must fit half of the buffer (the other half
       // is the room the slab plan counts on, and rescore_kernel holds at most cap/2 keys)
-      if (m > 0.f && kk > cap / 2) atomicExch(overflow, 1u);
+      if (m > 0.f && kk > cap / 2) atomicOr(overflow, CMX_OVF_BAND);
     }
   } else if (final_pass) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) top[i] = keys[i];
@@ -280,7 +309,7 @@ rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, 
   const uint32_t n_raw = cnt[q];
   if (threadIdx.x == 0) {
     s_m = 0;
-    if (n_raw > (uint32_t)cap) atomicExch(overflow, 1u);
+    if (n_raw > (uint32_t)cap) atomicOr(overflow, CMX_OVF_BUFFER);
   }
   const int n = (int)min(n_raw, (uint32_t)cap);
   for (int i = threadIdx.x; i < d; i += blockDim.x) qv[i] = Q[q * (int64_t)d + i];
@@ -307,7 +336,7 @@ rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, 
     if (valid && pos < (uint32_t)half) keys[pos] = key;
   }
   __syncthreads();
-  if (s_m > (uint32_t)half && threadIdx.x == 0) atomicExch(overflow, 1u);  // compact_kernel flags this first
+  if (s_m > (uint32_t)half && threadIdx.x == 0) atomicOr(overflow, CMX_OVF_BAND);  // compact_kernel flags this first
   const int m = (int)min(s_m, (uint32_t)half);
   // 2. exact scores, two rows per warp and iteration
   const bool vec = (d & 3) == 0;
@@ -376,12 +405,13 @@ static int pow2_at_least(int n) {
 }
 
 int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float* D, int64_t* I,
-                   int64_t id_base, cudaStream_t st) {
+                   int64_t id_base, cudaStream_t st, int spec_rank, int verify) {
   if (nq == 0) return CMX_OK;
   const size_t smem = ((size_t)ws.cap + pow2_at_least(k)) * sizeof(uint64_t);
   CMX_CUDA(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  compact_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(ws.cand, ws.cnt, ws.tau, ws.overflow, ws.margin, ws.cap, k,
-                                                          final_pass, D, I, id_base);
+  compact_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(ws.cand, ws.cnt, ws.tau, ws.overflow, ws.margin,
+                                                          ws.spec ? ws.spec : nullptr, ws.cap, k, final_pass,
+                                                          ws.spec ? spec_rank : 0, ws.spec ? verify : 0, D, I, id_base);
   CMX_LAUNCHED();
   return CMX_OK;
 }

@@ -296,9 +296,9 @@ def test_adversarial_order_triggers_safe_rerun(path, precision):
     finally:
         _lib.check(_lib.lib().cmx_debug_set_block_order(1))
     st = sh.last_stats()
-    # stream / split: planned slabs overflow, safe slabs succeed (1); rescore: the planned slabs
-    # overflow in both precisions before the safe schedule is reached (2)
-    assert st["reruns"] == (2 if (path == "tensor" and precision == "rescore") else 1), st
+    # stream: planned slabs overflow, safe slabs succeed (1); tensor: the schedule with a speculative
+    # last slab fails first (2), and the rescore precision gives way to split before the safe one (3)
+    assert st["reruns"] == (1 if path == "stream" else (3 if precision == "rescore" else 2)), st
     _check(D, I, X, Q, 100)
 
 
@@ -330,6 +330,41 @@ def test_block_order_makes_nonstationary_corpus_benign(nq, precision):
         _lib.check(_lib.lib().cmx_debug_set_block_order(1))
     assert sh.last_stats()["reruns"] >= 1, sh.last_stats()
     _check(D2, I2, X, Q, 100)  # same answer either way
+
+
+def test_speculative_last_slab_equals_planned_slabs(precision):
+    """The tensor path scores the tail of the corpus in ONE slab under a guessed threshold (verified
+    per query afterwards): fewer slabs, identical results; a guess that cannot hold (rows sorted so
+    that the tail is systematically better, in file order) is detected and redone."""
+    from cmx import _lib
+
+    rng = np.random.default_rng(23)
+    X, Q = _aniso(rng, 150000, 128), _aniso(rng, 300, 128)
+    sh = _shard(X)
+    k = 1000  # guess after the dense slab: rank 3 * 1341 * 8192 / 150000 = 220 of the 8192 rows seen
+    D, I = sh.search(Q, k, path="tensor")
+    st = sh.last_stats()
+    _lib.check(_lib.lib().cmx_debug_set_speculate(0))
+    try:
+        D0, I0 = sh.search(Q, k, path="tensor")
+        st0 = sh.last_stats()
+    finally:
+        _lib.check(_lib.lib().cmx_debug_set_speculate(1))
+    assert st["reruns"] == 0 and st0["reruns"] == 0
+    assert st["slabs"] < st0["slabs"], (st, st0)
+    assert np.array_equal(I, I0) and np.array_equal(D, D0)
+    _check(D, I, X, Q, k)
+    # file order + ascending scores: the guess made on the head of the file fails its verification
+    u = Q[:1]
+    Xs = X[np.argsort(X @ u[0])]
+    sh2 = _shard(Xs)
+    _lib.check(_lib.lib().cmx_debug_set_block_order(0))
+    try:
+        D2, I2 = sh2.search(Q[:40], k, path="tensor")
+    finally:
+        _lib.check(_lib.lib().cmx_debug_set_block_order(1))
+    assert sh2.last_stats()["reruns"] >= 1
+    _check(D2, I2, Xs, Q[:40], k)
 
 
 def test_incremental_add_and_reconstruct(precision):
