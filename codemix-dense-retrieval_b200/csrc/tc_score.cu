@@ -270,7 +270,6 @@ __device__ __forceinline__ void epilogue_filter_tile_two_pass(const TcParams& p,
     if (n) chunk_bits |= 1u << c;
   }
   if (!__any_sync(0xffffffffu, total != 0)) return;
-  if (p.flags & 8) return;  // timing experiment: filter only
   uint32_t pos = 0;
   if (total) pos = atomicAdd(&p.cnt[q], total);
   uint64_t* qcand = p.cand + q * (int64_t)p.cap;
@@ -309,7 +308,6 @@ struct EpiStage {
 __device__ __forceinline__ void epilogue_flush(const TcParams& p, const EpiStage& st, int& nst, int64_t q, float inv,
                                                int64_t tile_row0) {
   if (nst == 0) return;
-  if (p.flags & 8) { nst = 0; return; }  // timing experiment: filter only
   const uint32_t pos = atomicAdd(&p.cnt[q], (uint32_t)nst);
   uint64_t* qcand = p.cand + q * (int64_t)p.cap;
   for (int i = 0; i < nst; ++i) {

@@ -16,7 +16,7 @@ for N in [int(v) for v in sys.argv[1].split(",")]:
     while c * bench.CHUNK < N:
         x = bench.corpus_chunk(c, d, dev)
         sh.add(x[: min(bench.CHUNK, N - c * bench.CHUNK)]); del x; c += 1
-    for prec, flags in (("rescore", 0), ("rescore", 16), ("rescore", 32), ("rescore", 8)):
+    for prec, flags in (("rescore", 0), ("rescore", 16), ("rescore", 32)):
         sh.set_precision(prec)
         _lib.check(_lib.lib().cmx_debug_set_tensor_flags(flags))
         for _ in range(2):
