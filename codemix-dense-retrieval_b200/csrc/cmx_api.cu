@@ -262,19 +262,45 @@ static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe, bool
   return pl;
 }
 
-// Block multiplier of the tensor path's processing order (TcParams::perm): the odd-or-not integer
-// nearest to nblk / golden ratio that is coprime to nblk.  j -> (j * perm) mod nblk is then a
-// permutation of the blocks whose every prefix is spread evenly over the corpus (three-distance
-// theorem), so thresholds learnt on the first slabs hold for a corpus that is not stationary in
-// file order (EN rows then ZH rows in the bilingual index; passages grouped by source document).
+// Block multiplier of the tensor path's processing order (TcParams::perm): an integer P near
+// nblk / golden ratio, coprime to nblk, so that j -> (j * P) mod nblk is a permutation of the blocks
+// whose prefixes are spread evenly over the corpus (three-distance theorem) -- thresholds learnt on
+// the first slabs then hold for a corpus that is not stationary in file order (EN rows then ZH
+// rows in the bilingual index; passages grouped by source document).  Rounding nblk/phi to an
+// integer can ruin this: P/nblk is rational, and one large partial quotient a_i in its continued
+// fraction makes prefixes longer than the convergent's denominator pile up next to earlier
+// points (21346/34539 = [0;1,...,1,73,2]: beyond 233 blocks the new ones land 2 blocks from old
+// ones).  So the candidates within +-256 of nblk/phi are ranked by their largest partial quotient.
 static int g_block_order = 1;  // 0: file order (experiments / adversarial tests)
 static uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
+static uint64_t max_partial_quotient(uint64_t p, uint64_t q) {  // of p/q, 0 < p < q, skipping the leading 0
+  uint64_t worst = 0;
+  uint64_t num = q, den = p;  // q/p = a1 + ...
+  int depth = 0;
+  while (den) {
+    const uint64_t a = num / den, r = num % den;
+    // the last quotient of a finite expansion is an artefact of termination ([..., a] = [..., a-1, 1])
+    if (r != 0 || depth == 0) worst = std::max(worst, a);
+    else worst = std::max(worst, a - 1);
+    num = den;
+    den = r;
+    ++depth;
+  }
+  return worst;
+}
 static uint64_t pick_perm(int64_t nblk) {
   if (!g_block_order || nblk < 3) return 1;
-  uint64_t p = (uint64_t)((double)nblk * 0.6180339887498949);
-  if (p < 1) p = 1;
-  while (gcd_u64(p, (uint64_t)nblk) != 1) ++p;  // nblk - 1 is always coprime, so this ends below nblk
-  return p;
+  const uint64_t n = (uint64_t)nblk;
+  const uint64_t centre = std::max<uint64_t>(1, (uint64_t)((double)nblk * 0.6180339887498949));
+  uint64_t best = 0, best_q = ~0ull, best_dist = ~0ull;
+  const uint64_t lo = centre > 256 ? centre - 256 : 1, hi = std::min<uint64_t>(n - 1, centre + 256);
+  for (uint64_t p = lo; p <= hi; ++p) {
+    if (gcd_u64(p, n) != 1) continue;
+    const uint64_t q = max_partial_quotient(p, n);
+    const uint64_t dist = p > centre ? p - centre : centre - p;
+    if (q < best_q || (q == best_q && dist < best_dist)) { best = p; best_q = q; best_dist = dist; }
+  }
+  return best ? best : n - 1;  // n - 1 is always coprime
 }
 
 // one pass over the corpus for queries q_d[0..nq) (nq <= kQueryChunk)
@@ -928,6 +954,20 @@ int cmx_merge_topk_peers(const float* const* D_parts, const int64_t* const* I_pa
 CMX_API int cmx_debug_set_tensor_tile(int bn) { set_tensor_tile(bn); return CMX_OK; }
 CMX_API int cmx_debug_set_block_order(int on) { g_block_order = on ? 1 : 0; return CMX_OK; }
 CMX_API int cmx_debug_set_speculate(int on) { g_speculate = on ? 1 : 0; return CMX_OK; }
+/* test hooks (host logic, no GPU needed): the slab schedule of a tensor-path search and the block multiplier */
+CMX_API int cmx_debug_plan_slabs(int64_t ntotal, int k, int cap, int rescore, int safe, int speculate, int64_t* rows_out,
+                                 int max_slabs, int* nslabs, int* spec_slab, int* spec_rank) {
+  CMX_CHECK(ntotal > 0 && k >= 1 && cap >= 2 * k && rows_out && nslabs && spec_slab && spec_rank, "bad argument");
+  const int64_t nblk = (ntotal + 255) / 256;
+  const int k_plan = rescore ? std::min(cap / 2, k + k / 3 + 8) : k;
+  SlabPlan pl = plan_slabs(nblk * 256, k_plan, cap, 256, safe != 0, speculate != 0, k);
+  *nslabs = (int)pl.rows.size();
+  *spec_slab = pl.spec_slab;
+  *spec_rank = pl.spec_rank;
+  for (int i = 0; i < *nslabs && i < max_slabs; ++i) rows_out[i] = pl.rows[(size_t)i];
+  return CMX_OK;
+}
+CMX_API uint64_t cmx_debug_block_perm(int64_t nblk) { return pick_perm(nblk); }
 CMX_API int cmx_debug_set_tensor_window(int w) { set_tensor_window(w); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_small(int on) { set_tensor_small(on); return CMX_OK; }
 CMX_API int cmx_debug_set_tensor_pair(int on) { set_tensor_pair(on); return CMX_OK; }

@@ -226,6 +226,77 @@ def test_library_exports_every_declared_symbol():
     assert L.cmx_version() >= 100
 
 
+def _plan(n, k, cap, rescore=1, safe=0, spec=1):
+    from cmx import _lib
+
+    rows = (ctypes.c_int64 * 4096)()
+    ns, ss, sr = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(_lib.lib().cmx_debug_plan_slabs(n, k, cap, rescore, safe, spec, rows, 4096, ctypes.byref(ns), ctypes.byref(ss),
+                                               ctypes.byref(sr)))
+    return [int(rows[i]) for i in range(min(ns.value, 4096))], ns.value, ss.value, sr.value
+
+
+def test_slab_schedule_invariants():
+    """Host logic of the tensor path's slab schedule: whole 256-row blocks, dense first slab,
+    geometric growth, speculative last slab only when its rank estimate is trustworthy, safe slabs bounded."""
+    n = 8_841_823
+    npad = (n + 255) // 256 * 256
+    rows, ns, ss, sr = _plan(n, 1000, 8192)
+    assert rows == [8192, 20736, 73728, 262144, npad - 364800] and ss == 4
+    seen = sum(rows[:4])
+    r0 = 1341 * seen / npad
+    assert r0 >= 24 and sr == int(np.ceil(3 * r0)) and sr < 1000
+    rows_g, ns_g, ss_g, _ = _plan(n, 1000, 8192, spec=0)
+    assert ss_g == -1 and ns_g == 7 and rows_g[:4] == rows[:4] and sum(rows_g) == npad
+    for a, b in zip(rows_g[1:-1], rows_g[2:-1]):
+        assert 3.0 < b / a < 3.7  # x(1 + (C - k') / 2k') per slab
+    # a 1.1 M-row shard of an 8-GPU search: guess after the second slab
+    rows8, ns8, ss8, sr8 = _plan(1_105_228, 1000, 8192)
+    assert ns8 == 3 and ss8 == 2 and 72 <= sr8 < 1000
+    # small k: the geometric plan is already 3-4 slabs and the rank estimate never qualifies
+    assert _plan(n, 100, 8192)[2] == -1 and _plan(n, 10, 8192)[2] == -1
+    # split precision plans on k itself
+    rows_s, _, ss_s, sr_s = _plan(n, 1000, 8192, rescore=0)
+    assert sum(rows_s) == npad and ss_s >= 1 and sr_s < 1000
+    for r in (rows, rows_g, rows8, rows_s):
+        assert all(v % 256 == 0 and v > 0 for v in r) and r[0] == 8192
+    # worst-case-safe schedule: no slab larger than the free room; tiny buffers get pieces of one block
+    rows_safe, ns_safe, ss_safe, _ = _plan(100_000, 1000, 8192, rescore=0, safe=1)
+    assert ss_safe == -1 and max(rows_safe[1:]) <= 8192 - 1000 and sum(rows_safe) == (100_000 + 255) // 256 * 256
+    rows_tiny, _, _, _ = _plan(3000, 100, 256, rescore=0, safe=1)
+    assert rows_tiny[0] == 256 and max(rows_tiny[1:]) <= 156 and sum(rows_tiny) == 3072
+    pos = 256
+    for v in rows_tiny[1:]:
+        assert pos // 256 == (pos + v - 1) // 256  # never straddles a block
+        pos += v
+
+
+def test_block_order_is_a_well_spread_permutation():
+    """pick_perm: position j -> block (j * P) mod nblk is a permutation, and every prefix is spread evenly
+    over the corpus (what makes thresholds learnt on the first slabs valid for all rows)."""
+    from math import gcd
+
+    from cmx import _lib
+
+    L = _lib.lib()
+    for nblk in (1, 2, 3, 7, 20, 36, 157, 4096, 34539, 69077):
+        P = int(L.cmx_debug_block_perm(nblk))
+        assert 1 <= P < max(nblk, 2) and gcd(P, nblk) == 1
+        if nblk > 4096:
+            continue
+        order = [(j * P) % nblk for j in range(nblk)]
+        assert sorted(order) == list(range(nblk))
+    nblk = 34539  # C2
+    P = int(L.cmx_debug_block_perm(nblk))
+    assert abs(P / nblk - 0.6180339887) < 1e-3
+    for m in (32, 113, 401, 1425):  # prefixes = the first slabs
+        pts = np.sort((np.arange(m, dtype=np.int64) * P) % nblk)
+        gaps = np.diff(np.concatenate([pts, [pts[0] + nblk]]))
+        assert gaps.max() <= 3.3 * nblk / m, (m, gaps.max(), nblk / m)  # three-distance theorem: no big holes
+        half = (pts < nblk // 2).sum()
+        assert abs(half - m / 2) <= 2  # both halves of the file (EN rows, ZH rows) equally sampled
+
+
 def test_no_gpu_fails_loudly():
     """Without a CUDA device the product path must raise, never fall back to the CPU."""
     import torch
