@@ -217,13 +217,16 @@ struct SlabPlan {
 //
 // Speculative last slab (spec = true; tensor path, whose block order makes every prefix a uniform
 // sample): once `seen` rows are in, the k-th best of the WHOLE corpus is expected near the
-// (k seen/N)-th best so far.  When that rank is >= kSpecMinRank the rest of the corpus is scored in
+// (k seen/N)-th best so far.  When that rank r is >= kSpecMinRank the rest of the corpus is scored in
 // ONE slab filtered at the 3x deeper rank: ~3k survivors per query (+-3k/sqrt(rank), far inside the
 // buffer), while the chance that fewer than k rows clear it is P(Poisson(r) >= 3r) < 1e-12.  The
 // compaction after that slab VERIFIES the guess per query (k-th best >= threshold + margin); a miss
 // only costs a rerun with spec = false.  This replaces the last 2-3 geometric slabs and their
 // compactions, which is what a small shard of a multi-GPU search spends a fifth of its time on.
-constexpr double kSpecMinRank = 24.0;
+// The Poisson figure assumes independent rows; if a query's best rows come in clumps of c adjacent
+// rows (passages of one document) the effective rank is r0/c -- at r0 >= 32 and c = 3 a miss is still
+// < 1e-7 per query, and a miss is never wrong, only a second pass.
+constexpr double kSpecMinRank = 32.0;
 static int g_speculate = 1;  // 0: planned geometric slabs only (experiments)
 
 static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe, bool spec = false, int k_out = 0) {
