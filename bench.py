@@ -62,8 +62,13 @@ def parse_args():
 
 
 def workload_name(a) -> str:
-    full = (a.rows, a.dim, a.nq, a.k) == (N_FULL, D_FULL, NQ_FULL, K_FULL)
-    base = "C2 (BASELINE configs[1]): EN monolingual full mMARCO shape" if full else "REDUCED development shape"
+    shape = (a.rows, a.dim, a.nq, a.k)
+    if shape == (N_FULL, D_FULL, NQ_FULL, K_FULL):
+        base = "C2 (BASELINE configs[1]): EN monolingual full mMARCO shape"
+    elif shape == (2 * N_FULL, D_FULL, NQ_FULL, K_FULL):
+        base = "C3 (BASELINE configs[2]): EN+ZH bilingual combined index shape"
+    else:
+        base = "other shape (not the headline configuration)"
     var = "" if a.data == "iid" else f", data variant {a.data}"
     return f"{base}: {a.rows} x {a.dim} fp32 flat-IP, {a.nq} queries, alpha={ALPHA}, k={a.k}{var}"
 
