@@ -210,6 +210,19 @@ def test_faiss_shim_host_semantics():
     with pytest.raises(RuntimeError):
         faiss.IndexIDMap(idx.index)
     assert faiss.IndexShardsIP.split(10, 4) == [0, 2, 5, 7, 10]
+    # IndexIDMap id translation: -1 stays -1; the identity map (ids 0..n-1 in row order) is recognised
+    I = np.array([[1, 0, -1], [0, -1, -1]], dtype=np.int64)
+    assert idx._translate(I).tolist() == [[20, 10, -1], [10, -1, -1]]
+    idx.add_with_ids(np.ones((1, 4), np.float32), [7])  # the cached map follows later adds
+    assert idx._translate(np.array([[2, 1, -1]])).tolist() == [[7, 20, -1]]
+    ident = faiss.IndexIDMap(faiss.IndexFlatIP(4))
+    ident.add_with_ids(np.zeros((3, 4), np.float32), np.arange(3))
+    assert ident._translate(I) is I
+    ident.add_with_ids(np.zeros((2, 4), np.float32), [3, 9])  # no longer the identity
+    assert ident._translate(np.array([[4, 3, 0, -1]])).tolist() == [[9, 3, 0, -1]]
+    ident.reset()
+    ident.add_with_ids(np.zeros((2, 4), np.float32), [5, 6])
+    assert ident._translate(np.array([[1, 0]])).tolist() == [[6, 5]]
 
 
 def test_library_exports_every_declared_symbol():
