@@ -484,3 +484,11 @@ def read_index(path, io_flags: int = 0):
     from .io import read_index as _r
 
     return _r(path)
+
+
+def read_index_to_gpu(path, device: int = 0):
+    """Extension (not in faiss): read_index + index_cpu_to_gpu without the host-resident copy --
+    the file is validated, then streamed chunk by chunk into the device index."""
+    from .io import read_index_to_gpu as _r
+
+    return _r(path, device)

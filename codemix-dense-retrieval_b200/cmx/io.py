@@ -104,6 +104,96 @@ def read_index(path, device: Optional[int] = None):
         raise RuntimeError(f"read_index: unsupported index type {fourcc!r} (only IxMp / IxFI)")
 
 
+def inspect_index(path) -> dict:
+    """Validate the layout of an ``index.faiss`` file WITHOUT loading the vectors: fourccs, both
+    headers, the float count, the id_map length and the total file size must all agree.  Returns
+    ``{"kind": "IxMp"|"IxFI", "d", "ntotal", "vec_offset", "ids_offset"|None}``."""
+    path = pathlib.Path(path)
+    size = path.stat().st_size
+    with open(path, "rb") as fh:
+        kind = fh.read(4)
+        if kind not in (b"IxMp", b"IxFI"):
+            raise RuntimeError(f"read_index: unsupported index type {kind!r} (only IxMp / IxFI)")
+        outer = None
+        if kind == b"IxMp":
+            outer = _read_header(fh)
+            inner = fh.read(4)
+            if inner != b"IxFI":
+                raise RuntimeError(f"read_index: nested index {inner!r} is not IndexFlatIP (IxFI)")
+        d, ntotal = _read_header(fh)
+        if outer is not None and outer != (d, ntotal):
+            raise RuntimeError(f"read_index: IxMp header {outer} disagrees with the nested IxFI header {(d, ntotal)}")
+        raw = fh.read(8)
+        if len(raw) != 8:
+            raise RuntimeError("read_index: truncated vector block")
+        (count,) = struct.unpack("<Q", raw)
+        if count != ntotal * d:
+            raise RuntimeError(f"read_index: vector block holds {count} floats, expected {ntotal}*{d}")
+        vec_offset = fh.tell()
+        end = vec_offset + 4 * count
+        ids_offset = None
+        if kind == b"IxMp":
+            fh.seek(end)
+            raw = fh.read(8)
+            if len(raw) != 8:
+                raise RuntimeError("read_index: truncated id_map")
+            (n_ids,) = struct.unpack("<Q", raw)
+            if n_ids != ntotal:
+                raise RuntimeError(f"read_index: id_map has {n_ids} ids for {ntotal} rows")
+            ids_offset = end + 8
+            end = ids_offset + 8 * n_ids
+        if size != end:
+            raise RuntimeError(f"read_index: file is {size} bytes, layout needs {end}")
+    return {"kind": kind.decode(), "d": d, "ntotal": ntotal, "vec_offset": vec_offset, "ids_offset": ids_offset}
+
+
+def stream_index_rows(path, sink, row0: int = 0, row1: Optional[int] = None, chunk_rows: int = _CHUNK_ROWS,
+                      info: Optional[dict] = None) -> np.ndarray:
+    """Feed rows [row0, row1) of an ``index.faiss`` file to ``sink.add(x)`` in chunks of ``chunk_rows``
+    (256 MB at d = 1024) and return their user ids -- the loader for indexes that do not fit, or
+    should not transit, host memory: a GPU index (``GpuIndexFlatIP``) or one rank's row range of a
+    ``ShardedIndex`` (``sink.add_local``).  faiss.read_index + index_cpu_to_gpu
+    (onepass_dense_mix_run_custom_lang.py:250,658-664) needs the whole 36 GB twice in host RAM."""
+    info = info or inspect_index(path)
+    d, ntotal = info["d"], info["ntotal"]
+    row1 = ntotal if row1 is None else int(row1)
+    if not (0 <= row0 <= row1 <= ntotal):
+        raise RuntimeError(f"stream_index_rows: bad row range [{row0}, {row1}) of {ntotal}")
+    add = getattr(sink, "add_local", None) or sink.add
+    with open(path, "rb") as fh:
+        fh.seek(info["vec_offset"] + 4 * d * row0)
+        r = row0
+        while r < row1:
+            n = min(chunk_rows, row1 - r)
+            rows = np.fromfile(fh, dtype="<f4", count=n * d)
+            if rows.shape[0] != n * d:
+                raise RuntimeError("read_index: truncated vector block")
+            add(rows.reshape(n, d))
+            r += n
+        if info["ids_offset"] is None:
+            return np.arange(row0, row1, dtype=np.int64)
+        fh.seek(info["ids_offset"] + 8 * row0)
+        ids = np.fromfile(fh, dtype="<i8", count=row1 - row0)
+        if ids.shape[0] != row1 - row0:
+            raise RuntimeError("read_index: truncated id_map")
+    return ids.astype(np.int64, copy=False)
+
+
+def read_index_to_gpu(path, device: int = 0):
+    """``index.faiss`` -> ``IndexIDMap(GpuIndexFlatIP)`` (or a bare ``GpuIndexFlatIP`` for an IxFI file)
+    without a host-resident copy: the equivalent of read_index + index_cpu_to_gpu."""
+    from . import faiss as F
+
+    info = inspect_index(path)
+    flat = F.GpuIndexFlatIP(info["d"], device=device)
+    out = F.IndexIDMap(flat) if info["kind"] == "IxMp" else flat
+    flat.reserveMemory(info["ntotal"])
+    ids = stream_index_rows(path, flat, info=info)
+    if info["kind"] == "IxMp":
+        out._ids = [ids]
+    return out
+
+
 def _read_flat(fh, F, fourcc_read: bool = False):
     if not fourcc_read:
         fourcc = fh.read(4)

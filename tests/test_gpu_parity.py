@@ -496,6 +496,11 @@ def test_faiss_shim_dropin_flow(tmp_path):
         gpu.search(Q, 5000)  # k above the engine cap -> RuntimeError like faiss-gpu
     back = faiss.index_gpu_to_cpu(gpu)
     assert back.ntotal == 6000 and np.array_equal(back.index.reconstruct_n(0, 6000), X)
+    # streamed straight into the device index (no host-resident copy): same answers
+    direct = faiss.read_index_to_gpu(str(tmp_path / "index.faiss"), 0)
+    assert direct.ntotal == 6000 and direct.index.getDevice() == 0
+    D3, I3 = direct.search(Q, 100)
+    assert np.array_equal(I3, I) and np.array_equal(D3, D)
 
 
 def test_run_alpha_sweep_files(tmp_path):

@@ -192,6 +192,47 @@ def test_index_file_roundtrip(tmp_path):
         faiss.read_index(tmp_path / "trunc.faiss")
 
 
+def test_index_file_validator_and_streaming_reader(tmp_path):
+    """inspect_index checks the whole layout without loading vectors; stream_index_rows feeds any row
+    range to a sink (a GPU index or one rank's shard in production, a host index here)."""
+    import cmx.faiss as faiss
+
+    rng = np.random.default_rng(12)
+    n, d = 1000, 24
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    ids = rng.permutation(5000)[:n].astype(np.int64)
+    idx = faiss.IndexIDMap(faiss.IndexFlatIP(d))
+    idx.add_with_ids(X, ids)
+    path = tmp_path / "index.faiss"
+    faiss.write_index(idx, str(path))
+    info = cio.inspect_index(path)
+    assert info["kind"] == "IxMp" and (info["d"], info["ntotal"]) == (d, n)
+    for r0, r1, chunk in ((0, n, 64), (0, n, 4096), (137, 611, 100), (999, 1000, 7), (500, 500, 8)):
+        sink = faiss.IndexFlatIP(d)
+        got = cio.stream_index_rows(path, sink, r0, r1, chunk_rows=chunk)
+        assert got.tolist() == ids[r0:r1].tolist() and sink.ntotal == r1 - r0
+        if r1 > r0:
+            assert np.array_equal(sink.reconstruct_n(0, r1 - r0), X[r0:r1])
+    with pytest.raises(RuntimeError):
+        cio.stream_index_rows(path, faiss.IndexFlatIP(d), 10, n + 1)
+    flat_path = tmp_path / "flat.faiss"
+    faiss.write_index(idx.index, str(flat_path))
+    sink = faiss.IndexFlatIP(d)
+    assert cio.inspect_index(flat_path)["kind"] == "IxFI"
+    assert cio.stream_index_rows(flat_path, sink, 3, 9).tolist() == [3, 4, 5, 6, 7, 8]
+    # corrupted files are rejected before a single vector is read
+    raw = path.read_bytes()
+    bad = {"truncated": raw[:-5], "trailing": raw + b"\0" * 8, "fourcc": b"IxF2" + raw[4:],
+           "count": raw[:4 + 33 + 4 + 33] + (n * d + 1).to_bytes(8, "little") + raw[4 + 33 + 4 + 33 + 8:],
+           "outer_ntotal": raw[:8] + (n + 1).to_bytes(8, "little") + raw[16:],
+           "metric": raw[:4 + 29] + (1).to_bytes(4, "little") + raw[4 + 33:]}
+    for name, blob in bad.items():
+        f = tmp_path / f"bad_{name}.faiss"
+        f.write_bytes(blob)
+        with pytest.raises(RuntimeError):
+            cio.inspect_index(f)
+
+
 def test_faiss_shim_host_semantics():
     import cmx.faiss as faiss
 
