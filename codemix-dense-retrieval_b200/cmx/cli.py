@@ -141,10 +141,10 @@ def main_mono(argv: Optional[Sequence[str]] = None) -> int:
     if cached is None:
         raise SystemExit(f"No cached index for '{doc_lang}' under {args.index_root}; encoding the corpus is out of scope "
                          "(build it with the reference's encode_multilingual_corpus.py).")
-    id_lookup, kept, _ = cio.read_docid_map(cached["map_path"])
-    logging.info("Cached index ready for %s: %d vectors", doc_lang, len(kept))
+    id_lookup, docids_text, n_kept = cio.read_docid_table(cached["map_path"])
+    logging.info("Cached index ready for %s: %d vectors", doc_lang, n_kept)
     pathlib.Path(args.docids_out).parent.mkdir(parents=True, exist_ok=True)
-    pathlib.Path(args.docids_out).write_text("\n".join(sorted(set(kept))))
+    pathlib.Path(args.docids_out).write_text(docids_text)
     index = _place(cached["index"], args)
     _, qids, P, S = _load_queries(args)
     alphas = runloop.parse_alpha_list(args.cm_alphas)

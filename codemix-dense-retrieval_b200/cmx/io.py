@@ -246,6 +246,80 @@ def read_docid_map(path) -> Tuple[Dict[int, str], List[str], List[str]]:
     return id_lookup, kept, derived
 
 
+def read_docid_table(path):
+    """Fast path of ``read_docid_map`` for the run loops: -> (DocTable int_id -> base_id, text of
+    ``"\\n".join(sorted(set(base_ids)))`` for --docids_out, number of rows).
+
+    A clean 8.8 M-line map (plain decimal ids, a fixed number of tab-separated columns, no CR, no
+    repeated int ids) is parsed by pyarrow's multi-threaded CSV reader straight into the
+    one-buffer-plus-offsets layout the C formatter reads -- ~5 s instead of ~19 s of per-line
+    Python.  Anything else (or no pyarrow) goes through ``read_docid_map``, which follows the
+    reference readers literally (onepass_dense_mix_run_custom_lang.py:632-644)."""
+    from .runloop import DocTable, StrTable
+
+    try:
+        table = _docid_table_arrow(path, DocTable, StrTable)
+        if table is not None:
+            return table
+    except Exception:  # any surprise in the file: take the literal reader
+        pass
+    id_lookup, kept, _ = read_docid_map(path)
+    return DocTable(id_lookup), "\n".join(sorted(set(kept))), len(kept)
+
+
+def _docid_table_arrow(path, DocTable, StrTable):
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    import pyarrow.csv as pcsv
+
+    with open(path, "rb") as fh:
+        header = fh.readline()
+        if b"\r" in header:
+            return None
+        names = header.decode("utf-8").rstrip("\n").split("\t")
+        if len(names) < 3 or len(set(names)) != len(names):
+            return None
+    tbl = pcsv.read_csv(
+        path,
+        parse_options=pcsv.ParseOptions(delimiter="\t", quote_char=False, escape_char=False, newlines_in_values=False),
+        convert_options=pcsv.ConvertOptions(column_types={n: pa.string() for n in names}, strings_can_be_null=False,
+                                            include_columns=[names[0], names[2]]))
+    n = tbl.num_rows
+    if n == 0:
+        return None
+    base = tbl.column(1).combine_chunks()
+    if base.null_count or pc.any(pc.match_substring(base, "\r")).as_py():
+        return None
+    first = tbl.column(0).combine_chunks()
+    # plain ASCII decimal only: anything int() would accept beyond that (spaces, '+', '_', other scripts) is rare
+    if not pc.all(pc.match_substring_regex(first, "^-?[0-9]+$")).as_py():
+        return None
+    ids = pc.cast(first, pa.int64()).to_numpy(zero_copy_only=False)
+    if ids.shape[0] > 1 and not np.all(ids[1:] > ids[:-1]):  # not strictly increasing: order / duplicates matter
+        order = np.argsort(ids, kind="stable")
+        ids_sorted = ids[order]
+        if np.any(ids_sorted[1:] == ids_sorted[:-1]):
+            return None  # a repeated int id: the dict semantics (last wins) live in read_docid_map
+        base_sorted = base.take(pa.array(order))
+    else:
+        ids_sorted, base_sorted = ids, base
+    off = np.frombuffer(base_sorted.buffers()[1], dtype=np.int32, count=n + 1, offset=base_sorted.offset * 4).astype(np.int64)
+    data = base_sorted.buffers()[2]
+    raw = data.to_pybytes()[off[0]:off[-1]] if data is not None else b""
+    st = StrTable.__new__(StrTable)
+    st.n, st.buf, st.off = n, raw, np.ascontiguousarray(off - off[0])
+    docs = DocTable.__new__(DocTable)
+    docs.keys = None if (ids_sorted[0] == 0 and ids_sorted[-1] == n - 1) else np.ascontiguousarray(ids_sorted)
+    docs.table = st
+    srt = base.take(pc.sort_indices(base))
+    if n > 1:
+        keep = np.concatenate([[True], pc.not_equal(srt.slice(1), srt.slice(0, n - 1)).to_numpy(zero_copy_only=False)])
+        if not keep.all():
+            srt = srt.filter(pa.array(keep))
+    joined = pc.binary_join(pa.ListArray.from_arrays(pa.array([0, len(srt)], type=pa.int32()), srt), "\n")[0].as_py()
+    return docs, joined, n
+
+
 # ---- queries.npz ----------------------------------------------------------------
 def save_query_cache(cache_dir, lang: str, qids: Sequence[str], vecs) -> None:
     """vecs: [n,d] array in qid order, or a dict qid -> row."""

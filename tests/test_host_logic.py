@@ -158,6 +158,50 @@ def test_docid_map_roundtrip(tmp_path):
     assert lookup == {0: "7", 1: "9", 2: "4"} and kept == ["7", "9", "4"] and derived == ["7#en", "9#en", "4#en"]
 
 
+def test_docid_table_fast_path_equals_literal_reader(tmp_path):
+    """read_docid_table (pyarrow fast path with strict preconditions) == read_docid_map (the reference's
+    per-line reader) on clean maps, and falls back to it on anything unusual."""
+    rng = np.random.default_rng(31)
+
+    def fast(f):
+        try:
+            return cio._docid_table_arrow(f, runloop.DocTable, runloop.StrTable) is not None
+        except Exception:
+            return False
+
+    def check(name, lines, expect_keys_none=None, expect_fast=None):
+        f = tmp_path / f"{name}.tsv"
+        f.write_bytes("".join(lines).encode("utf-8"))
+        if expect_fast is not None:
+            assert fast(f) == expect_fast, name
+        id_lookup, kept, _ = cio.read_docid_map(f)
+        docs, text, n = cio.read_docid_table(f)
+        assert n == len(kept) and text == "\n".join(sorted(set(kept)))
+        probe = list(id_lookup.keys())[:50] + [-1, 10 ** 9] + [int(v) for v in rng.integers(0, 3000, 50)]
+        assert docs.lookup(probe) == [id_lookup.get(i, str(i)) for i in probe]
+        if expect_keys_none is not None:
+            assert (docs.keys is None) == expect_keys_none
+        return docs
+
+    hdr = "int_id\tderived_id\tbase_id\tlang\n"
+    n = 2000
+    clean = [hdr] + [f"{i}\t{i * 3}#en\t{i * 3}\ten\n" for i in range(n)]
+    check("clean", clean, True, expect_fast=True)
+    check("no_trailing_newline", clean[:-1] + [clean[-1].rstrip("\n")], True)
+    perm = rng.permutation(n)
+    check("shuffled", [hdr] + [f"{i}\t{i}#zh\tdoc-{i % 700}\tzh\n" for i in perm], True, expect_fast=True)  # repeated base ids
+    check("sparse", [hdr] + [f"{i * 5 + 2}\tx\tb{i}\ten\n" for i in range(500)], False, expect_fast=True)
+    check("unicode", [hdr] + [f"{i}\td\t\u6587\u6863{i}\u00e9\tzh\n" for i in range(300)], True)
+    check("three_columns", ["int_id\tderived_id\tbase_id\n"] + [f"{i}\td{i}\tb{i}\n" for i in range(100)], True)
+    # fallbacks: each of these must take the literal reader (and still agree with it)
+    check("dup_ids", expect_fast=False, lines=[hdr, "1\ta\tfirst\ten\n", "2\tb\tsecond\ten\n", "1\tc\tlast\ten\n"])
+    check("short_line", expect_fast=False, lines=[hdr, "0\ta\tb0\ten\n", "garbage\n", "1\ta\tb1\ten\n"])
+    check("bad_int", expect_fast=False, lines=[hdr, "0\ta\tb0\ten\n", "x7\ta\tb7\ten\n", " 2 \ta\tb2\ten\n", "+3\ta\tb3\ten\n"])
+    check("crlf", expect_fast=False, lines=[hdr.replace("\n", "\r\n"), "0\ta\tb0\ten\r\n", "1\ta\tb1\ten\r\n"])
+    check("quotes", [hdr, '0\ta\t"b0\ten\n', "1\ta\tb'1\ten\n"], True)
+    check("empty", expect_fast=False, lines=[hdr])
+
+
 def test_index_file_roundtrip(tmp_path):
     import cmx.faiss as faiss
 
