@@ -204,11 +204,26 @@ def write_mono_trec(path, qids: Sequence[str], D, I, docs, tag: str = "onepass-c
     return int(n.value)
 
 
+def _strtable_from_arrow(arr) -> "StrTable":
+    """StrTable over a pyarrow string array (no per-string Python objects)."""
+    n = len(arr)
+    off = np.frombuffer(arr.buffers()[1], dtype=np.int32, count=n + 1, offset=arr.offset * 4).astype(np.int64)
+    data = arr.buffers()[2]
+    st = StrTable.__new__(StrTable)
+    st.n = n
+    st.buf = data.to_pybytes()[off[0]:off[-1]] if (data is not None and n) else b""
+    st.off = np.ascontiguousarray(off - off[0])
+    return st
+
+
 class BaseTable:
-    """derived ids ``base#lang`` by position, plus their base-id grouping for the collapse."""
+    """derived ids ``base#lang`` by position, plus their base-id grouping for the collapse
+    (``base = did.split('#')[0]``, bases numbered in first-seen order)."""
 
     def __init__(self, id2doc: Sequence[str]):
-        names = list(id2doc)
+        names = id2doc if isinstance(id2doc, list) else list(id2doc)
+        if len(names) >= 4096 and self._init_arrow(names):  # 17.7 M ids: ~9 s instead of ~29 s of per-name Python
+            return
         self.docs = StrTable(names)
         code_of, bases, codes = {}, [], np.empty(len(names), dtype=np.int32)
         for i, nme in enumerate(names):
@@ -221,10 +236,22 @@ class BaseTable:
         self.codes = codes
         self.bases = StrTable(bases)
 
+    def _init_arrow(self, names) -> bool:
+        try:
+            import pyarrow as pa
+            import pyarrow.compute as pc
 
-def bilingual_texts(qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int = 0):
-    raw, col = bilingual_bytes(qids, D, I, id2doc, tag, nthreads)
-    return raw.decode("utf-8"), col.decode("utf-8")
+            arr = pa.array(names, type=pa.string())
+            if not isinstance(arr, pa.Array) or arr.null_count:
+                return False
+            base = pc.list_element(pc.split_pattern(arr, "#", max_splits=1), 0)
+            enc = pc.dictionary_encode(base)  # dictionary in order of first appearance
+            codes = enc.indices.to_numpy(zero_copy_only=False).astype(np.int32)
+            docs, bases = _strtable_from_arrow(arr), _strtable_from_arrow(enc.dictionary)
+        except Exception:
+            return False
+        self.docs, self.codes, self.bases = docs, np.ascontiguousarray(codes), bases
+        return True
 
 
 def bilingual_bytes(qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int = 0):

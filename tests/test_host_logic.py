@@ -128,6 +128,22 @@ def test_file_writers_and_pipelined_sweeps_equal_oracle_text(tmp_path):
     assert (tmp_path / "empty.trec").read_bytes() == b""
 
 
+def test_base_table_arrow_path_equals_python_path():
+    rng = np.random.default_rng(8)
+    names = [f"{int(v)}#{'en' if i % 2 else 'zh'}" for i, v in enumerate(rng.integers(0, 3000, 9000))]
+    names += ["plain", "a#b#c", "#x", "", "\u6587\u6863#zh", "a#b#c"]
+
+    class PyOnly(runloop.BaseTable):
+        def _init_arrow(self, names):
+            return False
+
+    fast, slow = runloop.BaseTable(names), PyOnly(names)
+    assert fast._init_arrow(names)  # the arrow path is available here and was taken
+    for a, b in ((fast.docs, slow.docs), (fast.bases, slow.bases)):
+        assert a.n == b.n and a.buf == b.buf and np.array_equal(a.off, b.off)
+    assert fast.codes.dtype == np.int32 and np.array_equal(fast.codes, slow.codes)
+
+
 def test_collapse_text_form_matches_golden(golden_dir, tmp_path):
     g = json.loads((golden_dir / "text_golden.json").read_text())
     pin, pout = tmp_path / "x_raw.trec", tmp_path / "x.trec"
