@@ -254,6 +254,11 @@ class BaseTable:
         return True
 
 
+def bilingual_texts(qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int = 0):
+    raw, col = bilingual_bytes(qids, D, I, id2doc, tag, nthreads)
+    return raw.decode("utf-8"), col.decode("utf-8")
+
+
 def bilingual_bytes(qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int = 0):
     """(raw run text, collapsed run text) of one bilingual alpha
     (onepass_bilingual_mix_hub_custom_lang.py:950-958 and collapse_run_max :165-181):
