@@ -244,7 +244,19 @@ void format_bilingual(const BiArgs& a, int nthreads, std::vector<Part>& raw, std
     char* p = rs.need((size_t)(q1 - q0) * (size_t)a.k * 52 + 64);
     char* c = cs.need((size_t)(q1 - q0) * (size_t)a.k * 40 + 64);
     if (!p || !c) return;
-    struct Grp { int32_t code; int64_t score6; bool neg; };  // score6 = |rounded score| * 1e6
+    // The collapsed run carries, per base id, the max over the scores AS THE RAW FILE PRINTS THEM.
+    // |score| < 1e11: fixed point, score6 = |rounded score| * 1e6 (exact).  Larger finite float32 values
+    // are integers, print as "<digits>.000000" and survive the text round trip unchanged: kept as is.
+    struct Grp { int32_t code; int64_t score6; bool neg; bool big; float orig; };
+    auto cmp = [](const Grp& x, const Grp& y) -> int {  // -1 / 0 / +1 like the parsed doubles compare
+      if (!x.big && !y.big) {
+        const int64_t vx = x.neg ? -x.score6 : x.score6, vy = y.neg ? -y.score6 : y.score6;
+        return (vx > vy) - (vx < vy);
+      }
+      const double dx = x.big ? (double)x.orig : (x.neg ? -1.0 : 1.0) * (double)x.score6 / 1e6;
+      const double dy = y.big ? (double)y.orig : (y.neg ? -1.0 : 1.0) * (double)y.score6 / 1e6;
+      return (dx > dy) - (dx < dy);
+    };
     std::vector<Grp> groups;
     std::unordered_map<int32_t, int> slot;
     std::vector<int> order;
@@ -276,44 +288,44 @@ void format_bilingual(const BiArgs& a, int nthreads, std::vector<Part>& raw, std
         *p++ = '\n';
         // collapse on the value the raw file carries: the 6-decimal rounded score
         const double ax = std::fabs((double)sc);
-        const bool fin = std::isfinite(sc) && ax < 1e11;
-        const int64_t v6 = fin ? (int64_t)std::nearbyint(ax * 1e6) : (int64_t)9e18;
+        const bool small = std::isfinite(sc) && ax < 1e11;
         const bool neg = std::signbit(sc);  // the sign survives the text round trip even for -0.000000
         const int32_t code = a.base_code[ix];
+        const Grp cand{code, small ? (int64_t)std::nearbyint(ax * 1e6) : 0, neg, !small, sc};
         auto it = slot.find(code);
         if (it == slot.end()) {
           slot.emplace(code, (int)groups.size());
-          groups.push_back({code, v6, neg});
+          groups.push_back(cand);
         } else {
           Grp& g = groups[(size_t)it->second];
-          const int64_t cur = g.neg ? -g.score6 : g.score6, nv = neg ? -v6 : v6;
-          if (nv > cur) { g.score6 = v6; g.neg = neg; }
+          if (cmp(cand, g) > 0) g = cand;
         }
       }
       order.resize(groups.size());
       for (size_t i = 0; i < groups.size(); ++i) order[i] = (int)i;
-      std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-        const int64_t vx = groups[(size_t)x].neg ? -groups[(size_t)x].score6 : groups[(size_t)x].score6;
-        const int64_t vy = groups[(size_t)y].neg ? -groups[(size_t)y].score6 : groups[(size_t)y].score6;
-        return vx > vy;
-      });
+      std::stable_sort(order.begin(), order.end(),
+                       [&](int x, int y) { return cmp(groups[(size_t)x], groups[(size_t)y]) > 0; });
       uint64_t rank = 1;
       for (int gi : order) {
         const Grp& g = groups[(size_t)gi];
         const size_t blen = (size_t)a.bt.len(g.code);
-        if (!cs.ensure(c, qlen + 4 + blen + 1 + 12 + 1 + 32 + 15)) return;
+        if (!cs.ensure(c, qlen + 4 + blen + 1 + 12 + 1 + kMaxFixed + 15)) return;
         c = put_str(c, qs, qlen);
         c = put_str(c, " Q0 ", 4);
         c = put_str(c, a.bt.ptr(g.code), blen);
         *c++ = ' ';
         c = put_uint(c, rank++);
         *c++ = ' ';
-        if (g.neg) *c++ = '-';
-        c = put_uint(c, (uint64_t)(g.score6 / 1000000));
-        *c++ = '.';
-        int64_t f = g.score6 % 1000000;
-        for (int i = 5; i >= 0; --i) { c[i] = (char)('0' + f % 10); f /= 10; }
-        c += 6;
+        if (g.big) {
+          c = put_fixed(c, g.orig, 6);
+        } else {
+          if (g.neg) *c++ = '-';
+          c = put_uint(c, (uint64_t)(g.score6 / 1000000));
+          *c++ = '.';
+          int64_t f = g.score6 % 1000000;
+          for (int i = 5; i >= 0; --i) { c[i] = (char)('0' + f % 10); f /= 10; }
+          c += 6;
+        }
         c = put_str(c, " bilingual-mix\n", 15);
       }
     }

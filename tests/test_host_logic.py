@@ -57,6 +57,38 @@ def test_mono_text_equals_oracle_lines():
     assert runloop.mono_trec_text(qids, D, I, runloop.DocTable(lookup)) == want
 
 
+def test_c_formatter_matches_python_on_arbitrary_float32():
+    """cmx_trec_mono / cmx_trec_bilingual print scores exactly like f"{x:.4f}" / f"{x:.6f}" for ANY float32:
+    random bit patterns over all exponents, halfway cases, -0.0, subnormals, huge values, inf and nan."""
+    rng = np.random.default_rng(99)
+    bits = rng.integers(0, 2 ** 32, 40000, dtype=np.uint64).astype(np.uint32)
+    vals = bits.view(np.float32).copy()
+    halfway = (rng.integers(-20000, 20000, 4000) / 20000.0 + 0.00005).astype(np.float32)  # x.xxxx5 at 4 decimals
+    halfway6 = (rng.integers(-2000000, 2000000, 4000) / 2000000.0 + 0.0000005).astype(np.float32)
+    special = np.array([0.0, -0.0, 1e-45, -1e-45, 1.17549435e-38, 3.4028235e38, -3.4028235e38, 9.9999997e10, 1.0e11,
+                        -1.0e11, 123456.789, np.inf, -np.inf, np.nan, 0.99995, 0.999995, -0.00005, 2.5e-5, 3.5e-5], np.float32)
+    allv = np.concatenate([vals, halfway, halfway6, special])
+    k = 97
+    pad = (-len(allv)) % k
+    allv = np.concatenate([allv, np.zeros(pad, np.float32)])
+    D = allv.reshape(-1, k)
+    nq = D.shape[0]
+    I = np.tile(np.arange(k, dtype=np.int64), (nq, 1))
+    qids = [str(i) for i in range(nq)]
+    lookup = {i: f"d{i}" for i in range(k)}
+    want = "\n".join(oracle.mono_trec_lines(qids, D, I, lookup))
+    assert runloop.mono_trec_bytes(qids, D, I, lookup).decode("utf-8") == want
+    id2doc = [f"{i}#en" for i in range(k)]  # every hit its own base: the collapsed file carries each rounded score
+    raw_lines = oracle.bilingual_raw_lines(qids, D, I, id2doc, "t")
+    raw, col = runloop.bilingual_bytes(qids, D, I, id2doc, "t")
+    assert raw.decode("utf-8") == "".join(raw_lines)
+    finite_rows = np.isfinite(D).all(axis=1)  # the reference's collapse re-parses text: float("nan") ordering is its own story
+    sub = np.nonzero(finite_rows)[0][:150]
+    qs = [qids[i] for i in sub]
+    raw_sub = oracle.bilingual_raw_lines(qs, D[sub], I[sub], id2doc, "t")
+    assert runloop.bilingual_bytes(qs, D[sub], I[sub], id2doc, "t")[1].decode("utf-8") == oracle.collapse_run_max_text(raw_sub)
+
+
 def test_bilingual_raw_and_collapse_equal_oracle():
     rng = np.random.default_rng(7)
     nq, k, nrows = 9, 60, 80
