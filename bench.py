@@ -381,6 +381,12 @@ def run_cmx(a) -> None:
     ok = bool((D[0, :, 1:] <= D[0, :, :-1]).all()) and int(I.min()) >= 0 and int(I.max()) < N
     if rank == 0 and not ok:
         print("bench.py: result self-check FAILED", file=sys.stderr)
+    # the end-to-end call (host buffers) must deliver exactly what the device-resident call computed
+    e2e_ok = True
+    if rank == 0:
+        e2e_ok = bool(torch.equal(Dh.reshape(-1), D.reshape(-1).cpu())) and bool(torch.equal(Ih.reshape(-1), I.reshape(-1).cpu()))
+        if not e2e_ok:
+            print("bench.py: e2e result differs from the device-resident result", file=sys.stderr)
 
     if rank != 0:
         if world > 1:
@@ -458,7 +464,7 @@ def run_cmx(a) -> None:
                    "path": "tensor" if used_tensor else "stream", "precision": a.precision if used_tensor else "fp32",
                    "slabs": stats["slabs"], "reruns": stats["reruns"]},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": t_e2e_ms / a.steps,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": t_e2e_ms / a.steps, "matches_device_result": e2e_ok,
                 "h2d_bytes_per_step": 2 * nq * d * 4, "d2h_bytes_per_step": nq * k * 12},
         "gpu_launches": launches,
         "roofline": roofline,

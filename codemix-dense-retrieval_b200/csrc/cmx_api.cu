@@ -418,8 +418,9 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
 static int fill_empty(float* D_d, int64_t* I_d, int64_t count, cudaStream_t st) {
   std::vector<float> d((size_t)count, CMX_NEG_PAD);
   std::vector<int64_t> i((size_t)count, -1);
-  CMX_CUDA(cudaMemcpyAsync(D_d, d.data(), count * sizeof(float), cudaMemcpyHostToDevice, st));
-  CMX_CUDA(cudaMemcpyAsync(I_d, i.data(), count * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  // cudaMemcpyDefault: the outputs may be device memory or device-mapped pinned host memory
+  CMX_CUDA(cudaMemcpyAsync(D_d, d.data(), count * sizeof(float), cudaMemcpyDefault, st));
+  CMX_CUDA(cudaMemcpyAsync(I_d, i.data(), count * sizeof(int64_t), cudaMemcpyDefault, st));
   CMX_CUDA(cudaStreamSynchronize(st));
   return CMX_OK;
 }
@@ -464,6 +465,24 @@ static int search_device(cmx_index* ix, const float* q_d, int64_t nq, int k, flo
     if (ovf) { set_error("internal: candidate buffer overflow in safe mode"); return CMX_ERR_INTERNAL; }
   }
   return CMX_OK;
+}
+
+// Host outputs in page-locked, device-mapped memory (cudaHostAlloc / torch pin_memory) can be
+// written by the final kernels directly: the (D, I) rows -- 84 MB at C2 -- then cross PCIe as
+// posted writes WHILE the rescoring kernel is still gathering rows from HBM, instead of in a
+// device-to-host copy after it.  Pageable buffers (numpy) keep the staged copy.
+static int g_mapped_outputs = 1;  // 0: always stage (experiments)
+static bool mapped_host_outputs(float* D, int64_t* I, float** Dm, int64_t** Im) {
+  if (!g_mapped_outputs) return false;
+  cudaPointerAttributes a, b;
+  if (cudaPointerGetAttributes(&a, D) != cudaSuccess || cudaPointerGetAttributes(&b, I) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (a.type != cudaMemoryTypeHost || b.type != cudaMemoryTypeHost || !a.devicePointer || !b.devicePointer) return false;
+  *Dm = (float*)a.devicePointer;
+  *Im = (int64_t*)b.devicePointer;
+  return true;
 }
 
 static void stats_begin(cmx_index* ix, int64_t nq) {
@@ -678,17 +697,21 @@ int cmx_index_search(cmx_index* ix, const float* q, int64_t nq, int k, float* D,
   const float* q_d = q;
   float* D_d = D;
   int64_t* I_d = I;
+  bool staged_out = false;
   if (!io_on_device) {
     CMX_TRY(ensure_buf(&ix->q_dev, &ix->q_cap, nq * (int64_t)ix->d));
-    CMX_TRY(ensure_buf(&ix->D_dev, &ix->D_cap, nq * (int64_t)k));
-    CMX_TRY(ensure_buf(&ix->I_dev, &ix->I_cap, nq * (int64_t)k));
     CMX_CUDA(cudaMemcpyAsync(ix->q_dev, q, (size_t)nq * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
     q_d = ix->q_dev;
-    D_d = ix->D_dev;
-    I_d = ix->I_dev;
+    if (!mapped_host_outputs(D, I, &D_d, &I_d)) {
+      CMX_TRY(ensure_buf(&ix->D_dev, &ix->D_cap, nq * (int64_t)k));
+      CMX_TRY(ensure_buf(&ix->I_dev, &ix->I_cap, nq * (int64_t)k));
+      D_d = ix->D_dev;
+      I_d = ix->I_dev;
+      staged_out = true;
+    }
   }
   CMX_TRY(search_device(ix, q_d, nq, k, D_d, I_d, id_base, path, st));
-  if (!io_on_device) {
+  if (staged_out) {
     CMX_CUDA(cudaMemcpyAsync(D, D_d, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
     CMX_CUDA(cudaMemcpyAsync(I, I_d, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   }
@@ -811,26 +834,30 @@ int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int64_t nq, 
   CMX_TRY(ensure_buf(&ix->flags_dev, &ix->flags_cap, nqt));
   CMX_TRY(ensure_buf(&ix->w_dev, &ix->w_cap, 2 * (int64_t)nA));
   CMX_TRY(ensure_buf(&ix->mode_dev, &ix->mode_cap, (int64_t)nA));
+  bool staged_out = false;
   if (!io_on_device) {
     CMX_TRY(ensure_buf(&ix->p_dev, &ix->p_cap, nq * (int64_t)ix->d));
     CMX_TRY(ensure_buf(&ix->s_dev, &ix->s_cap, nq * (int64_t)ix->d));
-    CMX_TRY(ensure_buf(&ix->D_dev, &ix->D_cap, nqt * (int64_t)k));
-    CMX_TRY(ensure_buf(&ix->I_dev, &ix->I_cap, nqt * (int64_t)k));
     CMX_CUDA(cudaMemcpyAsync(ix->p_dev, P, (size_t)nq * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
     CMX_CUDA(cudaMemcpyAsync(ix->s_dev, S, (size_t)nq * ix->d * sizeof(float), cudaMemcpyHostToDevice, st));
     P_d = ix->p_dev;
     S_d = ix->s_dev;
-    D_d = ix->D_dev;
-    I_d = ix->I_dev;
+    if (!mapped_host_outputs(D, I, &D_d, &I_d)) {
+      CMX_TRY(ensure_buf(&ix->D_dev, &ix->D_cap, nqt * (int64_t)k));
+      CMX_TRY(ensure_buf(&ix->I_dev, &ix->I_cap, nqt * (int64_t)k));
+      D_d = ix->D_dev;
+      I_d = ix->I_dev;
+      staged_out = true;
+    }
   }
   uint8_t* f_d = (io_on_device && flags) ? flags : ix->flags_dev;
   CMX_TRY(mix_on_device(P_d, S_d, nq, ix->d, alphas, nA, ix->q_dev, f_d, ix->w_dev, ix->mode_dev, st));
   CMX_TRY(search_device(ix, ix->q_dev, nqt, k, D_d, I_d, id_base, path, st));
-  if (!io_on_device) {
+  if (staged_out) {
     CMX_CUDA(cudaMemcpyAsync(D, D_d, (size_t)nqt * k * sizeof(float), cudaMemcpyDeviceToHost, st));
     CMX_CUDA(cudaMemcpyAsync(I, I_d, (size_t)nqt * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    if (flags) CMX_CUDA(cudaMemcpyAsync(flags, f_d, (size_t)nqt, cudaMemcpyDeviceToHost, st));
   }
+  if (!io_on_device && flags) CMX_CUDA(cudaMemcpyAsync(flags, f_d, (size_t)nqt, cudaMemcpyDeviceToHost, st));
   if (g_profiling) CMX_CUDA(cudaEventRecord(e1, st));
   CMX_CUDA(cudaStreamSynchronize(st));
   if (g_profiling) cudaEventElapsedTime(&ix->stats.total_ms, e0, e1);
@@ -957,6 +984,7 @@ int cmx_merge_topk_peers(const float* const* D_parts, const int64_t* const* I_pa
 CMX_API int cmx_debug_set_tensor_tile(int bn) { set_tensor_tile(bn); return CMX_OK; }
 CMX_API int cmx_debug_set_block_order(int on) { g_block_order = on ? 1 : 0; return CMX_OK; }
 CMX_API int cmx_debug_set_speculate(int on) { g_speculate = on ? 1 : 0; return CMX_OK; }
+CMX_API int cmx_debug_set_mapped_outputs(int on) { g_mapped_outputs = on ? 1 : 0; return CMX_OK; }
 /* test hooks (host logic, no GPU needed): the slab schedule of a tensor-path search and the block multiplier */
 CMX_API int cmx_debug_plan_slabs(int64_t ntotal, int k, int cap, int rescore, int safe, int speculate, int64_t* rows_out,
                                  int max_slabs, int* nslabs, int* spec_slab, int* spec_rank) {
