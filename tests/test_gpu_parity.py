@@ -728,3 +728,41 @@ def test_two_phase_sharded_search_on_one_gpu(G):
     # each shard returned only rows inside the global band: far fewer than k valid entries per query
     valid = (Ip >= 0).sum(dim=2).float().mean(dim=1).cpu().numpy()
     assert valid.sum() < 1.6 * k and (valid < 0.9 * k).all(), valid
+
+
+def test_pinned_host_outputs_are_written_in_place(precision):
+    """Page-locked (device-mapped) host output buffers are written by the final kernels directly -- no
+    staged device-to-host copy; the result is bit-identical to the staged path (pageable numpy
+    buffers, or the same pinned buffers with the switch off)."""
+    import torch
+
+    from cmx import _lib
+
+    rng = np.random.default_rng(91)
+    X, P, S = _unit(rng, 30000, 128), _unit(rng, 70, 128), _unit(rng, 70, 128)
+    sh = _shard(X)
+    alphas, k = [0.0, 0.4], 50
+    D0, I0 = sh.search_mixed(P, S, alphas, k, path="tensor")  # numpy in, numpy out: staged copies
+    Pp, Sp = torch.from_numpy(P).pin_memory(), torch.from_numpy(S).pin_memory()
+
+    def pinned_run():
+        Dp = torch.full((len(alphas), 70, k), 7.0, dtype=torch.float32).pin_memory()
+        Ip = torch.full((len(alphas), 70, k), 7, dtype=torch.int64).pin_memory()
+        sh.search_mixed(Pp, Sp, alphas, k, path="tensor", out=(Dp, Ip))
+        return Dp.numpy().copy(), Ip.numpy().copy()
+
+    D1, I1 = pinned_run()
+    assert np.array_equal(D1, np.asarray(D0)) and np.array_equal(I1, np.asarray(I0))
+    _lib.check(_lib.lib().cmx_debug_set_mapped_outputs(0))
+    try:
+        D2, I2 = pinned_run()
+    finally:
+        _lib.check(_lib.lib().cmx_debug_set_mapped_outputs(1))
+    assert np.array_equal(D2, D1) and np.array_equal(I2, I1)
+    # plain search through the same boundary
+    Q = _unit(rng, 33, 128)
+    Dq0, Iq0 = sh.search(Q, 20, path="tensor")
+    Dq = torch.full((33, 20), 7.0, dtype=torch.float32).pin_memory()
+    Iq = torch.full((33, 20), 7, dtype=torch.int64).pin_memory()
+    sh.search(torch.from_numpy(Q).pin_memory(), 20, path="tensor", out=(Dq, Iq))
+    assert np.array_equal(Dq.numpy(), np.asarray(Dq0)) and np.array_equal(Iq.numpy(), np.asarray(Iq0))
