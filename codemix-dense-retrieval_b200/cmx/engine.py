@@ -187,25 +187,37 @@ class Shard:
         return (D, I, flags) if want_flags else (D, I)
 
     # ---- two-phase search for sharded indexes (device tensors, rescore precision) --------------
-    def search_mixed_begin(self, P, S, alphas: Sequence[float], k: int, id_base: int, kth_out) -> bool:
-        """Phase 1: fused prologue + approximate pass; writes this shard's k best approximate scores
-        per query to ``kth_out`` [nA*nq*k] (CUDA float32, order arbitrary).  Returns True when the
-        candidate buffers overflowed (every shard must then fall back to ``search_mixed``)."""
+    # Building blocks that only ENQUEUE work on the current stream (include/cmx.h): the caller
+    # provides the cross-shard barriers and reads the status word at the end of the step.
+    def search_prepare(self, P, S, alphas: Sequence[float]) -> int:
+        """Fused mix + normalise of nA alphas into the shard's own query buffer; returns the device
+        address of the mixed queries [nA*nq, d]."""
         P = _as_f32_2d(P, self.d, "P")
         S = _as_f32_2d(S, self.d, "S")
-        assert P.is_cuda and S.is_cuda and kth_out.is_cuda, "two-phase search works on CUDA tensors"
+        assert P.is_cuda and S.is_cuda and tuple(P.shape) == tuple(S.shape), "two-phase search works on CUDA tensors"
         nA = len(alphas)
         a = (C.c_double * nA)(*[float(v) for v in alphas])
-        ovf = C.c_int(0)
-        check(_lib.lib().cmx_search_mixed_begin(self._h, _ptr(P)[0], _ptr(S)[0], int(P.shape[0]), a, nA, int(k), int(id_base),
-                                                int(kth_out.data_ptr()), C.byref(ovf), _stream(self.device)))
-        return bool(ovf.value)
+        q = C.c_void_p()
+        check(_lib.lib().cmx_search_prepare(self._h, _ptr(P)[0], _ptr(S)[0], int(P.shape[0]), a, nA, C.byref(q), _stream(self.device)))
+        return int(q.value)
 
-    def search_end(self, kth_ptrs: Sequence[int], D, I) -> None:
-        """Phase 2: exact rescoring of the rows that can still reach the global top-k, given every
-        shard's k-th best approximate scores (device pointers, peer memory allowed)."""
+    def export_bounds(self, out2_ptr: int) -> None:
+        """{max row norm, max fp16-residual norm} of this shard -> 2 floats at a device address."""
+        check(_lib.lib().cmx_index_export_bounds(self._h, int(out2_ptr), _stream(self.device)))
+
+    def search_begin(self, q_ptr: int, nq: int, k: int, id_base: int, bounds_ptrs: Sequence[int], est_scale: float,
+                     scores_ptr: int, flag_ptr: int) -> None:
+        """Phase 1 for queries at device address ``q_ptr`` [nq <= 8192, d]: approximate pass; the shard's k
+        best approximate scores per query -> ``scores_ptr`` [nq, k], its status word -> ``flag_ptr``."""
+        arr = (C.c_void_p * max(1, len(bounds_ptrs)))(*[int(p) for p in bounds_ptrs])
+        check(_lib.lib().cmx_search_begin(self._h, int(q_ptr), int(nq), int(k), int(id_base), arr, len(bounds_ptrs),
+                                          float(est_scale), int(scores_ptr), int(flag_ptr), _stream(self.device)))
+
+    def search_end(self, kth_ptrs: Sequence[int], D_ptr: int, I_ptr: int) -> None:
+        """Phase 2: exact rescoring of the rows that can still reach the global top-k, given the global
+        k-th best approximate scores (device pointers, peer memory allowed) -> D, I [nq, k] at device addresses."""
         arr = (C.c_void_p * len(kth_ptrs))(*[int(p) for p in kth_ptrs])
-        check(_lib.lib().cmx_search_end(self._h, arr, len(kth_ptrs), int(D.data_ptr()), int(I.data_ptr()), _stream(self.device)))
+        check(_lib.lib().cmx_search_end(self._h, arr, len(kth_ptrs), int(D_ptr), int(I_ptr), _stream(self.device)))
 
     def last_stats(self) -> dict:
         st = _lib.SearchStats()
@@ -240,13 +252,45 @@ def mix_normalize(P, S, alphas: Sequence[float], device: int = 0, want_flags: bo
     return (out, flags) if want_flags else out
 
 
-def union_kth(score_ptrs: Sequence[int], nq: int, k: int, q0: int, q1: int, out_ptrs: Sequence[int], device: int) -> None:
+def union_kth(score_ptrs: Sequence[int], nq: int, k: int, q0: int, q1: int, out_ptrs: Sequence[int], device: int,
+              flag_ptrs: Sequence[int] = (), flag_any_ptr: int = 0) -> None:
     """Global k-th best approximate score of queries [q0, q1) over all shards' exported lists
-    (device pointers, peer memory allowed), written to every ``out_ptrs[o][q]``.  Asynchronous."""
+    (device pointers, peer memory allowed), written to every ``out_ptrs[o][q]``; the shards' status
+    words ``flag_ptrs`` are OR-ed into the word at ``flag_any_ptr``.  Asynchronous."""
     parts = (C.c_void_p * len(score_ptrs))(*[int(p) for p in score_ptrs])
     outs = (C.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
-    check(_lib.lib().cmx_union_kth(parts, len(score_ptrs), int(nq), int(k), int(q0), int(q1), outs, len(out_ptrs), int(device),
-                                   _stream(device)))
+    flags = (C.c_void_p * max(1, len(flag_ptrs)))(*[int(p) for p in flag_ptrs])
+    check(_lib.lib().cmx_union_kth(parts, len(score_ptrs), int(nq), int(k), int(q0), int(q1), outs, len(out_ptrs),
+                                   flags, len(flag_ptrs), int(flag_any_ptr) or None, int(device), _stream(device)))
+
+
+def merge_topk_peers(D_ptrs: Sequence[int], I_ptrs: Sequence[int], nq: int, k: int, q0: int, q1: int,
+                     Dout_ptrs: Sequence[int], Iout_ptrs: Sequence[int], device: int) -> None:
+    """Fused exchange + merge of queries [q0, q1): reads every part's [nq, k] lists in place (peer memory)
+    and stores the merged rows into every output (device, peer, or the device alias of pinned host
+    memory).  Asynchronous; the caller provides the barriers."""
+    arr = lambda ptrs: (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])  # noqa: E731
+    check(_lib.lib().cmx_merge_topk_peers(arr(D_ptrs), arr(I_ptrs), len(D_ptrs), int(nq), int(k), int(q0), int(q1),
+                                          arr(Dout_ptrs), arr(Iout_ptrs), len(Dout_ptrs), int(device), _stream(device)))
+
+
+def peer_broadcast(src_ptr: int, dst_ptrs: Sequence[int], nbytes: int, device: int) -> None:
+    """``nbytes`` at device address ``src_ptr`` -> every ``dst_ptrs[i]`` (peer memory).  Asynchronous."""
+    if not dst_ptrs or nbytes <= 0:
+        return
+    dsts = (C.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+    check(_lib.lib().cmx_peer_broadcast(int(src_ptr), dsts, len(dst_ptrs), int(nbytes), int(device), _stream(device)))
+
+
+def host_register(ptr: int, nbytes: int) -> int:
+    """Page-lock + device-map a host range; returns the device-side alias."""
+    out = C.c_void_p()
+    check(_lib.lib().cmx_host_register(int(ptr), int(nbytes), C.byref(out)))
+    return int(out.value)
+
+
+def host_unregister(ptr: int) -> None:
+    check(_lib.lib().cmx_host_unregister(int(ptr)))
 
 
 def merge_topk(D_parts, I_parts, k: Optional[int] = None, device: int = 0):

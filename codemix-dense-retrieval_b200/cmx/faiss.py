@@ -370,18 +370,40 @@ class IndexShardsIP(_Searchable):
     """Row-sharded flat IP index over several GPUs driven from ONE process
     (faiss.index_cpu_to_all_gpus(..., shard=True) analogue; new capability, the
     reference never shards).  Shard g holds the contiguous rows
-    [bounds[g], bounds[g+1]); every shard searches the full query batch
-    concurrently, partial results are merged on shards[0]'s device by the k-way
-    merge kernel.  Result == the single-GPU result exactly (same tie order)."""
+    [bounds[g], bounds[g+1]).  A search runs the SAME step as the one-process-per-GPU
+    ``cmx.dist.ShardedIndex`` -- one thread per GPU executes it over a ``LocalFabric``
+    (peer access between the devices, event barriers between their streams): every
+    shard uploads 1/G of the query vectors and replicates it over NVLink, the shards
+    exchange their global k-th approximate scores before the exact rescoring, and each
+    merge kernel writes its slice of the queries straight into ONE pinned host buffer.
+    Result == the single-GPU result exactly (same tie order).
+
+    The returned (D, I) are numpy views of that pinned buffer; two buffers alternate,
+    so a result stays valid until the search after the next one (what the run loops'
+    "format alpha i while alpha i+1 is searched" pipeline needs)."""
 
     is_trained = True
     metric_type = METRIC_INNER_PRODUCT
 
     def __init__(self, d: int, devices: Sequence[int]):
+        from .dist import LocalGroup
+
         self.d = int(d)
         self.devices = [int(v) for v in devices]
         self.shards = [GpuIndexFlatIP(d, device=dev) for dev in self.devices]
-        self._pool = ThreadPoolExecutor(max_workers=len(self.devices))
+        self._group = LocalGroup(self.devices)
+        # one persistent thread per device (its CUDA device is set once)
+        self._threads = [ThreadPoolExecutor(max_workers=1, initializer=self._bind, initargs=(dev,)) for dev in self.devices]
+        self._views = None      # per-shard ShardedIndex over the current row counts
+        self._views_key = None
+        self._out = {}          # (rank, slot, shape) -> HostResult
+        self._turn = 0
+        self.two_phase_used = False
+
+    @staticmethod
+    def _bind(dev: int) -> None:
+        if torch is not None and torch.cuda.is_available():
+            torch.cuda.set_device(dev)
 
     @property
     def ntotal(self) -> int:
@@ -403,7 +425,7 @@ class IndexShardsIP(_Searchable):
         """Appends to the LAST shard (keeps global row order = add order)."""
         self.shards[-1].add(x)
 
-    def add_sharded(self, rows: np.ndarray) -> None:
+    def add_sharded(self, rows) -> None:
         assert self.ntotal == 0, "add_sharded needs an empty index"
         b = self.split(rows.shape[0], len(self.shards))
         for g, sh in enumerate(self.shards):
@@ -423,29 +445,77 @@ class IndexShardsIP(_Searchable):
         raise RuntimeError(f"reconstruct: index {i} out of range [0, {b[-1]})")
 
     def _fanout(self, fn):
+        """fn(rank, view) on every device's thread, concurrently (the step has cross-shard barriers)."""
+        def guarded(g):
+            try:
+                return fn(g, self._views[g])
+            except BaseException:
+                self._group.tbar.abort()  # the other shards would wait for this one forever
+                raise
+
+        futs = [t.submit(guarded, g) for g, t in enumerate(self._threads)]
+        errs, outs = [], []
+        for f in futs:
+            try:
+                outs.append(f.result())
+            except Exception as exc:  # noqa: BLE001
+                errs.append(exc)
+        if errs:
+            self._group.tbar.reset()
+            import threading
+
+            real = [e for e in errs if not isinstance(e, threading.BrokenBarrierError)]
+            raise (real or errs)[0]
+        return outs
+
+    def _ensure_views(self) -> None:
+        from .dist import LocalFabric, ShardedIndex
+
         b = self.bounds
-        futs = [self._pool.submit(fn, sh, b[g]) for g, sh in enumerate(self.shards)]
-        parts = [f.result() for f in futs]
-        Dp = np.stack([np.asarray(p[0]) for p in parts])
-        Ip = np.stack([np.asarray(p[1]) for p in parts])
-        return Dp, Ip
+        key = tuple(b)
+        if self._views is not None and self._views_key == key:
+            for v in self._views:
+                v.path = self.path
+            return
+        self._views = []
+        for g, sh in enumerate(self.shards):
+            fab = LocalFabric(self._group, g)
+            v = ShardedIndex(self.d, b[-1], device=self.devices[g], fabric=fab, local=sh._shard, bounds=b, exchange="p2p")
+            v.path = self.path
+            self._views.append(v)
+        self._views_key = key
+        self._out = {}
+
+    def _host_out(self, rank: int, view, shape):
+        key = (rank, self._turn, shape)
+        o = self._out.get(key)
+        if o is None:
+            for k2 in [k2 for k2 in self._out if k2[0] == rank and k2[1] == self._turn]:
+                del self._out[k2]
+            o = self._out[key] = view.host_output(*shape)
+        return o
 
     def search(self, x, k: int):
-        if _is_torch(x):
-            x = x.detach().cpu().numpy()
-        x = _as_f32_2d(x, self.d, "search(x)")
-        path = self.path
-        Dp, Ip = self._fanout(lambda sh, base: sh._shard.search(x, k, id_base=base, path=path))
-        return merge_topk(Dp, Ip, k, device=self.devices[0])
+        """``index.search(x, k)`` = the alpha = 0 case of the fused step (P rows pass through unchanged)."""
+        x = _as_f32_2d(x.detach().cpu().numpy() if _is_torch(x) else x, self.d, "search(x)")
+        D, I = self.search_mixed(x, x, [0.0], k)
+        return D[0], I[0]
 
     def search_mixed(self, P, S, alphas, k: int):
-        P = _as_f32_2d(P.detach().cpu().numpy() if _is_torch(P) else P, self.d, "P")
-        S = _as_f32_2d(S.detach().cpu().numpy() if _is_torch(S) else S, self.d, "S")
-        path = self.path
-        Dp, Ip = self._fanout(lambda sh, base: sh._shard.search_mixed(P, S, alphas, k, id_base=base, path=path))
-        G, nA, nq, kk = Dp.shape
-        D, I = merge_topk(Dp.reshape(G, nA * nq, kk), Ip.reshape(G, nA * nq, kk), k, device=self.devices[0])
-        return D.reshape(nA, nq, kk), I.reshape(nA, nq, kk)
+        P = _as_f32_2d(P.detach().cpu() if _is_torch(P) else P, self.d, "P")
+        S = _as_f32_2d(S.detach().cpu() if _is_torch(S) else S, self.d, "S")
+        assert tuple(P.shape) == tuple(S.shape)
+        self._ensure_views()
+        shape = (len(alphas), int(P.shape[0]), int(k))
+
+        def step(rank, view):
+            out = self._host_out(rank, view, shape)
+            return view.search_mixed_host(P, S, alphas, k, out=out)
+
+        D, I = self._fanout(step)[0]
+        self._turn ^= 1
+        self.two_phase_used = any(v.two_phase_used for v in self._views)
+        return D.numpy(), I.numpy()
 
 
 def index_cpu_to_gpus_list(index, co=None, gpus: Optional[Sequence[int]] = None, ngpu: int = -1):

@@ -8,9 +8,14 @@
 #include <cstring>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace cmx {
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 static thread_local std::string t_error;
 std::atomic<uint64_t> g_launches{0};
@@ -55,6 +60,7 @@ static int ensure_buf(T** ptr, int64_t* cap, int64_t need) {
 
 constexpr int kMaxSlabEvents = 64;
 constexpr int64_t kQueryChunk = 8192;  // queries per corpus pass (bounds workspace + Q L2 footprint)
+constexpr int kMaxSub = 8;             // scoring launches the last slab of a rescore-mode search is cut into
 
 }  // namespace cmx
 
@@ -89,17 +95,26 @@ struct cmx_index {
   float* margin_buf = nullptr;
   unsigned long long* progress = nullptr;  // tile-progress counter of the tensor kernels
   // two-phase (sharded) search state between cmx_search_mixed_begin and cmx_search_end
-  bool pending = false;
+  bool pending = false;  // cleared by every entry point that touches the workspace or the row store
   int64_t pend_nq = 0, pend_id_base = 0;
   int pend_k = 0;
   float* q_scale = nullptr;  // {scale, 1/scale}
   float* D_dev = nullptr; int64_t D_cap = 0;
   int64_t* I_dev = nullptr; int64_t I_cap = 0;
   uint8_t* flags_dev = nullptr; int64_t flags_cap = 0;
-  float* w_dev = nullptr; int64_t w_cap = 0;  // w1[nA], w2[nA]
-  int* mode_dev = nullptr; int64_t mode_cap = 0;
   cudaEvent_t ev[4 * kMaxSlabEvents];
   bool ev_ready = false;
+  int timed_slabs = 0;  // slabs of an asynchronous pass whose event times have not been read yet
+  // prescoring (exact scores ahead of time, beside the scoring kernel): second stream, launch-boundary
+  // events, snapshots of the append cursors
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_sub[kMaxSub + 1], ev_side_done = nullptr;
+  uint32_t* snap = nullptr; int64_t snap_cap = 0;  // [kMaxSub + 1, nq_pad]
+  float* est_buf = nullptr; int64_t est_cap = 0;
+  const float* pend_q = nullptr;  // queries of the pending two-phase search (device)
+  bool pend_skip = false;
+  float* bounds_dev = nullptr;    // {max row norm, max residual norm} over all shards, reduced on device
+  bool bounds_from_dev = false;
   cmx_search_stats stats;
 };
 
@@ -194,6 +209,13 @@ static int ensure_planes(cmx_index* ix, bool need_lo, cudaStream_t st) {
   return CMX_OK;
 }
 
+// the one-pass (rescore) arithmetic needs finite corpus maxima for its error bound; a corpus with a finite
+// row whose fp32 sum of squares overflows reports +inf (row_norm_max_kernel) and uses split precision
+static bool rescore_usable(const cmx_index* ix) {
+  return ix->precision == CMX_PRECISION_RESCORE && ix->row_norm_max > 0.f && std::isfinite(ix->row_norm_max) &&
+         std::isfinite(ix->norm_floor) && std::isfinite(ix->resid_floor);
+}
+
 static int pick_cap(const cmx_index* ix, int k) {
   int cap = ix->cand_cap_override;
   if (cap <= 0) cap = (k <= 1024) ? 8192 : 16384;
@@ -205,9 +227,10 @@ static int pick_cap(const cmx_index* ix, int k) {
 }
 
 struct SlabPlan {
-  std::vector<int64_t> rows;  // slab sizes, in order; slab 0 is the dense one
-  int spec_slab = -1;         // >= 1: this (last) slab runs under a speculative threshold ...
-  int spec_rank = 0;          // ... the spec_rank-th best score after the slab before it
+  std::vector<int64_t> rows;   // slab sizes, in order; slab 0 is the dense one
+  std::vector<int> spec_rank;  // > 0: the slab runs under a speculative threshold, the spec_rank-th best score after
+                               // the slab before it (published and later verified by the compactions); 0: planned slab
+  int nspec() const { int c = 0; for (int r : spec_rank) c += r > 0; return c; }
 };
 
 // Geometric slab schedule: slab 0 fills the (empty) candidate buffers densely, every
@@ -215,35 +238,45 @@ struct SlabPlan {
 // number of rows beating the stale threshold is half of the free room (cap - k).
 // safe = worst-case schedule (every row may pass): rows <= cap - k per slab.
 //
-// Speculative last slab (spec = true; tensor path, whose block order makes every prefix a uniform
-// sample): once `seen` rows are in, the k-th best of the WHOLE corpus is expected near the
-// (k seen/N)-th best so far.  When that rank r is >= kSpecMinRank the rest of the corpus is scored in
-// ONE slab filtered at the 3x deeper rank: ~3k survivors per query (+-3k/sqrt(rank), far inside the
-// buffer), while the chance that fewer than k rows clear it is P(Poisson(r) >= 3r) < 1e-12.  The
-// compaction after that slab VERIFIES the guess per query (k-th best >= threshold + margin); a miss
-// only costs a rerun with spec = false.  This replaces the last 2-3 geometric slabs and their
-// compactions, which is what a small shard of a multi-GPU search spends a fifth of its time on.
+// Speculative slabs (spec = true; tensor path, whose block order makes every prefix a uniform
+// sample).  Once `seen` rows are in, the k-th best of the first T >= seen rows is expected near the
+// r0 = k seen/T -th best so far.  A slab covering rows [seen, T) may therefore be filtered at the 3x
+// deeper rank R = 3 r0: ~3k survivors per query whatever T is (+-3k/sqrt(R), far inside the buffer),
+// while the chance that fewer than k of the T rows clear it is P(Poisson(r0) >= 3 r0) < 1e-12 at
+// r0 >= kSpecMinRank.  The compaction after the slab VERIFIES the guess per query (k-th best >=
+// threshold + margin); a miss only costs a rerun with spec = false.  Two uses:
+//   final: T = N as soon as r0 >= kSpecMinRank -- the rest of the corpus in ONE slab;
+//   mid:   otherwise the largest T with r0 = kSpecMinRank, if that beats the geometric slab -- at
+//          k = 1000 the dense slab of 8 192 rows is followed by one slab of 335 k rows instead of
+//          three geometric ones (20 k, 74 k, 262 k) and their compactions.
 // The Poisson figure assumes independent rows; if a query's best rows come in clumps of c adjacent
 // rows (passages of one document) the effective rank is r0/c -- at r0 >= 32 and c = 3 a miss is still
 // < 1e-7 per query, and a miss is never wrong, only a second pass.
 constexpr double kSpecMinRank = 32.0;
 static int g_speculate = 1;  // 0: planned geometric slabs only (experiments)
 
-static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe, bool spec = false, int k_out = 0) {
+static SlabPlan plan_slabs_one(int64_t N, int k, int cap, int align, bool safe, bool spec, int k_out, bool mid) {
   SlabPlan pl;
   int64_t seen = 0;
   const int64_t room = cap - k;
   auto round_dn = [&](int64_t v) { return std::max<int64_t>(align, v / align * align); };
+  auto push = [&](int64_t rows, int rank) { pl.rows.push_back(rows); pl.spec_rank.push_back(rank); seen += rows; };
   while (seen < N) {
+    const double g = (double)seen * (double)room / (2.0 * (double)k);  // geometric slab
     if (spec && !safe && g_speculate && seen > 0) {
+      const int rank_min = (int)std::ceil(3.0 * kSpecMinRank);
       const double r0 = (double)k * (double)seen / (double)N;  // expected rank of the final k-th best
-      const double g = (double)seen * (double)room / (2.0 * (double)k);
-      // worth it only if the geometric plan still needs two or more slabs
+      // final: worth it only if the geometric plan still needs two or more slabs
       if (r0 >= kSpecMinRank && std::ceil(3.0 * r0) < (double)k_out && 3.0 * r0 < 0.75 * k && (double)(N - seen) > g) {
-        pl.spec_slab = (int)pl.rows.size();
-        pl.spec_rank = (int)std::ceil(3.0 * r0);
-        pl.rows.push_back(N - seen);
+        push(N - seen, (int)std::ceil(3.0 * r0));
         break;
+      }
+      // mid: up to the row count T at which r0 = kSpecMinRank
+      const int64_t T = (int64_t)((double)k * (double)seen / kSpecMinRank);
+      if (mid && r0 < kSpecMinRank && rank_min < k_out && 3.0 * kSpecMinRank < 0.75 * k && 4.5 * k <= cap &&
+          T - seen > (int64_t)(1.5 * g)) {
+        push(std::min(round_dn(T - seen), N - seen), rank_min);
+        continue;
       }
     }
     int64_t rows;
@@ -255,14 +288,19 @@ static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe, bool
       // in pieces that never straddle a unit (the tensor kernels address whole 256-row blocks)
       rows = room >= align ? room / align * align : std::min<int64_t>(room, align - seen % align);
     } else {
-      const double g = (double)seen * (double)room / (2.0 * (double)k);
       rows = round_dn((int64_t)std::min<double>(g, 4e18));
     }
-    rows = std::min(rows, N - seen);
-    pl.rows.push_back(rows);
-    seen += rows;
+    push(std::min(rows, N - seen), 0);
   }
   return pl;
+}
+
+// a speculative mid slab is used only where it saves launches
+static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe, bool spec = false, int k_out = 0) {
+  SlabPlan plain = plan_slabs_one(N, k, cap, align, safe, spec, k_out, false);
+  if (!spec || safe || !g_speculate) return plain;
+  SlabPlan mid = plan_slabs_one(N, k, cap, align, safe, spec, k_out, true);
+  return mid.rows.size() < plain.rows.size() ? mid : plain;
 }
 
 // Block multiplier of the tensor path's processing order (TcParams::perm): an integer P near
@@ -306,17 +344,8 @@ static uint64_t pick_perm(int64_t nblk) {
   return best ? best : n - 1;  // n - 1 is always coprime
 }
 
-// one pass over the corpus for queries q_d[0..nq) (nq <= kQueryChunk)
-// rescore = true: the tensor kernels run ONE fp16 MMA pass (approximate scores), the buffers keep
-// everything within 2*eps(q) of the k-th best approximate score, and the survivors get exact fp32
-// scores at the end; rescore = false: three-pass split precision, scores final as they come
-// defer = true (two-phase sharded search): stop after the last compaction, leaving the candidate
-// superset in the workspace; cmx_search_end rescoring follows once the shards have exchanged their
-// k-th best approximate scores
-static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d,
-                       int64_t id_base, int path, bool rescore, bool safe, bool speculate, cudaStream_t st,
-                       unsigned* overflowed, bool defer = false) {
-  if (path != CMX_PATH_TENSOR) rescore = false;
+// workspace + (tensor path) operand planes, query planes and rescore margins for queries q_d[0..nq)
+static int prepare_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, int path, bool rescore, cudaStream_t st) {
   const int cap = pick_cap(ix, k);
   const int64_t nq_pad = (nq + 127) / 128 * 128;
   CMX_TRY(ensure_buf(&ix->ws.tau, &ix->tau_cap, 2 * nq_pad));
@@ -345,15 +374,66 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
     }
     CMX_TRY(launch_split_planes(q_d, nq, ix->d, ix->d_pad, ix->q_scale, 1.0f, ix->Qhi, rescore ? nullptr : ix->Qlo, st));
     if (rescore) {
-      // |approx - exact| <= eps(q), margin = 2 eps(q): see query_margin_kernel.  gamma = 2*d*2^-23 bounds
-      // the fp32 accumulation error of the tensor core plus that of the exact rescoring chain.
+      // |approx - exact| <= eps(q), margin = 2 eps(q): see query_margin_kernel and DESIGN.md 4b.  gamma =
+      // 2*d*2^-23 covers the fp32 accumulation error of the tensor core (measured: tests/test_gpu_eps_bound.py)
+      // plus that of the exact rescoring chain.
       const float gamma = 2.0f * (float)ix->d * 1.1920929e-07f;
       CMX_TRY(ensure_buf(&ix->margin_buf, &ix->margin_cap, nq_pad));
       CMX_TRY(launch_query_margin(q_d, ix->Qhi, nq, ix->d, ix->d_pad, ix->q_scale, std::max(ix->row_norm_max, ix->norm_floor),
-                                  std::max(ix->row_resid_max, ix->resid_floor), gamma, ix->margin_buf, st));
+                                  std::max(ix->row_resid_max, ix->resid_floor), ix->bounds_from_dev ? ix->bounds_dev : nullptr,
+                                  gamma, ix->margin_buf, st));
       ix->ws.margin = ix->margin_buf;
     }
   }
+  return CMX_OK;
+}
+
+// ---- prescoring resources ----------------------------------------------------------------------
+static int g_prescore = 1;  // 0: all exact scores after the last slab (experiments)
+constexpr int64_t kSubRows = 180 * 1024;  // rows per scoring launch of a prescored last slab (>= 2 ms of tensor work)
+
+static int ensure_side(cmx_index* ix) {
+  if (ix->side) return CMX_OK;
+  CMX_CUDA(cudaStreamCreateWithFlags(&ix->side, cudaStreamNonBlocking));
+  for (int i = 0; i <= kMaxSub; ++i) CMX_CUDA(cudaEventCreateWithFlags(&ix->ev_sub[i], cudaEventDisableTiming));
+  CMX_CUDA(cudaEventCreateWithFlags(&ix->ev_side_done, cudaEventDisableTiming));
+  return CMX_OK;
+}
+
+// event times of the slabs of the last pass -> stats (the events must have completed)
+static void collect_slab_times(cmx_index* ix) {
+  for (int s = 0; s < ix->timed_slabs; ++s) {
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, ix->ev[4 * s + 0], ix->ev[4 * s + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (cudaEventElapsedTime(&b, ix->ev[4 * s + 1], ix->ev[4 * s + 2]) != cudaSuccess) { cudaGetLastError(); continue; }
+    ix->stats.score_ms += a;
+    ix->stats.select_ms += b;
+    if (getenv("CMX_DEBUG_SLABS")) fprintf(stderr, "[cmx] slab %d score %.3f ms select %.3f ms\n", s, a, b);
+  }
+  ix->timed_slabs = 0;
+}
+
+// one pass over the corpus for queries q_d[0..nq) (nq <= kQueryChunk)
+// rescore = true: the tensor kernels run ONE fp16 MMA pass (approximate scores), the buffers keep
+// everything within 2*eps(q) of the k-th best approximate score, and the survivors get exact fp32
+// scores at the end; rescore = false: three-pass split precision, scores final as they come
+// defer = true (two-phase sharded search): stop after the last compaction, leaving the candidate
+// superset in the workspace; cmx_search_end rescoring follows once the shards have exchanged their
+// k-th best approximate scores.  overflowed == NULL: asynchronous -- nothing is read back, the
+// caller looks at ws.overflow (and the event times) later.
+// est_scale: fraction of this shard's k best that is expected in the final answer (1 / number of
+// shards): sets how deep prescore_kernel goes.
+static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float* D_d, int64_t* I_d,
+                       int64_t id_base, int path, bool rescore, bool safe, bool speculate, cudaStream_t st,
+                       unsigned* overflowed, bool defer = false, float est_scale = 1.0f) {
+  if (path != CMX_PATH_TENSOR) rescore = false;
+  CMX_NVTX("cmx:search_pass");
+  {
+    CMX_NVTX("cmx:prologue");
+    CMX_TRY(prepare_pass(ix, q_d, nq, k, path, rescore, st));
+  }
+  const int cap = ix->ws.cap;
+  const int64_t nq_pad = (nq + 127) / 128 * 128;
 
   const int align = (path == CMX_PATH_TENSOR) ? 256 : 32;
   // rescore mode keeps the margin band on top of the k best: plan for ~4/3 k resident candidates
@@ -363,55 +443,104 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
   const uint64_t perm = pick_perm(nblk);
   const int64_t n_plan = (path == CMX_PATH_TENSOR) ? nblk * 256 : ix->n;
   SlabPlan pl = plan_slabs(n_plan, k_plan, cap, align, safe, speculate && path == CMX_PATH_TENSOR, k);
-  const bool prof = g_profiling && !safe && (int)pl.rows.size() <= kMaxSlabEvents;
-  if (prof) CMX_TRY(ensure_events(ix));
-  int64_t seen = 0;
   const int nslabs = (int)pl.rows.size();
+  const bool prof = g_profiling && !safe && nslabs <= kMaxSlabEvents;
+  if (prof) CMX_TRY(ensure_events(ix));
+  ix->timed_slabs = 0;
+
+  // Prescoring: the last slab is cut into up to kMaxSub scoring launches; between them the append
+  // cursors are snapshotted, and prescore_kernel -- on a second stream, beside the next scoring
+  // launch -- gives exact scores to the likely winners found so far (select.cu).
+  int nsub = 1;
+  if (rescore && !safe && g_prescore && nslabs >= 2 && prescore_smem_bytes(ix->d) <= kPrescoreMaxSmem) {
+    nsub = (int)std::min<int64_t>(kMaxSub, std::max<int64_t>(1, pl.rows[nslabs - 1] / kSubRows));
+    CMX_TRY(ensure_side(ix));
+    CMX_TRY(ensure_buf(&ix->snap, &ix->snap_cap, (int64_t)(kMaxSub + 1) * nq_pad));
+    CMX_TRY(ensure_buf(&ix->est_buf, &ix->est_cap, nq_pad));
+    ix->ws.est = ix->est_buf;
+  } else {
+    ix->ws.est = nullptr;
+  }
+  const bool prescoring = ix->ws.est != nullptr;
+
+  auto score = [&](int s, int64_t row0, int64_t rows, int64_t seen_before) -> int {
+    const int dense = (s == 0) ? 1 : 0;
+    if (path == CMX_PATH_TENSOR)
+      return launch_tensor_score(ix->Bhi, ix->Blo, ix->n, row0, rows, ix->d_pad, ix->Qhi, ix->Qlo, nq, nq_pad, ix->q_scale + 1,
+                                 1.0f / ix->plane_scale, ix->ws, dense, perm, rescore ? 1 : 3,
+                                 seen_before > 0 ? (double)(pl.spec_rank[s] > 0 ? pl.spec_rank[s] : k_plan) / (double)seen_before : 1.0,
+                                 ix->progress, st, ix->sm_count);
+    return launch_stream_score(ix->X, row0, rows, ix->d, q_d, (int)nq, ix->ws, 0, dense, row0, st, ix->sm_count);
+  };
+
+  int64_t seen = 0;
   for (int s = 0; s < nslabs; ++s) {
     const int64_t rows = pl.rows[s];
-    const int dense = (s == 0) ? 1 : 0;
+    const int last = (s == nslabs - 1) ? 1 : 0;
     if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 0], st));
-    if (path == CMX_PATH_TENSOR) {
-      CMX_TRY(launch_tensor_score(ix->Bhi, ix->Blo, ix->n, seen, rows, ix->d_pad, ix->Qhi, ix->Qlo, nq, nq_pad,
-                                  ix->q_scale + 1, 1.0f / ix->plane_scale, ix->ws, dense, perm, rescore ? 1 : 3,
-                                  seen > 0 ? (double)(s == pl.spec_slab ? pl.spec_rank : k_plan) / (double)seen : 1.0,
-                                  ix->progress, st, ix->sm_count));
-    } else {
-      CMX_TRY(launch_stream_score(ix->X, seen, rows, ix->d, q_d, (int)nq, ix->ws, 0, dense, seen, st, ix->sm_count));
+    {
+      CMX_NVTX("cmx:score");
+      if (last && prescoring) {
+        // candidates kept so far: exact scores while the first launch runs
+        CMX_TRY(launch_snapshot_counts(ix->ws, nq, ix->snap, st));
+        CMX_CUDA(cudaEventRecord(ix->ev_sub[0], st));
+        CMX_CUDA(cudaStreamWaitEvent(ix->side, ix->ev_sub[0], 0));
+        CMX_TRY(launch_prescore(ix->X, ix->d, q_d, ix->ws, nq, nullptr, ix->snap, ix->side));
+        const int64_t blocks = rows / 256;  // whole 256-row blocks (a speculative / geometric slab always is)
+        int64_t b0 = 0;
+        for (int i = 0; i < nsub; ++i) {
+          const int64_t b1 = (i == nsub - 1) ? blocks : blocks * (i + 1) / nsub;
+          const int64_t r0 = b0 * 256, r1 = (i == nsub - 1) ? rows : b1 * 256;
+          if (r1 > r0) CMX_TRY(score(s, seen + r0, r1 - r0, seen));
+          if (i < nsub - 1) {
+            uint32_t* snap_hi = ix->snap + (int64_t)(i + 1) * nq_pad;
+            CMX_TRY(launch_snapshot_counts(ix->ws, nq, snap_hi, st));
+            CMX_CUDA(cudaEventRecord(ix->ev_sub[i + 1], st));
+            CMX_CUDA(cudaStreamWaitEvent(ix->side, ix->ev_sub[i + 1], 0));
+            CMX_TRY(launch_prescore(ix->X, ix->d, q_d, ix->ws, nq, ix->snap + (int64_t)i * nq_pad, snap_hi, ix->side));
+          }
+          b0 = b1;
+        }
+        CMX_CUDA(cudaEventRecord(ix->ev_side_done, ix->side));
+        CMX_CUDA(cudaStreamWaitEvent(st, ix->ev_side_done, 0));  // the compaction moves keys: prescoring must be done
+      } else {
+        CMX_TRY(score(s, seen, rows, seen));
+      }
     }
     if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 1], st));
-    if (dense) CMX_TRY(launch_set_counts(ix->ws, nq, (uint32_t)rows, st));
-    const int last = (s == nslabs - 1) ? 1 : 0;
-    const int spec_rank = (s + 1 == pl.spec_slab) ? pl.spec_rank : 0;  // publish the guess for the next slab
-    const int verify = (s == pl.spec_slab) ? 1 : 0;                    // this slab ran under a guess
-    if (rescore) {
-      // keep the margin band, then (after the last slab) exact fp32 scores + exact top-k
-      CMX_TRY(launch_compact(ix->ws, nq, k, 0, D_d, I_d, id_base, st, spec_rank, verify));
-      if (last && !defer) CMX_TRY(launch_rescore(ix->X, ix->d, q_d, ix->ws, nq, k, D_d, I_d, id_base, RescoreCut(), st));
-    } else {
-      CMX_TRY(launch_compact(ix->ws, nq, k, last, D_d, I_d, id_base, st, spec_rank, verify));
+    if (s == 0) CMX_TRY(launch_set_counts(ix->ws, nq, (uint32_t)rows, st));
+    const int spec_rank = last ? 0 : pl.spec_rank[s + 1];  // publish the guess for the next slab
+    const int verify = pl.spec_rank[s] > 0 ? 1 : 0;        // this slab ran under a guess
+    int est_rank = 0;
+    if (prescoring && s == nslabs - 2) {
+      // where the FINAL k-th best is expected among the rows seen so far (x est_scale when only that share of
+      // this shard's best can make the global answer); 1.5x deeper: wasted prescoring is hidden, missed is not
+      const double r0 = (double)k_plan * (double)(seen + rows) / (double)n_plan * (double)est_scale;
+      est_rank = (int)std::min<double>(std::max(1.0, std::ceil(1.5 * r0)), (double)(k - 1));
+    }
+    {
+      CMX_NVTX(last ? "cmx:compact+rescore" : "cmx:compact");
+      if (rescore) {
+        // keep the margin band, then (after the last slab) exact fp32 scores + exact top-k
+        CMX_TRY(launch_compact(ix->ws, nq, k, 0, D_d, I_d, id_base, st, spec_rank, verify, est_rank));
+        if (last && !defer) CMX_TRY(launch_rescore(ix->X, ix->d, q_d, ix->ws, nq, k, D_d, I_d, id_base, RescoreCut(), st));
+      } else {
+        CMX_TRY(launch_compact(ix->ws, nq, k, last, D_d, I_d, id_base, st, spec_rank, verify, 0));
+      }
     }
     if (prof) CMX_CUDA(cudaEventRecord(ix->ev[4 * s + 2], st));
     seen += rows;
   }
+  ix->stats.slabs += nslabs;
+  ix->stats.score_launches += (path == CMX_PATH_TENSOR) ? nslabs - 1 + nsub : nslabs * (int)((nq + 7) / 8);
+  ix->stats.select_launches += nslabs + ((rescore && !defer) ? 1 : 0);
+  if (prof) ix->timed_slabs = nslabs;
+  if (overflowed == nullptr) return CMX_OK;  // asynchronous: flags and times are read later
   uint32_t ovf = 0;
   CMX_CUDA(cudaMemcpyAsync(&ovf, ix->ws.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CMX_CUDA(cudaStreamSynchronize(st));
   *overflowed = ovf;
-  ix->stats.slabs += nslabs;
-  ix->stats.score_launches += nslabs * ((path == CMX_PATH_TENSOR) ? 1 : (int)((nq + 7) / 8));
-  ix->stats.select_launches += nslabs + (rescore ? 1 : 0);
-  if (prof) {
-    for (int s = 0; s < nslabs; ++s) {
-      float a = 0.f, b = 0.f;
-      cudaEventElapsedTime(&a, ix->ev[4 * s + 0], ix->ev[4 * s + 1]);
-      cudaEventElapsedTime(&b, ix->ev[4 * s + 1], ix->ev[4 * s + 2]);
-      ix->stats.score_ms += a;
-      ix->stats.select_ms += b;
-      if (getenv("CMX_DEBUG_SLABS"))
-        fprintf(stderr, "[cmx] slab %d rows %lld score %.3f ms select %.3f ms\n", s, (long long)pl.rows[s], a, b);
-    }
-  }
+  collect_slab_times(ix);
   return CMX_OK;
 }
 
@@ -434,14 +563,14 @@ static int search_device(cmx_index* ix, const float* q_d, int64_t nq, int k, flo
   // (1-4 queries, 7.0-7.3 TB/s), the split-precision tensor kernels 5.0-5.2 ms (up to 32 queries),
   // the one-pass tensor kernels of the rescore mode 2.5-2.8 ms (they read only the 18 GB hi plane)
   if (path == CMX_PATH_AUTO) {
-    const bool rescore_ok = ix->precision == CMX_PRECISION_RESCORE && ix->row_norm_max > 0.f;
+    const bool rescore_ok = rescore_usable(ix);
     path = (rescore_ok || nq > 4) ? CMX_PATH_TENSOR : CMX_PATH_STREAM;
   }
   if (path == CMX_PATH_STREAM && (ix->d & 3) != 0) path = CMX_PATH_TENSOR;
   ix->stats.path = path;
   for (int64_t q0 = 0; q0 < nq; q0 += kQueryChunk) {
     const int64_t nqc = std::min<int64_t>(kQueryChunk, nq - q0);
-    const bool rescore = path == CMX_PATH_TENSOR && ix->precision == CMX_PRECISION_RESCORE && ix->row_norm_max > 0.f;
+    const bool rescore = path == CMX_PATH_TENSOR && rescore_usable(ix);
     // Attempts, cheapest first; stats.reruns = how many of them had to be repeated.  An attempt is a
     // precision (rescore: one fp16 pass + exact rescoring of the margin band; split: exact scores, no
     // band) and a slab schedule (0 = geometric slabs with a speculative last slab, 1 = geometric
@@ -547,9 +676,14 @@ int cmx_index_free(cmx_index* ix) {
   DevGuard g(ix->device);
   void* ptrs[] = {ix->X, ix->Bhi, ix->Blo, ix->absmax_dev, ix->ws.tau, ix->ws.cnt, ix->ws.cand, ix->ws.overflow,
                   ix->q_dev, ix->p_dev, ix->s_dev, ix->Qhi, ix->Qlo, ix->q_absmax, ix->q_scale, ix->margin_buf, ix->progress, ix->D_dev, ix->I_dev,
-                  ix->flags_dev, ix->w_dev, ix->mode_dev};
+                  ix->flags_dev, ix->snap, ix->est_buf, ix->bounds_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (ix->side) {
+    cudaStreamDestroy(ix->side);
+    for (int i = 0; i <= kMaxSub; ++i) cudaEventDestroy(ix->ev_sub[i]);
+    cudaEventDestroy(ix->ev_side_done);
+  }
   if (ix->ev_ready)
     for (int i = 0; i < 4 * kMaxSlabEvents; ++i) cudaEventDestroy(ix->ev[i]);
   delete ix;
@@ -560,6 +694,7 @@ int cmx_index_reserve(cmx_index* ix, int64_t n) {
   CMX_CHECK(ix != nullptr, "null index");
   CMX_CHECK(n >= 0 && n < (int64_t)0x7fffff00, "reserve: row count %lld out of range (max 2^31 rows per shard)", (long long)n);
   DevGuard g(ix->device);
+  ix->pending = false;
   return grow_store(ix, n);
 }
 
@@ -570,6 +705,7 @@ int cmx_index_add(cmx_index* ix, const float* x, int64_t n, int x_on_device) {
   CMX_CHECK(x != nullptr, "null data");
   CMX_CHECK(ix->n + n < (int64_t)0x7fffff00, "index would exceed 2^31 rows per shard");
   DevGuard g(ix->device);
+  ix->pending = false;
   CMX_TRY(grow_store(ix, ix->n + n));
   float* dst = ix->X + ix->n * ix->d;
   CMX_CUDA(cudaMemcpy(dst, x, (size_t)n * ix->d * sizeof(float), x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
@@ -591,6 +727,7 @@ int cmx_index_add(cmx_index* ix, const float* x, int64_t n, int x_on_device) {
 
 int cmx_index_reset(cmx_index* ix) {
   CMX_CHECK(ix != nullptr, "null index");
+  ix->pending = false;
   ix->n = 0;
   ix->plane_rows = 0;
   ix->lo_rows = 0;
@@ -670,8 +807,14 @@ int cmx_index_set_precision(cmx_index* ix, int mode) {
   return CMX_OK;
 }
 
-int cmx_index_last_stats(const cmx_index* ix, cmx_search_stats* out) {
-  CMX_CHECK(ix && out, "null argument");
+int cmx_index_last_stats(const cmx_index* cix, cmx_search_stats* out) {
+  CMX_CHECK(cix && out, "null argument");
+  cmx_index* ix = const_cast<cmx_index*>(cix);
+  if (ix->timed_slabs > 0) {  // an asynchronous pass: its events complete with the work
+    DevGuard g(ix->device);
+    cudaEventSynchronize(ix->ev[4 * (ix->timed_slabs - 1) + 2]);
+    collect_slab_times(ix);
+  }
   *out = ix->stats;
   return CMX_OK;
 }
@@ -686,6 +829,7 @@ int cmx_index_search(cmx_index* ix, const float* q, int64_t nq, int k, float* D,
   CMX_CHECK(q && D && I, "null buffer");
   DevGuard g(ix->device);
   cudaStream_t st = (cudaStream_t)stream;
+  ix->pending = false;
   stats_begin(ix, nq);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_profiling) {
@@ -739,16 +883,14 @@ static int prepare_alphas(const double* alphas, int nA, std::vector<float>& w, s
   return CMX_OK;
 }
 
-// shared by cmx_mix_normalize (ix == NULL: temporary buffers) and cmx_search_mixed
+// shared by cmx_mix_normalize, cmx_search_mixed and cmx_search_prepare: asynchronous (the weights are kernel arguments)
 static int mix_on_device(const float* P_d, const float* S_d, int64_t nq, int d, const double* alphas, int nA,
-                         float* out_d, uint8_t* flags_d, float* w_d, int* mode_d, cudaStream_t st) {
+                         float* out_d, uint8_t* flags_d, cudaStream_t st) {
   std::vector<float> w;
   std::vector<int> mode;
   prepare_alphas(alphas, nA, w, mode);
-  CMX_CUDA(cudaMemcpyAsync(w_d, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-  CMX_CUDA(cudaMemcpyAsync(mode_d, mode.data(), mode.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  CMX_CUDA(cudaStreamSynchronize(st));  // w/mode are stack-owned host vectors
-  return launch_mix_normalize(P_d, S_d, nq, d, w_d, w_d + nA, mode_d, nA, out_d, flags_d, st);
+  CMX_NVTX("cmx:mix_normalize");
+  return launch_mix_normalize(P_d, S_d, nq, d, w.data(), w.data() + nA, mode.data(), nA, out_d, flags_d, st);
 }
 
 int cmx_mix_normalize(const float* P, const float* S, int64_t nq, int d, const double* alphas, int nA, float* out,
@@ -763,14 +905,11 @@ int cmx_mix_normalize(const float* P, const float* S, int64_t nq, int d, const d
   cudaStream_t st = (cudaStream_t)stream;
   const size_t in_bytes = (size_t)nq * d * sizeof(float);
   const size_t out_elems = (size_t)nA * nq * d;
-  float *P_d = nullptr, *S_d = nullptr, *out_d = nullptr, *w_d = nullptr;
+  float *P_d = nullptr, *S_d = nullptr, *out_d = nullptr;
   uint8_t* f_d = nullptr;
-  int* m_d = nullptr;
   int rc = CMX_OK;
   auto cleanup = [&]() {
     if (!io_on_device) { cudaFree(P_d); cudaFree(S_d); cudaFree(out_d); cudaFree(f_d); }
-    cudaFree(w_d);
-    cudaFree(m_d);
   };
 #define MIX_CUDA(expr)                                                             \
   do {                                                                             \
@@ -781,8 +920,6 @@ int cmx_mix_normalize(const float* P, const float* S, int64_t nq, int d, const d
       return CMX_ERR_CUDA;                                                         \
     }                                                                              \
   } while (0)
-  MIX_CUDA(cudaMalloc((void**)&w_d, 2 * (size_t)nA * sizeof(float)));
-  MIX_CUDA(cudaMalloc((void**)&m_d, (size_t)nA * sizeof(int)));
   if (io_on_device) {
     P_d = const_cast<float*>(P);
     S_d = const_cast<float*>(S);
@@ -796,7 +933,7 @@ int cmx_mix_normalize(const float* P, const float* S, int64_t nq, int d, const d
     MIX_CUDA(cudaMemcpyAsync(P_d, P, in_bytes, cudaMemcpyHostToDevice, st));
     MIX_CUDA(cudaMemcpyAsync(S_d, S, in_bytes, cudaMemcpyHostToDevice, st));
   }
-  rc = mix_on_device(P_d, S_d, nq, d, alphas, nA, out_d, f_d, w_d, m_d, st);
+  rc = mix_on_device(P_d, S_d, nq, d, alphas, nA, out_d, f_d, st);
   if (rc != CMX_OK) { cleanup(); return rc; }
   if (!io_on_device) {
     MIX_CUDA(cudaMemcpyAsync(out, out_d, out_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -819,6 +956,7 @@ int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int64_t nq, 
   DevGuard g(ix->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t nqt = nq * (int64_t)nA;
+  ix->pending = false;
   stats_begin(ix, nqt);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_profiling) {
@@ -832,8 +970,6 @@ int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int64_t nq, 
   int64_t* I_d = I;
   CMX_TRY(ensure_buf(&ix->q_dev, &ix->q_cap, nqt * (int64_t)ix->d));
   CMX_TRY(ensure_buf(&ix->flags_dev, &ix->flags_cap, nqt));
-  CMX_TRY(ensure_buf(&ix->w_dev, &ix->w_cap, 2 * (int64_t)nA));
-  CMX_TRY(ensure_buf(&ix->mode_dev, &ix->mode_cap, (int64_t)nA));
   bool staged_out = false;
   if (!io_on_device) {
     CMX_TRY(ensure_buf(&ix->p_dev, &ix->p_cap, nq * (int64_t)ix->d));
@@ -851,7 +987,7 @@ int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int64_t nq, 
     }
   }
   uint8_t* f_d = (io_on_device && flags) ? flags : ix->flags_dev;
-  CMX_TRY(mix_on_device(P_d, S_d, nq, ix->d, alphas, nA, ix->q_dev, f_d, ix->w_dev, ix->mode_dev, st));
+  CMX_TRY(mix_on_device(P_d, S_d, nq, ix->d, alphas, nA, ix->q_dev, f_d, st));
   CMX_TRY(search_device(ix, ix->q_dev, nqt, k, D_d, I_d, id_base, path, st));
   if (staged_out) {
     CMX_CUDA(cudaMemcpyAsync(D, D_d, (size_t)nqt * k * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -865,33 +1001,78 @@ int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int64_t nq, 
   return CMX_OK;
 }
 
-int cmx_search_mixed_begin(cmx_index* ix, const float* P, const float* S, int64_t nq, const double* alphas, int nA, int k,
-                           int64_t id_base, float* scores_out, int* overflowed, void* stream) {
-  CMX_CHECK(ix != nullptr, "null index");
+// ---- sharded (two-phase) search: asynchronous building blocks ------------------------------------
+int cmx_search_prepare(cmx_index* ix, const float* P, const float* S, int64_t nq, const double* alphas, int nA,
+                       const float** q_out, void* stream) {
+  CMX_CHECK(ix != nullptr && q_out != nullptr, "null argument");
   CMX_CHECK(nq > 0 && nA > 0, "bad shape");
-  CMX_CHECK(k >= 1 && k <= CMX_MAX_K, "k=%d out of range [1, %d]", k, CMX_MAX_K);
-  CMX_CHECK(P && S && alphas && scores_out && overflowed, "null buffer");
-  const int64_t nqt = nq * (int64_t)nA;
-  CMX_CHECK(nqt <= kQueryChunk, "two-phase search handles at most %lld queries per call", (long long)kQueryChunk);
-  CMX_CHECK(ix->precision == CMX_PRECISION_RESCORE && ix->row_norm_max > 0.f && ix->n > 0,
-            "two-phase search needs the rescore precision and a non-empty index");
+  CMX_CHECK(P && S && alphas, "null buffer");
   DevGuard g(ix->device);
   cudaStream_t st = (cudaStream_t)stream;
-  stats_begin(ix, nqt);
-  ix->stats.path = CMX_PATH_TENSOR;
   ix->pending = false;
+  const int64_t nqt = nq * (int64_t)nA;
   CMX_TRY(ensure_buf(&ix->q_dev, &ix->q_cap, nqt * (int64_t)ix->d));
   CMX_TRY(ensure_buf(&ix->flags_dev, &ix->flags_cap, nqt));
-  CMX_TRY(ensure_buf(&ix->w_dev, &ix->w_cap, 2 * (int64_t)nA));
-  CMX_TRY(ensure_buf(&ix->mode_dev, &ix->mode_cap, (int64_t)nA));
-  CMX_TRY(mix_on_device(P, S, nq, ix->d, alphas, nA, ix->q_dev, ix->flags_dev, ix->w_dev, ix->mode_dev, st));
-  unsigned ovf = 0;
-  CMX_TRY(search_pass(ix, ix->q_dev, nqt, k, nullptr, nullptr, id_base, CMX_PATH_TENSOR, true, false, true, st, &ovf, true));
-  CMX_TRY(launch_export_scores(ix->ws, nqt, k, scores_out, st));
-  CMX_CUDA(cudaStreamSynchronize(st));
-  *overflowed = ovf ? 1 : 0;
-  ix->pending = !ovf;
-  ix->pend_nq = nqt;
+  CMX_TRY(mix_on_device(P, S, nq, ix->d, alphas, nA, ix->q_dev, ix->flags_dev, st));
+  *q_out = ix->q_dev;
+  return CMX_OK;
+}
+
+int cmx_index_export_bounds(cmx_index* ix, float* out2_dev, void* stream) {
+  CMX_CHECK(ix && out2_dev, "null argument");
+  DevGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ix->n > 0 && ix->precision == CMX_PRECISION_RESCORE) CMX_TRY(ensure_planes(ix, false, st));
+  return launch_store2(out2_dev, std::max(ix->row_norm_max, ix->norm_floor), std::max(ix->row_resid_max, ix->resid_floor), st);
+}
+
+int cmx_search_begin(cmx_index* ix, const float* q, int64_t nq, int k, int64_t id_base, const float* const* bounds_parts,
+                     int nparts, float est_scale, float* scores_out, uint32_t* flag_out, void* stream) {
+  CMX_CHECK(ix != nullptr, "null index");
+  CMX_CHECK(nq > 0 && nq <= kQueryChunk, "two-phase search handles 1..%lld queries per call (got %lld): chunk the batch",
+            (long long)kQueryChunk, (long long)nq);
+  CMX_CHECK(k >= 1 && k <= CMX_MAX_K, "k=%d out of range [1, %d]", k, CMX_MAX_K);
+  CMX_CHECK(q && scores_out && flag_out, "null buffer");
+  CMX_CHECK(nparts >= 0 && nparts <= CMX_MAX_PEERS && (nparts == 0 || bounds_parts != nullptr), "bad bounds_parts");
+  CMX_CHECK(est_scale > 0.f && est_scale <= 1.f, "est_scale must lie in (0, 1]");
+  DevGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  stats_begin(ix, nq);
+  ix->stats.path = CMX_PATH_TENSOR;
+  ix->pending = false;
+  if (!ix->ws.overflow) CMX_CUDA(cudaMalloc((void**)&ix->ws.overflow, sizeof(uint32_t)));
+  // a shard that cannot run the one-pass arithmetic (split precision requested, non-finite error bound)
+  // says so in its status word: every shard reads every word, so all of them fall back together
+  const bool usable = ix->n == 0 || rescore_usable(ix);
+  if (!usable || ix->n == 0) {
+    CMX_TRY(launch_fill_f32(scores_out, nq * (int64_t)k, CMX_NEG_PAD, st));
+    CMX_TRY(launch_publish_flag(nullptr, usable ? 0u : CMX_FLAG_NO_TWO_PHASE, flag_out, st));
+    if (usable) {  // empty shard: no candidates, cmx_search_end writes padding
+      const int64_t nq_pad = (nq + 127) / 128 * 128;
+      CMX_TRY(ensure_buf(&ix->ws.cnt, &ix->cnt_cap, nq_pad));
+      CMX_TRY(ensure_buf(&ix->ws.cand, &ix->cand_cap_elems, nq * (int64_t)pick_cap(ix, k)));
+      ix->ws.cap = pick_cap(ix, k);
+      ix->ws.margin = nullptr;
+      CMX_CUDA(cudaMemsetAsync(ix->ws.cnt, 0, (size_t)nq_pad * sizeof(uint32_t), st));
+      CMX_CUDA(cudaMemsetAsync(ix->ws.overflow, 0, sizeof(uint32_t), st));
+    }
+  } else {
+    // the margin of every shard comes from the corpus maxima over ALL shards (read in place)
+    if (nparts > 0) {
+      if (!ix->bounds_dev) CMX_CUDA(cudaMalloc((void**)&ix->bounds_dev, 2 * sizeof(float)));
+      CMX_TRY(launch_max_bounds(bounds_parts, nparts, ix->bounds_dev, st));
+    }
+    ix->bounds_from_dev = nparts > 0;
+    const int rc = search_pass(ix, q, nq, k, nullptr, nullptr, id_base, CMX_PATH_TENSOR, true, false, true, st, nullptr, true, est_scale);
+    ix->bounds_from_dev = false;
+    CMX_TRY(rc);
+    CMX_TRY(launch_export_scores(ix->ws, nq, k, scores_out, st));
+    CMX_TRY(launch_publish_flag(ix->ws.overflow, 0u, flag_out, st));
+  }
+  ix->pending = true;
+  ix->pend_skip = !usable;  // flagged: cmx_search_end is a no-op, the step is redone without the two-phase cut
+  ix->pend_q = q;
+  ix->pend_nq = nq;
   ix->pend_k = k;
   ix->pend_id_base = id_base;
   stats_end(ix);
@@ -899,7 +1080,8 @@ int cmx_search_mixed_begin(cmx_index* ix, const float* P, const float* S, int64_
 }
 
 int cmx_union_kth(const float* const* score_parts, int nparts, int64_t nq, int k, int64_t q0, int64_t q1,
-                  float* const* kth_outs, int nouts, int device, void* stream) {
+                  float* const* kth_outs, int nouts, const uint32_t* const* flag_parts, int nflags, uint32_t* flag_any,
+                  int device, void* stream) {
   CMX_CHECK(score_parts && kth_outs, "null pointer table");
   CMX_CHECK(k >= 1 && k <= CMX_MAX_K, "k=%d out of range [1, %d]", k, CMX_MAX_K);
   CMX_CHECK(q0 >= 0 && q0 <= q1 && q1 <= nq, "bad query slice");
@@ -907,12 +1089,13 @@ int cmx_union_kth(const float* const* score_parts, int nparts, int64_t nq, int k
   CMX_TRY(cmx_device_count(&ndev));
   CMX_CHECK(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
   DevGuard g(device);
-  return launch_union_kth(score_parts, nparts, k, q0, q1, kth_outs, nouts, (cudaStream_t)stream);
+  CMX_NVTX("cmx:union_kth");
+  return launch_union_kth(score_parts, nparts, k, q0, q1, kth_outs, nouts, flag_parts, nflags, flag_any, (cudaStream_t)stream);
 }
 
 int cmx_search_end(cmx_index* ix, const float* const* kth_parts, int nparts, float* D, int64_t* I, void* stream) {
   CMX_CHECK(ix != nullptr && D && I, "null argument");
-  CMX_CHECK(ix->pending, "cmx_search_end without a successful cmx_search_mixed_begin");
+  CMX_CHECK(ix->pending, "cmx_search_end without a pending cmx_search_begin (a search / add / reset in between cancels it)");
   CMX_CHECK(nparts >= 0 && nparts <= CMX_MAX_PEERS && (nparts == 0 || kth_parts != nullptr), "bad kth_parts");
   DevGuard g(ix->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -920,11 +1103,57 @@ int cmx_search_end(cmx_index* ix, const float* const* kth_parts, int nparts, flo
   cut.nparts = nparts;
   for (int i = 0; i < nparts; ++i) cut.kth[i] = kth_parts[i];
   const int launches0 = (int)g_launches.load();
-  CMX_TRY(launch_rescore(ix->X, ix->d, ix->q_dev, ix->ws, ix->pend_nq, ix->pend_k, D, I, ix->pend_id_base, cut, st));
-  CMX_CUDA(cudaStreamSynchronize(st));
   ix->pending = false;
+  if (ix->pend_skip) return CMX_OK;
+  {
+    CMX_NVTX("cmx:rescore");
+    CMX_TRY(launch_rescore(ix->X, ix->d, ix->pend_q, ix->ws, ix->pend_nq, ix->pend_k, D, I, ix->pend_id_base, cut, st));
+  }
   ix->stats.launches += (int)g_launches.load() - launches0;
   ix->stats.select_launches += 1;
+  return CMX_OK;
+}
+
+int cmx_peer_broadcast(const void* src, void* const* dsts, int ndst, int64_t bytes, int device, void* stream) {
+  CMX_CHECK(bytes >= 0 && ndst >= 0 && ndst <= CMX_MAX_PEERS, "bad argument");
+  if (bytes == 0 || ndst == 0) return CMX_OK;
+  CMX_CHECK(src && dsts, "null pointer");
+  CMX_CHECK((bytes & 15) == 0 && ((uintptr_t)src & 15) == 0, "peer broadcast works on 16-byte aligned blocks");
+  for (int i = 0; i < ndst; ++i) CMX_CHECK(dsts[i] && ((uintptr_t)dsts[i] & 15) == 0, "bad destination %d", i);
+  DevGuard g(device);
+  CMX_NVTX("cmx:peer_broadcast");
+  return launch_peer_broadcast(src, dsts, ndst, bytes, (cudaStream_t)stream);
+}
+
+int cmx_host_register(void* p, int64_t bytes, void** dev_ptr) {
+  CMX_CHECK(p && bytes > 0 && dev_ptr, "bad argument");
+  cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); e = cudaSuccess; }
+  CMX_CUDA(e);
+  CMX_CUDA(cudaHostGetDevicePointer(dev_ptr, p, 0));
+  return CMX_OK;
+}
+
+int cmx_host_unregister(void* p) {
+  CMX_CHECK(p != nullptr, "null pointer");
+  cudaError_t e = cudaHostUnregister(p);
+  if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); e = cudaSuccess; }
+  CMX_CUDA(e);
+  return CMX_OK;
+}
+
+int cmx_enable_peer_access(int device, int peer) {
+  int ndev = 0;
+  CMX_TRY(cmx_device_count(&ndev));
+  CMX_CHECK(device >= 0 && device < ndev && peer >= 0 && peer < ndev, "device %d / peer %d out of range (have %d)", device, peer, ndev);
+  if (device == peer) return CMX_OK;
+  int can = 0;
+  CMX_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+  CMX_CHECK(can, "device %d cannot map the memory of device %d (no NVLink / PCIe peer access)", device, peer);
+  DevGuard g(device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+  CMX_CUDA(e);
   return CMX_OK;
 }
 
@@ -993,9 +1222,50 @@ CMX_API int cmx_debug_plan_slabs(int64_t ntotal, int k, int cap, int rescore, in
   const int k_plan = rescore ? std::min(cap / 2, k + k / 3 + 8) : k;
   SlabPlan pl = plan_slabs(nblk * 256, k_plan, cap, 256, safe != 0, speculate != 0, k);
   *nslabs = (int)pl.rows.size();
-  *spec_slab = pl.spec_slab;
-  *spec_rank = pl.spec_rank;
+  // the LAST speculative slab and its rank (-1 / 0: none); spec_rank_out of every slab via cmx_debug_plan_ranks
+  *spec_slab = -1;
+  *spec_rank = 0;
+  for (int i = 0; i < *nslabs; ++i)
+    if (pl.spec_rank[(size_t)i] > 0) { *spec_slab = i; *spec_rank = pl.spec_rank[(size_t)i]; }
   for (int i = 0; i < *nslabs && i < max_slabs; ++i) rows_out[i] = pl.rows[(size_t)i];
+  return CMX_OK;
+}
+CMX_API int cmx_debug_plan_ranks(int64_t ntotal, int k, int cap, int rescore, int safe, int speculate, int* ranks_out, int max_slabs) {
+  CMX_CHECK(ntotal > 0 && k >= 1 && cap >= 2 * k && ranks_out, "bad argument");
+  const int64_t nblk = (ntotal + 255) / 256;
+  const int k_plan = rescore ? std::min(cap / 2, k + k / 3 + 8) : k;
+  SlabPlan pl = plan_slabs(nblk * 256, k_plan, cap, 256, safe != 0, speculate != 0, k);
+  for (int i = 0; i < (int)pl.rows.size() && i < max_slabs; ++i) ranks_out[i] = pl.spec_rank[(size_t)i];
+  return CMX_OK;
+}
+CMX_API int cmx_debug_set_prescore(int on) { g_prescore = on ? 1 : 0; return CMX_OK; }
+/* test hook: the APPROXIMATE scores the one-pass tensor scorer produces (rescore precision), for the `nrows` (a multiple
+ * of 256, <= the candidate capacity) row positions starting at position `pos0` of the processing order.  q, scores_out
+ * [nq, nrows], rows_out [nq, nrows] (corpus row of each score; -1 = padding) and margin_out [nq] (= 2 eps(q)) are device
+ * buffers.  Lets a test measure |approx - exact| against eps(q) directly. */
+CMX_API int cmx_debug_approx_scores(cmx_index* ix, const float* q, int64_t nq, int64_t pos0, int64_t nrows, float* scores_out,
+                                    int64_t* rows_out, float* margin_out, void* stream) {
+  CMX_CHECK(ix && q && scores_out && rows_out && margin_out, "null argument");
+  CMX_CHECK(nq > 0 && nq <= kQueryChunk, "1..%lld queries", (long long)kQueryChunk);
+  CMX_CHECK(ix->n > 0 && rescore_usable(ix), "needs a non-empty index in rescore precision");
+  DevGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  ix->pending = false;
+  const int k = 1;
+  CMX_TRY(prepare_pass(ix, q, nq, k, CMX_PATH_TENSOR, true, st));
+  const int cap = ix->ws.cap;
+  const int64_t nblk = (ix->n + 255) / 256;
+  CMX_CHECK(nrows > 0 && nrows <= cap && (nrows & 255) == 0 && (pos0 & 255) == 0 && pos0 + nrows <= nblk * 256,
+            "bad position range [%lld, +%lld) (capacity %d, %lld positions)", (long long)pos0, (long long)nrows, cap, (long long)(nblk * 256));
+  const int64_t nq_pad = (nq + 127) / 128 * 128;
+  CMX_CUDA(cudaMemsetAsync(ix->ws.cand, 0, (size_t)nq * cap * sizeof(uint64_t), st));
+  CMX_TRY(launch_tensor_score(ix->Bhi, ix->Blo, ix->n, pos0, nrows, ix->d_pad, ix->Qhi, ix->Qlo, nq, nq_pad, ix->q_scale + 1,
+                              1.0f / ix->plane_scale, ix->ws, 1, pick_perm(nblk), 1, 1.0, ix->progress, st, ix->sm_count));
+  for (int64_t qi = 0; qi < nq; ++qi)  // rows of the [nq, cap] buffer -> [nq, nrows]
+    if (nrows == cap) { CMX_TRY(launch_decode_keys(ix->ws.cand, nq * (int64_t)cap, scores_out, rows_out, st)); break; }
+    else CMX_TRY(launch_decode_keys(ix->ws.cand + qi * cap, nrows, scores_out + qi * nrows, rows_out + qi * nrows, st));
+  CMX_CUDA(cudaMemcpyAsync(margin_out, ix->margin_buf, (size_t)nq * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CMX_CUDA(cudaStreamSynchronize(st));
   return CMX_OK;
 }
 CMX_API uint64_t cmx_debug_block_perm(int64_t nblk) { return pick_perm(nblk); }

@@ -50,9 +50,14 @@ extern int g_profiling;
   } while (0)
 
 // ---- candidate keys ---------------------------------------------------------
-// A candidate is one 64-bit key: high word = score mapped to an unsigned that
-// orders like the float, low word = ~row, so that a DESCENDING sort of keys
-// yields score descending, row ascending.  key 0 is below every real candidate.
+// A candidate is one 64-bit key: high word = score mapped to an unsigned that orders like the
+// float; low word = bit 31 "score is approximate" | 31 bits of (0x7fffffff - row).  A
+// DESCENDING sort of keys with equal flags yields score descending, row ascending.  The flag is
+// set by the scoring kernels (fp16 one-pass scores of the rescore precision) and cleared once a
+// key carries the exact fp32 score (prescore_kernel / rescore_kernel): selection may mix both
+// kinds -- every key's score is within eps(q) of the exact one, which is all the margin proof
+// of DESIGN.md 4b needs -- and the final lists hold exact keys only.  Rows are < 2^31 per shard.
+// key 0 is below every real candidate.
 __host__ __device__ __forceinline__ uint32_t f32_to_ordered(float f) {
 #ifdef __CUDA_ARCH__
   uint32_t b = __float_as_uint(f);
@@ -69,11 +74,18 @@ __host__ __device__ __forceinline__ float ordered_to_f32(uint32_t o) {
   union { float f; uint32_t u; } c; c.u = b; return c.f;
 #endif
 }
+constexpr uint32_t CMX_KEY_APPROX = 0x80000000u;
 __host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
-  return ((uint64_t)f32_to_ordered(score) << 32) | (uint64_t)(0xffffffffu - row);
+  return ((uint64_t)f32_to_ordered(score) << 32) | (uint64_t)(CMX_KEY_APPROX | (0x7fffffffu - row));
 }
+__host__ __device__ __forceinline__ uint64_t make_key_exact(float score, uint32_t row) {
+  return ((uint64_t)f32_to_ordered(score) << 32) | (uint64_t)(0x7fffffffu - row);
+}
+// smallest key carrying `score` (every real key with that score compares >= it)
+__host__ __device__ __forceinline__ uint64_t make_key_floor(float score) { return (uint64_t)f32_to_ordered(score) << 32; }
 __host__ __device__ __forceinline__ float key_score(uint64_t k) { return ordered_to_f32((uint32_t)(k >> 32)); }
-__host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return 0xffffffffu - (uint32_t)(k & 0xffffffffu); }
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return 0x7fffffffu - ((uint32_t)k & 0x7fffffffu); }
+__host__ __device__ __forceinline__ bool key_is_exact(uint64_t k) { return ((uint32_t)k & CMX_KEY_APPROX) == 0u; }
 
 #define CMX_NEG_PAD (-3.402823466e+38f) /* FAISS pads IP results with lowest float */
 
@@ -84,6 +96,16 @@ __host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return 0xffff
 constexpr unsigned CMX_OVF_BUFFER = 1u;  // more survivors than a candidate buffer holds (row order / bad guess)
 constexpr unsigned CMX_OVF_BAND = 2u;    // rescore mode: the margin band of some query outgrew cap/2
 constexpr unsigned CMX_OVF_SPEC = 4u;    // a speculative threshold was not cleared by the k-th best
+constexpr unsigned CMX_FLAG_NO_TWO_PHASE = 0x100u;  // sharded search: this shard cannot run the one-pass arithmetic
+
+// ---- NVTX ranges (visible in nsys / ncu --nvtx; no-ops without a profiler attached) ------------
+struct NvtxRange {
+  explicit NvtxRange(const char* name);
+  ~NvtxRange();
+};
+#define CMX_NVTX_CAT2(a, b) a##b
+#define CMX_NVTX_CAT(a, b) CMX_NVTX_CAT2(a, b)
+#define CMX_NVTX(name) cmx::NvtxRange CMX_NVTX_CAT(_nvtx_, __LINE__)(name)
 
 struct SearchWs {
   float* tau = nullptr;        // [nq_pad] running k-th best score per query (filter threshold)
@@ -92,12 +114,19 @@ struct SearchWs {
   uint32_t* overflow = nullptr;// [1] set when some query's buffer overflowed
   float* margin = nullptr;     // [nq_pad] rescore mode: 2*eps(q), the slack kept below the k-th best
                                // APPROXIMATE score so that the exact top-k is provably contained; else 0
-  float* spec = nullptr;       // [nq_pad] speculative threshold in force for the last slab (lowest-float = none)
+  float* spec = nullptr;       // [nq_pad] speculative threshold in force for the slab being scored (lowest-float = none)
+  float* est = nullptr;        // [nq_pad] rescore mode: candidates scoring at least this are prescored (lowest-float = none)
   int cap = 0;
   int64_t nq_cap = 0;
 };
 
 // ---- kernels (launchers return CMX codes) -------------------------------------
+constexpr int kMixMaxAlphas = 32;
+struct MixParams {
+  float w1[kMixMaxAlphas], w2[kMixMaxAlphas];
+  int mode[kMixMaxAlphas];
+};
+// w1 / w2 / mode are HOST arrays [nA] (passed to the kernel by value; asynchronous)
 int launch_mix_normalize(const float* P, const float* S, int64_t nq, int d, const float* w1,
                          const float* w2, const int* mode, int nA, float* out, uint8_t* flags,
                          cudaStream_t st);
@@ -115,8 +144,16 @@ int launch_row_norm_max(const float* x, int64_t rows, int d, uint32_t* max_bits,
 int launch_row_resid_max(const float* x, const __half* hi, int64_t rows, int d, int d_pad, float inv_scale,
                          uint32_t* max_bits, cudaStream_t st);
 // margin[q] = 2 eps(q), eps(q) = ||q - qh|| xmax + (||q|| + ||q - qh||) xres + gamma ||q|| xmax
+// bounds_dev (may be NULL): {xmax, xres} over all shards on the device; the larger of each pair is used
 int launch_query_margin(const float* Q, const __half* Qhi, int64_t nq, int d, int d_pad, const float* q_scale,
-                        float xmax, float xres, float gamma, float* margin, cudaStream_t st);
+                        float xmax, float xres, const float* bounds_dev, float gamma, float* margin, cudaStream_t st);
+// small asynchronous plumbing of the sharded search (prologue.cu)
+int launch_store2(float* out2, float a, float b, cudaStream_t st);
+int launch_fill_f32(float* out, int64_t n, float v, cudaStream_t st);
+int launch_publish_flag(const uint32_t* overflow, uint32_t extra, uint32_t* flag_out, cudaStream_t st);
+int launch_max_bounds(const float* const* parts, int nparts, float* out2, cudaStream_t st);
+int launch_peer_broadcast(const void* src, void* const* dsts, int ndst, int64_t bytes, cudaStream_t st);
+int launch_decode_keys(const uint64_t* keys, int64_t n, float* scores, int64_t* rows, cudaStream_t st);
 
 int launch_stream_score(const float* X, int64_t row0, int64_t nrows, int d, const float* Q,
                         int nq, const SearchWs& ws, int64_t q0, int dense, int64_t dense_row0,
@@ -145,8 +182,17 @@ int launch_set_counts(const SearchWs& ws, int64_t nq, uint32_t value, cudaStream
 // spec_rank > 0: additionally publish the speculative threshold of the remaining corpus (the
 // spec_rank-th best score so far, minus the margin); verify = 1: the slab just compacted ran under a
 // speculative threshold -- flag `overflow` for any query whose k-th best does not clear it
+// est_rank > 0: also publish ws.est = the est_rank-th best score so far (prescore_kernel's threshold)
 int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float* D, int64_t* I,
-                   int64_t id_base, cudaStream_t st, int spec_rank = 0, int verify = 0);
+                   int64_t id_base, cudaStream_t st, int spec_rank = 0, int verify = 0, int est_rank = 0);
+// snap[q] = cnt[q] (taken between two scoring launches of one slab)
+int launch_snapshot_counts(const SearchWs& ws, int64_t nq, uint32_t* snap, cudaStream_t st);
+// exact fp32 scores, in place, for the candidates in buffer positions [lo[q], hi[q]) (lo == NULL: from 0)
+// that reach ws.est[q]; meant to run on a second stream beside the scoring kernel
+constexpr int kPrescoreMaxSmem = 16 * 1024;  // the query copy must fit next to the resident scoring CTA
+int prescore_smem_bytes(int d);
+int launch_prescore(const float* X, int d, const float* Q, const SearchWs& ws, int64_t nq, const uint32_t* lo,
+                    const uint32_t* hi, cudaStream_t st);
 // rescore mode: exact fp32 scores of every surviving candidate from the fp32 row store, then
 // the exact top-k (score desc, row asc) -> D, I
 struct RescoreCut {
@@ -155,8 +201,9 @@ struct RescoreCut {
 };
 int launch_kth_approx(const SearchWs& ws, int64_t nq, float* out, cudaStream_t st);
 int launch_export_scores(const SearchWs& ws, int64_t nq, int k, float* out, cudaStream_t st);
+// flags (may be NULL): per-shard status words, OR-ed into *flag_any by block 0
 int launch_union_kth(const float* const* parts, int nparts, int k, int64_t q0, int64_t q1, float* const* outs, int nouts,
-                     cudaStream_t st);
+                     const uint32_t* const* flags, int nflags, uint32_t* flag_any, cudaStream_t st);
 int launch_rescore(const float* X, int d, const float* Q, const SearchWs& ws, int64_t nq, int k, float* D,
                    int64_t* I, int64_t id_base, const RescoreCut& cut, cudaStream_t st);
 int launch_merge(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,

@@ -18,11 +18,11 @@ __device__ __forceinline__ bool is_finite_f(float v) {
 
 // mode[a]: bits 0-1: 0 = mix, 1 = copy primary, 2 = copy secondary;
 //          bits 4-5: fallback row on non-finite output (1 = primary, 2 = secondary)
+// The weights travel as kernel arguments (MixParams, up to 32 alphas per launch): nothing is
+// staged through device memory, so the launch needs no host synchronisation.
 __global__ void __launch_bounds__(256)
 mix_normalize_kernel(const float* __restrict__ P, const float* __restrict__ S, int64_t nq, int d,
-                     const float* __restrict__ w1s, const float* __restrict__ w2s,
-                     const int* __restrict__ modes, int nA, float* __restrict__ out,
-                     uint8_t* __restrict__ flags) {
+                     const MixParams mp, int nA, float* __restrict__ out, uint8_t* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (int64_t)nA * nq) return;
@@ -31,13 +31,13 @@ mix_normalize_kernel(const float* __restrict__ P, const float* __restrict__ S, i
   const float* p = P + q * d;
   const float* s = S + q * d;
   float* o = out + row * d;
-  const int mode = modes[a];
+  const int mode = mp.mode[a];
   const int sel = mode & 3;
   uint8_t flag = 0;
   const bool vec = (d & 3) == 0;
 
   if (sel == 0) {
-    const float w1 = w1s[a], w2 = w2s[a];
+    const float w1 = mp.w1[a], w2 = mp.w2[a];
     float ss = 0.f;
     if (vec) {
       const float4* p4 = reinterpret_cast<const float4*>(p);
@@ -104,12 +104,18 @@ mix_normalize_kernel(const float* __restrict__ P, const float* __restrict__ S, i
 int launch_mix_normalize(const float* P, const float* S, int64_t nq, int d, const float* w1,
                          const float* w2, const int* mode, int nA, float* out, uint8_t* flags,
                          cudaStream_t st) {
-  const int64_t rows = (int64_t)nA * nq;
-  if (rows == 0) return CMX_OK;
+  if (nq == 0) return CMX_OK;
   const int warps = 8;
-  const int64_t blocks = (rows + warps - 1) / warps;
-  mix_normalize_kernel<<<(unsigned)blocks, warps * 32, 0, st>>>(P, S, nq, d, w1, w2, mode, nA, out, flags);
-  CMX_LAUNCHED();
+  for (int a0 = 0; a0 < nA; a0 += kMixMaxAlphas) {
+    const int na = nA - a0 < kMixMaxAlphas ? nA - a0 : kMixMaxAlphas;
+    MixParams mp;
+    for (int a = 0; a < na; ++a) { mp.w1[a] = w1[a0 + a]; mp.w2[a] = w2[a0 + a]; mp.mode[a] = mode[a0 + a]; }
+    const int64_t rows = (int64_t)na * nq;
+    const int64_t blocks = (rows + warps - 1) / warps;
+    mix_normalize_kernel<<<(unsigned)blocks, warps * 32, 0, st>>>(P, S, nq, d, mp, na, out + (int64_t)a0 * nq * d,
+                                                                  flags ? flags + (int64_t)a0 * nq : nullptr);
+    CMX_LAUNCHED();
+  }
   return CMX_OK;
 }
 
@@ -168,7 +174,7 @@ int launch_scale_from_absmax(const uint32_t* absmax_bits, float* scale_out, cuda
 float host_scale_for_absmax_bits(uint32_t bits) { return scale_for_absmax_bits(bits); }
 
 // ---- row norms (rescore mode error bound) ----------------------------------------
-// one warp per row; rows with a non-finite norm are ignored
+// one warp per row; rows holding inf / NaN elements are ignored
 __global__ void __launch_bounds__(256)
 row_norm_max_kernel(const float* __restrict__ x, int64_t rows, int d, uint32_t* __restrict__ max_bits) {
   const int lane = threadIdx.x & 31;
@@ -177,10 +183,15 @@ row_norm_max_kernel(const float* __restrict__ x, int64_t rows, int d, uint32_t* 
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
     const float* row = x + r * d;
     float ss = 0.f;
-    for (int i = lane; i < d; i += 32) { const float v = row[i]; ss = fmaf(v, v, ss); }
+    bool finite = true;
+    for (int i = lane; i < d; i += 32) { const float v = row[i]; finite &= is_finite_f(v); ss = fmaf(v, v, ss); }
     ss = warp_sum(ss);
+    finite = __all_sync(0xffffffffu, finite);
     const float nrm = sqrtf(ss);
     if (is_finite_f(nrm)) best = fmaxf(best, nrm);
+    // a FINITE row whose fp32 sum of squares overflows (||x|| > 1.8e19): the error bound of the
+    // one-pass scorer cannot be stated in fp32 -- report +inf, the index then uses split precision
+    else if (finite) best = __int_as_float(0x7f800000);
   }
   if (lane == 0 && best > 0.f) atomicMax(max_bits, __float_as_uint(best));
 }
@@ -235,14 +246,18 @@ int launch_row_resid_max(const float* x, const __half* hi, int64_t rows, int d, 
 // bounded by 2^-11 ||.||: typical fp16 rounding loses ~0.4 of the worst case.
 __global__ void __launch_bounds__(256)
 query_margin_kernel(const float* __restrict__ Q, const __half* __restrict__ Qhi, int64_t nq, int d, int d_pad,
-                    const float* __restrict__ q_scale, float xmax, float xres, float gamma,
-                    float* __restrict__ margin) {
+                    const float* __restrict__ q_scale, float xmax, float xres, const float* __restrict__ bounds,
+                    float gamma, float* __restrict__ margin) {
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq) return;
   const float* row = Q + q * d;
   const __half* hrow = Qhi + q * d_pad;
   const float inv_scale = q_scale[1];
+  if (bounds != nullptr) {  // sharded search: corpus maxima over ALL shards, reduced on the device
+    xmax = fmaxf(xmax, bounds[0]);
+    xres = fmaxf(xres, bounds[1]);
+  }
   float ss = 0.f, rr = 0.f;
   for (int i = lane; i < d; i += 32) {
     const float v = row[i];
@@ -261,9 +276,9 @@ query_margin_kernel(const float* __restrict__ Q, const __half* __restrict__ Qhi,
 }
 
 int launch_query_margin(const float* Q, const __half* Qhi, int64_t nq, int d, int d_pad, const float* q_scale,
-                        float xmax, float xres, float gamma, float* margin, cudaStream_t st) {
+                        float xmax, float xres, const float* bounds_dev, float gamma, float* margin, cudaStream_t st) {
   if (nq == 0) return CMX_OK;
-  query_margin_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(Q, Qhi, nq, d, d_pad, q_scale, xmax, xres, gamma, margin);
+  query_margin_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(Q, Qhi, nq, d, d_pad, q_scale, xmax, xres, bounds_dev, gamma, margin);
   CMX_LAUNCHED();
   return CMX_OK;
 }
@@ -317,6 +332,97 @@ int launch_split_planes(const float* x, int64_t rows, int d, int d_pad, const fl
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   split_planes_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, rows, d, d_pad, scale_dev, scale_host, hi, lo);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+// ---- small device-side plumbing of the sharded search (all asynchronous) ---------------------------
+__global__ void store2_kernel(float* out, float a, float b) { out[0] = a; out[1] = b; }
+int launch_store2(float* out2, float a, float b, cudaStream_t st) {
+  store2_kernel<<<1, 1, 0, st>>>(out2, a, b);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+__global__ void fill_f32_kernel(float* out, int64_t n, float v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
+}
+int launch_fill_f32(float* out, int64_t n, float v, cudaStream_t st) {
+  if (n <= 0) return CMX_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fill_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(out, n, v);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+// flag_out[0] = (overflow ? overflow[0] : 0) | extra  -- the shard's status word of this step
+__global__ void publish_flag_kernel(const uint32_t* overflow, uint32_t extra, uint32_t* flag_out) {
+  flag_out[0] = (overflow ? overflow[0] : 0u) | extra;
+}
+int launch_publish_flag(const uint32_t* overflow, uint32_t extra, uint32_t* flag_out, cudaStream_t st) {
+  publish_flag_kernel<<<1, 1, 0, st>>>(overflow, extra, flag_out);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+// out2 = element-wise max over the shards' {max row norm, max residual norm} (peer reads)
+struct BoundsArgs { const float* parts[CMX_MAX_PEERS]; };
+__global__ void max_bounds_kernel(const BoundsArgs a, int nparts, float* out2) {
+  float x = 0.f, r = 0.f;
+  for (int g = 0; g < nparts; ++g) {
+    // NaN-safe: a non-finite bound must survive the reduction (the margins then become non-finite,
+    // everything passes the filter, the buffers overflow and the step falls back)
+    const float xg = a.parts[g][0], rg = a.parts[g][1];
+    x = (xg != xg || xg > x) ? xg : x;
+    r = (rg != rg || rg > r) ? rg : r;
+  }
+  out2[0] = x;
+  out2[1] = r;
+}
+int launch_max_bounds(const float* const* parts, int nparts, float* out2, cudaStream_t st) {
+  BoundsArgs a;
+  for (int g = 0; g < nparts; ++g) a.parts[g] = parts[g];
+  max_bounds_kernel<<<1, 1, 0, st>>>(a, nparts, out2);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+// one read of src, one 128-bit store into each destination (peer memory over NVLink)
+struct BcastArgs { uint4* dst[CMX_MAX_PEERS]; };
+__global__ void __launch_bounds__(256) peer_broadcast_kernel(const uint4* __restrict__ src, const BcastArgs a, int ndst, int64_t n16) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = src[i];
+    for (int g = 0; g < ndst; ++g) a.dst[g][i] = v;
+  }
+}
+int launch_peer_broadcast(const void* src, void* const* dsts, int ndst, int64_t bytes, cudaStream_t st) {
+  BcastArgs a;
+  for (int g = 0; g < ndst; ++g) a.dst[g] = reinterpret_cast<uint4*>(dsts[g]);
+  const int64_t n16 = bytes / 16;
+  int64_t blocks = (n16 + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  peer_broadcast_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), a, ndst, n16);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+// test hook: candidate keys -> (score, row)
+__global__ void decode_keys_kernel(const uint64_t* __restrict__ keys, int64_t n, float* __restrict__ scores, int64_t* __restrict__ rows) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t k = keys[i];
+    scores[i] = k ? key_score(k) : CMX_NEG_PAD;
+    rows[i] = k ? (int64_t)key_row(k) : -1;
+  }
+}
+int launch_decode_keys(const uint64_t* keys, int64_t n, float* scores, int64_t* rows, cudaStream_t st) {
+  if (n <= 0) return CMX_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  decode_keys_kernel<<<(unsigned)blocks, 256, 0, st>>>(keys, n, scores, rows);
   CMX_LAUNCHED();
   return CMX_OK;
 }

@@ -184,16 +184,26 @@ __device__ int block_partition(const uint64_t* keys, int n, uint64_t kth, uint64
   return (int)sh.count;
 }
 
-// One CTA per query.  Keeps the query's best k candidates at the front of its buffer and
-// sets tau to the k-th best score.  Because later corpus slabs only hold larger row
-// numbers, "score > tau" (strict) is then an exact filter under the (score desc, row
-// asc) order.  final_pass additionally sorts the survivors and writes D / I.
+// One CTA per query.  Keeps the query's best k candidates (plus, in rescore mode, the margin
+// band below them) at the front of its buffer and sets the filter threshold tau for the next
+// slab.  The tensor kernels visit the corpus in a permuted block order, so rows of later slabs
+// are NOT larger than the ones seen: the filter is exact because of the margin (rescore mode:
+// everything within 2 eps of the running k-th best approximate score is kept); with
+// a zero margin (split precision, stream path in file order) the strict "score > tau" admits no
+// row that ties the current k-th score, which at an exact tie across the k-th place yields one
+// of the tied rows, not necessarily the smallest id ("Ties").
+// final_pass additionally sorts the survivors and writes D / I.
+// spec_rank / est_rank > 0 publish two order statistics of the survivors for the NEXT slab:
+//   spec[q] (and tau[q]) = score of rank spec_rank - margin: the speculative filter threshold
+//   est[q]               = score of rank est_rank: candidates at or above it will very likely be in
+//                          the final top-k, prescore_kernel gives them exact scores while the next
+//                          slab is still being scored
 // dynamic smem: cap keys, then next_pow2(k) keys for the final sort
 __global__ void __launch_bounds__(kSelThreads)
 compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* __restrict__ tau,
-               uint32_t* __restrict__ overflow, const float* __restrict__ margin, float* __restrict__ spec, int cap,
-               int k, int final_pass, int spec_rank, int verify, float* __restrict__ D, int64_t* __restrict__ I,
-               int64_t id_base) {
+               uint32_t* __restrict__ overflow, const float* __restrict__ margin, float* __restrict__ spec,
+               float* __restrict__ est, int cap, int k, int final_pass, int spec_rank, int est_rank, int verify,
+               float* __restrict__ D, int64_t* __restrict__ I, int64_t id_base) {
   extern __shared__ __align__(16) uint64_t keys[];
   __shared__ SelectShared sh;
   const int64_t q = blockIdx.x;
@@ -210,6 +220,7 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
     atomicOr(overflow, CMX_OVF_SPEC);
     spec[q] = CMX_NEG_PAD;
   }
+  if (est && est_rank > 0 && threadIdx.x == 0) est[q] = CMX_NEG_PAD;  // no estimate unless set below
   if (!final_pass && n <= k) return;  // nothing to drop yet; tau stays
   uint64_t* buf = cand + q * (int64_t)cap;
   for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = buf[i];
@@ -226,22 +237,34 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
     float new_tau = key_score(kth);
     if (m > 0.f && kth != 0ull) {
       new_tau = key_score(kth) - m;
-      thr = make_key(new_tau, 0xffffffffu);  // smallest key carrying that score
+      thr = make_key_floor(new_tau);
     }
     if (spec_old > CMX_NEG_PAD && threadIdx.x == 0) {
       const bool cleared = kth != 0ull && (m > 0.f ? key_score(kth) >= spec_old + m : key_score(kth) > spec_old);
       if (!cleared) atomicOr(overflow, CMX_OVF_SPEC);
       spec[q] = CMX_NEG_PAD;
     }
-    float spec_tau = CMX_NEG_PAD;
-    if (spec_rank > 0 && spec_rank < k && kth != 0ull) {
-      // the spec_rank-th best so far estimates (with a 3x safety factor, plan_slabs) where the k-th
-      // best of the WHOLE corpus will be; `keys` still holds all n candidates
-      __syncthreads();
-      const uint64_t rth = block_kth_largest(keys, n, spec_rank, sh);
-      if (rth != 0ull) spec_tau = key_score(rth) - m;
-    }
     kk = block_partition(keys, n, thr, final_pass ? top : buf, sh);
+    float spec_tau = CMX_NEG_PAD, est_tau = CMX_NEG_PAD;
+    const bool want_spec = spec_rank > 0 && spec_rank < k;
+    const bool want_est = est != nullptr && est_rank > 0 && est_rank < k;
+    if (!final_pass && kth != 0ull && (want_spec || want_est)) {
+      // order statistics of the survivors only (kk << n after a large slab): reload them compacted
+      __syncthreads();
+      for (int i = threadIdx.x; i < kk; i += blockDim.x) keys[i] = buf[i];
+      __syncthreads();
+      if (want_spec) {
+        // the spec_rank-th best so far estimates (with a 3x safety factor, plan_slabs) where the k-th
+        // best of the rows up to the end of the next slab will be
+        const uint64_t rth = block_kth_largest(keys, kk, spec_rank, sh);
+        if (rth != 0ull) spec_tau = key_score(rth) - m;
+        __syncthreads();
+      }
+      if (want_est) {
+        const uint64_t eth = block_kth_largest(keys, kk, est_rank, sh);
+        if (eth != 0ull) est_tau = key_score(eth);
+      }
+    }
     if (threadIdx.x == 0) {
       cnt[q] = (uint32_t)kk;
       if (kth != 0ull) tau[q] = new_tau;
@@ -249,6 +272,7 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
         tau[q] = spec_tau;
         spec[q] = spec_tau;
       }
+      if (want_est) est[q] = est_tau;
       // rescore mode: the k best plus their margin band must fit half of the buffer (the other half
       // is the room the slab plan counts on, and rescore_kernel holds at most cap/2 keys)
       if (m > 0.f && kk > cap / 2) atomicOr(overflow, CMX_OVF_BAND);
@@ -275,25 +299,140 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
   }
 }
 
+// ---- exact fp32 score of one (query, row) pair: THE arithmetic of the rescore precision -------
+// One warp per row, lane l takes the float4 groups l, l+32, ...: an fp32 FMA chain over the lane's
+// elements (x, y, z, w in order), then a xor-shuffle tree.  prescore_kernel and rescore_kernel
+// both use these two functions, so a (query, row) score is bit-identical wherever and whenever it
+// is computed (1 GPU == G GPUs, prescored == rescored).  qv: the query in shared memory.
+__device__ __forceinline__ float warp_reduce_sum(float acc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+__device__ __forceinline__ void exact_dot_pair(const float* __restrict__ x0, const float* __restrict__ x1,
+                                               const float* qv, int d, int lane, float& out0, float& out1) {
+  float acc0 = 0.f, acc1 = 0.f;
+  if ((d & 3) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(x0);
+    const float4* b4 = reinterpret_cast<const float4*>(x1);
+    const float4* q4 = reinterpret_cast<const float4*>(qv);
+#pragma unroll 4
+    for (int j = lane; j < (d >> 2); j += 32) {
+      const float4 a = a4[j], b = b4[j], c = q4[j];
+      acc0 = fmaf(a.x, c.x, acc0); acc0 = fmaf(a.y, c.y, acc0); acc0 = fmaf(a.z, c.z, acc0); acc0 = fmaf(a.w, c.w, acc0);
+      acc1 = fmaf(b.x, c.x, acc1); acc1 = fmaf(b.y, c.y, acc1); acc1 = fmaf(b.z, c.z, acc1); acc1 = fmaf(b.w, c.w, acc1);
+    }
+  } else {
+    // same element -> lane assignment as the vector loop: group j = elements 4j .. 4j+3
+    for (int j = lane; 4 * j < d; j += 32) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * j + e;
+        if (i < d) {
+          const float c = qv[i];
+          acc0 = fmaf(x0[i], c, acc0);
+          acc1 = fmaf(x1[i], c, acc1);
+        }
+      }
+    }
+  }
+  out0 = warp_reduce_sum(acc0);
+  out1 = warp_reduce_sum(acc1);
+}
+
+// ---- exact scores ahead of time --------------------------------------------------------------
+// While the LAST slab of a rescore-mode search is being scored (in several launches), this kernel
+// runs on a second stream next to the scoring kernel (one small CTA per query: 4 warps, the query
+// in shared memory -- it fits beside the persistent scoring CTA) and replaces, in place, the
+// approximate score of every candidate in buffer positions [lo[q], hi[q]) whose score reaches
+// est[q] by its exact fp32 score (key flag cleared).  Those are the candidates that will very
+// likely survive to the end, so rescore_kernel finds most of its work done: the 4 KB row gathers
+// (HBM-bound, 5-6 ms at C2 when done after the last tile) hide behind tensor-bound scoring that
+// uses 3 % of the DRAM bandwidth.  Positions below hi[q] are final (the scoring launch that
+// appended them has completed: hi is a snapshot taken between launches), positions being
+// appended concurrently are >= hi[q].
+constexpr int kPreThreads = 128;
+
+__global__ void __launch_bounds__(kPreThreads)
+prescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, uint64_t* __restrict__ cand,
+                const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi, const float* __restrict__ est, int cap) {
+  extern __shared__ __align__(16) float qv_pre[];
+  const int64_t q = blockIdx.x;
+  const uint32_t a = lo ? min(lo[q], (uint32_t)cap) : 0u;
+  const uint32_t b = min(hi[q], (uint32_t)cap);
+  const float e = est[q];
+  if (a >= b || !(e > CMX_NEG_PAD)) return;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) qv_pre[i] = Q[q * (int64_t)d + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  uint64_t* buf = cand + q * (int64_t)cap;
+  for (uint32_t base = a + (uint32_t)warp * 32u; base < b; base += (uint32_t)nwarps * 32u) {
+    const uint32_t i = base + (uint32_t)lane;
+    const uint64_t key = i < b ? buf[i] : 0ull;
+    const bool want = key != 0ull && !key_is_exact(key) && key_score(key) >= e;
+    uint32_t mask = __ballot_sync(0xffffffffu, want);
+    while (mask) {
+      const int j0 = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      int j1 = j0;
+      if (mask) { j1 = __ffs(mask) - 1; mask &= mask - 1u; }
+      const uint32_t row0 = key_row(__shfl_sync(0xffffffffu, key, j0));
+      const uint32_t row1 = key_row(__shfl_sync(0xffffffffu, key, j1));
+      float s0, s1;
+      exact_dot_pair(X + (int64_t)row0 * d, X + (int64_t)row1 * d, qv_pre, d, lane, s0, s1);
+      if (lane == 0) {
+        buf[base + j0] = s0 > CMX_NEG_PAD ? make_key_exact(s0, row0) : 0ull;
+        if (j1 != j0) buf[base + j1] = s1 > CMX_NEG_PAD ? make_key_exact(s1, row1) : 0ull;
+      }
+    }
+  }
+}
+
+__global__ void snapshot_counts_kernel(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ snap, int64_t nq) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) snap[i] = cnt[i];
+}
+
+int launch_snapshot_counts(const SearchWs& ws, int64_t nq, uint32_t* snap, cudaStream_t st) {
+  if (nq == 0) return CMX_OK;
+  snapshot_counts_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(ws.cnt, snap, nq);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
+int prescore_smem_bytes(int d) { return (d * (int)sizeof(float) + 15) / 16 * 16; }
+
+int launch_prescore(const float* X, int d, const float* Q, const SearchWs& ws, int64_t nq, const uint32_t* lo,
+                    const uint32_t* hi, cudaStream_t st) {
+  if (nq == 0) return CMX_OK;
+  const int smem = prescore_smem_bytes(d);
+  CMX_CHECK(smem <= kPrescoreMaxSmem, "prescore: d=%d too large", d);
+  // same shared-memory carveout as the persistent scoring CTA it has to run beside
+  static bool configured = false;
+  if (!configured) {
+    CMX_CUDA(cudaFuncSetAttribute(prescore_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
+  prescore_kernel<<<(unsigned)nq, kPreThreads, smem, st>>>(X, d, Q, ws.cand, lo, hi, ws.est, ws.cap);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
 // Rescore mode, last step.  One CTA per query: every surviving candidate (a superset of the
 // exact top-k, selected on approximate fp16 tensor-core scores) gets its EXACT fp32 score
 // from the fp32 row store, then the exact top-k under (score desc, row asc) is selected,
 // sorted and written to D / I.
 //  1. the candidates that pass the cut are gathered into shared memory (sharded search: the
 //     cut is the GLOBAL k-th best approximate score minus the margin, so a shard keeps ~1/G
-//     of its local band);
-//  2. one warp per TWO candidate rows at a time (16 independent 128-bit loads in flight per
-//     lane), fp32 FMA chain + shuffle reduction -- deterministic for a given (query, row);
+//     of its local band): the ones still carrying an approximate score at the front, the ones
+//     prescore_kernel already made exact at the back;
+//  2. one warp per TWO approximate candidates at a time (16 independent 128-bit loads in flight
+//     per lane), exact_dot_pair -- deterministic for a given (query, row);
 //  3. radix select + bitonic sort of the k best exact keys.
 // dynamic smem: cap/2 keys | next_pow2(k) keys | d floats (the query): 44 KB at k = 1000,
 // d = 1024, so four 512-thread CTAs share an SM and the row gathers of one hide the select
 // phase of another.
-__device__ __forceinline__ float dot_row_pair_reduce(float acc) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  return acc;
-}
-
 __global__ void __launch_bounds__(kSelThreads)
 rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, const uint64_t* __restrict__ cand,
                const uint32_t* __restrict__ cnt, uint32_t* __restrict__ overflow, const float* __restrict__ margin,
@@ -301,14 +440,15 @@ rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, 
                int64_t id_base) {
   extern __shared__ __align__(16) uint64_t keys[];
   __shared__ SelectShared sh;
-  __shared__ uint32_t s_m;
+  __shared__ uint32_t s_ma, s_me;
   const int half = cap >> 1;
   uint64_t* top = keys + half;
   float* qv = reinterpret_cast<float*>(top + topn);
   const int64_t q = blockIdx.x;
   const uint32_t n_raw = cnt[q];
   if (threadIdx.x == 0) {
-    s_m = 0;
+    s_ma = 0;
+    s_me = 0;
     if (n_raw > (uint32_t)cap) atomicOr(overflow, CMX_OVF_BUFFER);
   }
   const int n = (int)min(n_raw, (uint32_t)cap);
@@ -328,51 +468,56 @@ rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, 
     const int i = base + threadIdx.x;
     const uint64_t key = i < n ? buf[i] : 0ull;
     const bool valid = key != 0ull && key_score(key) >= lowest;
-    const uint32_t ballot = __ballot_sync(0xffffffffu, valid);
-    uint32_t wbase = 0;
-    if (lane == 0 && ballot) wbase = atomicAdd(&s_m, (uint32_t)__popc(ballot));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    const uint32_t pos = wbase + __popc(ballot & ((1u << lane) - 1u));
-    if (valid && pos < (uint32_t)half) keys[pos] = key;
+    const bool ex = valid && key_is_exact(key);
+    const bool ap = valid && !ex;
+    const uint32_t b_ap = __ballot_sync(0xffffffffu, ap), b_ex = __ballot_sync(0xffffffffu, ex);
+    uint32_t base_ap = 0, base_ex = 0;
+    if (lane == 0) {
+      if (b_ap) base_ap = atomicAdd(&s_ma, (uint32_t)__popc(b_ap));
+      if (b_ex) base_ex = atomicAdd(&s_me, (uint32_t)__popc(b_ex));
+    }
+    base_ap = __shfl_sync(0xffffffffu, base_ap, 0);
+    base_ex = __shfl_sync(0xffffffffu, base_ex, 0);
+    const uint32_t lt = (1u << lane) - 1u;
+    if (ap) {
+      const uint32_t pos = base_ap + __popc(b_ap & lt);
+      if (pos < (uint32_t)half) keys[pos] = key;
+    } else if (ex) {
+      const uint32_t pos = base_ex + __popc(b_ex & lt);  // from the back: half-1, half-2, ...
+      if (pos < (uint32_t)half) keys[half - 1 - (int)pos] = key;
+    }
   }
   __syncthreads();
-  if (s_m > (uint32_t)half && threadIdx.x == 0) atomicOr(overflow, CMX_OVF_BAND);  // compact_kernel flags this first
-  const int m = (int)min(s_m, (uint32_t)half);
-  // 2. exact scores, two rows per warp and iteration
-  const bool vec = (d & 3) == 0;
-  for (int i = 2 * warp; i < m; i += 2 * nwarps) {
-    const bool two = i + 1 < m;
+  // fronts and backs collide when more than cap/2 keys pass: compact_kernel flags that first
+  const bool band_ovf = s_ma + s_me > (uint32_t)half;
+  if (band_ovf && threadIdx.x == 0) atomicOr(overflow, CMX_OVF_BAND);
+  const int ma = (int)min(s_ma, (uint32_t)half);
+  const int me = band_ovf ? 0 : (int)s_me;
+  // 2. exact scores of the approximate keys, two rows per warp and iteration
+  for (int i = 2 * warp; i < ma; i += 2 * nwarps) {
+    const bool two = i + 1 < ma;
     const uint32_t row0 = key_row(keys[i]);
     const uint32_t row1 = two ? key_row(keys[i + 1]) : row0;
-    const float* x0 = X + (int64_t)row0 * d;
-    const float* x1 = X + (int64_t)row1 * d;
-    float acc0 = 0.f, acc1 = 0.f;
-    if (vec) {
-      const float4* a4 = reinterpret_cast<const float4*>(x0);
-      const float4* b4 = reinterpret_cast<const float4*>(x1);
-      const float4* q4 = reinterpret_cast<const float4*>(qv);
-#pragma unroll 4
-      for (int j = lane; j < (d >> 2); j += 32) {
-        const float4 a = a4[j], b = b4[j], c = q4[j];
-        acc0 = fmaf(a.x, c.x, acc0); acc0 = fmaf(a.y, c.y, acc0); acc0 = fmaf(a.z, c.z, acc0); acc0 = fmaf(a.w, c.w, acc0);
-        acc1 = fmaf(b.x, c.x, acc1); acc1 = fmaf(b.y, c.y, acc1); acc1 = fmaf(b.z, c.z, acc1); acc1 = fmaf(b.w, c.w, acc1);
-      }
-    } else {
-      for (int j = lane; j < d; j += 32) {
-        const float c = qv[j];
-        acc0 = fmaf(x0[j], c, acc0);
-        acc1 = fmaf(x1[j], c, acc1);
-      }
-    }
-    acc0 = dot_row_pair_reduce(acc0);
-    acc1 = dot_row_pair_reduce(acc1);
+    float acc0, acc1;
+    exact_dot_pair(X + (int64_t)row0 * d, X + (int64_t)row1 * d, qv, d, lane, acc0, acc1);
     __syncwarp();
     if (lane == 0) {
-      keys[i] = acc0 > CMX_NEG_PAD ? make_key(acc0, row0) : 0ull;
-      if (two) keys[i + 1] = acc1 > CMX_NEG_PAD ? make_key(acc1, row1) : 0ull;
+      keys[i] = acc0 > CMX_NEG_PAD ? make_key_exact(acc0, row0) : 0ull;
+      if (two) keys[i + 1] = acc1 > CMX_NEG_PAD ? make_key_exact(acc1, row1) : 0ull;
     }
   }
   __syncthreads();
+  // the prescored keys join the list: move the back segment down to [ma, ma + me)
+  // (destination index < source index for every element, rounds in ascending order)
+  for (int j0 = 0; j0 < me; j0 += blockDim.x) {
+    const int j = j0 + threadIdx.x;
+    uint64_t v = 0ull;
+    if (j < me) v = keys[half - me + j];
+    __syncthreads();
+    if (j < me) keys[ma + j] = v;
+    __syncthreads();
+  }
+  const int m = ma + me;
   // 3. exact top-k
   int kk = m;
   if (m > k) {
@@ -405,13 +550,13 @@ static int pow2_at_least(int n) {
 }
 
 int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float* D, int64_t* I,
-                   int64_t id_base, cudaStream_t st, int spec_rank, int verify) {
+                   int64_t id_base, cudaStream_t st, int spec_rank, int verify, int est_rank) {
   if (nq == 0) return CMX_OK;
   const size_t smem = ((size_t)ws.cap + pow2_at_least(k)) * sizeof(uint64_t);
   CMX_CUDA(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  compact_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(ws.cand, ws.cnt, ws.tau, ws.overflow, ws.margin,
-                                                          ws.spec ? ws.spec : nullptr, ws.cap, k, final_pass,
-                                                          ws.spec ? spec_rank : 0, ws.spec ? verify : 0, D, I, id_base);
+  compact_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(ws.cand, ws.cnt, ws.tau, ws.overflow, ws.margin, ws.spec, ws.est,
+                                                          ws.cap, k, final_pass, ws.spec ? spec_rank : 0,
+                                                          ws.est ? est_rank : 0, ws.spec ? verify : 0, D, I, id_base);
   CMX_LAUNCHED();
   return CMX_OK;
 }
@@ -459,15 +604,26 @@ int launch_export_scores(const SearchWs& ws, int64_t nq, int k, float* out, cuda
 
 // GLOBAL k-th best approximate score of queries [q0, q1): the k-th largest of the union of every
 // shard's exported list, read in place (peer memory), written into every shard's kth array.
+// Block 0 also ORs the shards' status words (buffer overflow / cannot run two-phase) into this
+// shard's `flag_any`: every shard reads the same words after the same barrier, so all of them take
+// the same decision at the end of the step -- no host round trip, no collective.
 struct UnionArgs {
   const float* parts[CMX_MAX_PEERS];
   float* outs[CMX_MAX_PEERS];
+  const uint32_t* flags[CMX_MAX_PEERS];
 };
 
 __global__ void __launch_bounds__(kSelThreads)
-union_kth_kernel(const UnionArgs a, int nparts, int nouts, int64_t q0, int k) {
+union_kth_kernel(const UnionArgs a, int nparts, int nouts, int nflags, uint32_t* __restrict__ flag_any, int64_t q0,
+                 int64_t nq_slice, int k) {
   extern __shared__ __align__(16) uint64_t keys[];
   __shared__ SelectShared sh;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && flag_any != nullptr) {
+    uint32_t f = 0;
+    for (int g = 0; g < nflags; ++g) f |= a.flags[g][0];
+    if (f) atomicOr(flag_any, f);
+  }
+  if ((int64_t)blockIdx.x >= nq_slice) return;
   const int64_t q = q0 + blockIdx.x;
   const int n_all = nparts * k;
   for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
@@ -495,17 +651,22 @@ union_kth_kernel(const UnionArgs a, int nparts, int nouts, int64_t q0, int k) {
 }
 
 int launch_union_kth(const float* const* parts, int nparts, int k, int64_t q0, int64_t q1, float* const* outs, int nouts,
-                     cudaStream_t st) {
-  if (q1 <= q0) return CMX_OK;
-  CMX_CHECK(nparts >= 1 && nparts <= CMX_MAX_PEERS && nouts >= 1 && nouts <= CMX_MAX_PEERS, "union_kth: at most %d parts",
-            CMX_MAX_PEERS);
+                     const uint32_t* const* flags, int nflags, uint32_t* flag_any, cudaStream_t st) {
+  const bool have_flags = flags != nullptr && nflags > 0 && flag_any != nullptr;
+  if (q1 <= q0 && !have_flags) return CMX_OK;
+  CMX_CHECK(nparts >= 1 && nparts <= CMX_MAX_PEERS && nouts >= 1 && nouts <= CMX_MAX_PEERS && nflags <= CMX_MAX_PEERS,
+            "union_kth: at most %d parts", CMX_MAX_PEERS);
   const size_t smem = (size_t)nparts * k * sizeof(uint64_t);
   CMX_CHECK(smem <= 200 * 1024, "union_kth: nparts*k = %d too large", nparts * k);
   UnionArgs a;
   for (int g = 0; g < nparts; ++g) a.parts[g] = parts[g];
   for (int o = 0; o < nouts; ++o) a.outs[o] = outs[o];
+  for (int g = 0; g < (have_flags ? nflags : 0); ++g) a.flags[g] = flags[g];
   CMX_CUDA(cudaFuncSetAttribute(union_kth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  union_kth_kernel<<<(unsigned)(q1 - q0), kSelThreads, smem, st>>>(a, nparts, nouts, q0, k);
+  const int64_t nslice = q1 > q0 ? q1 - q0 : 0;
+  const unsigned grid = (unsigned)(nslice > 0 ? nslice : 1);
+  union_kth_kernel<<<grid, kSelThreads, smem, st>>>(a, nparts, nouts, have_flags ? nflags : 0, have_flags ? flag_any : nullptr,
+                                                    q0, nslice, k);
   CMX_LAUNCHED();
   return CMX_OK;
 }
@@ -532,14 +693,43 @@ int launch_rescore(const float* X, int d, const float* Q, const SearchWs& ws, in
 
 // k-way merge: parts are individually sorted (score desc, row asc) and ordered by
 // ascending row range, so (part, position) is the tie-break that reproduces the
-// single-shard order exactly.  dynamic smem: nparts*k keys, then next_pow2(k) keys
-__global__ void __launch_bounds__(kSelThreads)
-merge_kernel(const float* __restrict__ Dp, const int64_t* __restrict__ Ip, int nparts, int64_t nq,
-             int k, float* __restrict__ D, int64_t* __restrict__ I) {
-  extern __shared__ __align__(16) uint64_t keys[];
-  __shared__ SelectShared sh;
-  __shared__ uint32_t s_valid;
-  const int64_t q = blockIdx.x;
+// single-shard order exactly.  dynamic smem: nparts*k keys, then next_pow2(k) keys.
+// Src tells where entry `pos` of part g of query q lives and where the merged row goes:
+// GatheredSrc = parts stacked in one buffer [nparts, nq, k] (after an all_gather),
+// PeerSrc = one pointer per part, each possibly resident on another GPU.
+struct GatheredSrc {
+  const float* Dp;
+  const int64_t* Ip;
+  float* D;
+  int64_t* I;
+  int64_t nq;
+  __device__ __forceinline__ float score(int g, int64_t q, int k, int pos) const { return Dp[((int64_t)g * nq + q) * k + pos]; }
+  __device__ __forceinline__ int64_t id(int g, int64_t q, int k, int pos) const { return Ip[((int64_t)g * nq + q) * k + pos]; }
+  __device__ __forceinline__ void store(int64_t q, int k, int i, float s, int64_t v) const {
+    D[q * k + i] = s;
+    I[q * k + i] = v;
+  }
+};
+
+struct PeerSrc {
+  const float* D[CMX_MAX_PEERS];
+  const int64_t* I[CMX_MAX_PEERS];
+  float* Do[CMX_MAX_PEERS];
+  int64_t* Io[CMX_MAX_PEERS];
+  int nouts;
+  __device__ __forceinline__ float score(int g, int64_t q, int k, int pos) const { return D[g][q * k + pos]; }
+  __device__ __forceinline__ int64_t id(int g, int64_t q, int k, int pos) const { return I[g][q * k + pos]; }
+  __device__ __forceinline__ void store(int64_t q, int k, int i, float s, int64_t v) const {
+    for (int o = 0; o < nouts; ++o) {
+      Do[o][q * k + i] = s;
+      Io[o][q * k + i] = v;
+    }
+  }
+};
+
+template <typename Src>
+__device__ __forceinline__ void merge_query(const Src& src, int nparts, int64_t q, int k, uint64_t* keys, SelectShared& sh,
+                                            uint32_t& s_valid) {
   const int n_all = nparts * k;
   if (threadIdx.x == 0) s_valid = 0;
   __syncthreads();
@@ -552,9 +742,8 @@ merge_kernel(const float* __restrict__ Dp, const int64_t* __restrict__ Ip, int n
       uint64_t key = 0ull;
       if (i < n_all) {
         const int g = i / k, pos = i - g * k;
-        const int64_t src = ((int64_t)g * nq + q) * k + pos;
-        valid = Ip[src] >= 0;
-        if (valid) key = make_key(Dp[src], (uint32_t)i);
+        valid = src.id(g, q, k, pos) >= 0;
+        if (valid) key = make_key(src.score(g, q, k, pos), (uint32_t)i);
       }
       const uint32_t ballot = __ballot_sync(0xffffffffu, valid);
       uint32_t wbase = 0;
@@ -584,83 +773,32 @@ merge_kernel(const float* __restrict__ Dp, const int64_t* __restrict__ Ip, int n
     if (i < kk) {
       const uint32_t src_i = key_row(top[i]);
       const int g = src_i / k, pos = src_i - g * k;
-      const int64_t src = ((int64_t)g * nq + q) * k + pos;
-      s = Dp[src];
-      id = Ip[src];
+      s = src.score(g, q, k, pos);
+      id = src.id(g, q, k, pos);
     }
-    D[q * k + i] = s;
-    I[q * k + i] = id;
+    src.store(q, k, i, s, id);
   }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+merge_kernel(const GatheredSrc src, int nparts, int k) {
+  extern __shared__ __align__(16) uint64_t keys[];
+  __shared__ SelectShared sh;
+  __shared__ uint32_t s_valid;
+  merge_query(src, nparts, (int64_t)blockIdx.x, k, keys, sh, s_valid);
 }
 
 // Fused exchange + merge over peer memory: part g's list lives in GPU g's memory and is read
 // here directly through NVLink peer pointers (no all_gather, no staging copy); the merged
-// rows of queries [q0, q1) are stored into every rank's output buffer (peer stores), so
-// after one cross-rank barrier each rank holds the full result.
-struct MergePeerArgs {
-  const float* D[CMX_MAX_PEERS];
-  const int64_t* I[CMX_MAX_PEERS];
-  float* Do[CMX_MAX_PEERS];
-  int64_t* Io[CMX_MAX_PEERS];
-};
-
+// rows of queries [q0, q1) are stored into every output buffer (peer stores into the ranks'
+// device buffers, or posted PCIe writes into a device-mapped pinned HOST buffer shared by the
+// ranks), so after one cross-rank barrier the full result is in place.
 __global__ void __launch_bounds__(kSelThreads)
-merge_peers_kernel(const MergePeerArgs a, int nparts, int nouts, int64_t q0, int k) {
+merge_peers_kernel(const PeerSrc src, int nparts, int64_t q0, int k) {
   extern __shared__ __align__(16) uint64_t keys[];
   __shared__ SelectShared sh;
   __shared__ uint32_t s_valid;
-  const int64_t q = q0 + blockIdx.x;
-  const int n_all = nparts * k;
-  if (threadIdx.x == 0) s_valid = 0;
-  __syncthreads();
-  {
-    const int lane = threadIdx.x & 31;
-    for (int base = 0; base < n_all; base += blockDim.x) {
-      const int i = base + threadIdx.x;
-      bool valid = false;
-      uint64_t key = 0ull;
-      if (i < n_all) {
-        const int g = i / k, pos = i - g * k;
-        const int64_t src = q * k + pos;
-        valid = a.I[g][src] >= 0;
-        if (valid) key = make_key(a.D[g][src], (uint32_t)i);
-      }
-      const uint32_t ballot = __ballot_sync(0xffffffffu, valid);
-      uint32_t wbase = 0;
-      if (lane == 0 && ballot) wbase = atomicAdd(&s_valid, (uint32_t)__popc(ballot));
-      wbase = __shfl_sync(0xffffffffu, wbase, 0);
-      if (valid) keys[wbase + __popc(ballot & ((1u << lane) - 1u))] = key;
-    }
-  }
-  __syncthreads();
-  const int n = (int)s_valid;
-  uint64_t* top = keys + n_all;
-  int kk = n;
-  if (n > k) {
-    const uint64_t kth = block_kth_largest(keys, n, k, sh);
-    kk = block_partition(keys, n, kth, top, sh);
-  } else {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) top[i] = keys[i];
-    __syncthreads();
-  }
-  const int P = next_pow2(max(kk, 2));
-  for (int i = kk + threadIdx.x; i < P; i += blockDim.x) top[i] = 0ull;
-  __syncthreads();
-  bitonic_sort_desc(top, P);
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    float s = CMX_NEG_PAD;
-    int64_t id = -1;
-    if (i < kk) {
-      const uint32_t src_i = key_row(top[i]);
-      const int g = src_i / k, pos = src_i - g * k;
-      s = a.D[g][q * k + pos];
-      id = a.I[g][q * k + pos];
-    }
-    for (int o = 0; o < nouts; ++o) {
-      a.Do[o][q * k + i] = s;
-      a.Io[o][q * k + i] = id;
-    }
-  }
+  merge_query(src, nparts, q0 + blockIdx.x, k, keys, sh, s_valid);
 }
 
 int launch_merge_peers(const float* const* D_parts, const int64_t* const* I_parts, int nparts, int k,
@@ -674,11 +812,12 @@ int launch_merge_peers(const float* const* D_parts, const int64_t* const* I_part
     set_error("merge: nparts*k = %d too large for one shared-memory selection", nparts * k);
     return CMX_ERR_INVALID;
   }
-  MergePeerArgs a;
+  PeerSrc a;
   for (int g = 0; g < nparts; ++g) { a.D[g] = D_parts[g]; a.I[g] = I_parts[g]; }
   for (int o = 0; o < nouts; ++o) { a.Do[o] = D_outs[o]; a.Io[o] = I_outs[o]; }
+  a.nouts = nouts;
   CMX_CUDA(cudaFuncSetAttribute(merge_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_peers_kernel<<<(unsigned)(q1 - q0), kSelThreads, smem, st>>>(a, nparts, nouts, q0, k);
+  merge_peers_kernel<<<(unsigned)(q1 - q0), kSelThreads, smem, st>>>(a, nparts, q0, k);
   CMX_LAUNCHED();
   return CMX_OK;
 }
@@ -692,7 +831,8 @@ int launch_merge(const float* D_parts, const int64_t* I_parts, int nparts, int64
     return CMX_ERR_INVALID;
   }
   CMX_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(D_parts, I_parts, nparts, nq, k, D, I);
+  GatheredSrc src{D_parts, I_parts, D, I, nq};
+  merge_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(src, nparts, k);
   CMX_LAUNCHED();
   return CMX_OK;
 }

@@ -127,24 +127,57 @@ CMX_API int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int6
                      int io_on_device, int64_t id_base, int path, void* stream);
 
 /* ---- two-phase search for row-sharded indexes (rescore precision, device buffers) -------------
- * A shard that rescored its own k best would do G times the necessary exact work.
- *  1. cmx_search_mixed_begin: fused prologue + approximate pass; writes the shard's k best
- *     APPROXIMATE scores per query to scores_out [nA*nq, k] (order arbitrary, short lists padded
- *     with lowest-float).  *overflowed = 1: the approximate pass overflowed its buffers; every
- *     shard must then use cmx_search_mixed instead (decide collectively).  nA*nq <= 8192.
- *  2. cmx_union_kth: the GLOBAL k-th best approximate score of queries [q0, q1) = k-th largest of
- *     the union of all shards' lists, read in place (score_parts[g] may be peer memory) and
- *     written to every kth_outs[o][q] (local or peer).  Asynchronous on `stream`.
+ * New capability (BASELINE north_star (4)); the reference never shards (it calls
+ * index_cpu_to_gpu(res, ONE gpu, index): onepass_dense_mix_run_custom_lang.py:661-663).
+ * A shard that rescored its own k best would do G times the necessary exact work, and a step that
+ * stopped for host decisions would leave G GPUs idle.  These entry points are building blocks that
+ * only ENQUEUE work on `stream` (no host synchronisation; unlike the rest of this header results are
+ * valid once the stream has been synchronised).  The caller provides the cross-shard barriers
+ * (symmetric-memory barriers between processes, events between the streams of one process).
+ *  0. cmx_search_prepare: the fused mix + normalise prologue for nA alphas into the index's own query
+ *     buffer; *q_out [nA*nq, d] (device) is valid until the next prepare / search_mixed on the index.
+ *     cmx_index_export_bounds: this shard's {max row norm, max fp16-residual norm} -> out2 (device,
+ *     e.g. this shard's slot of a symmetric buffer).          [barrier: bounds of all shards visible]
+ *  1. cmx_search_begin: approximate pass over the shard for queries q [nq <= 8192, d] (chunk larger
+ *     batches); the filter margin uses the maxima over bounds_parts[0..nparts) (peer memory allowed);
+ *     writes the shard's k best APPROXIMATE scores per query to scores_out [nq, k] (order arbitrary,
+ *     short lists padded with lowest-float) and its status word to flag_out (0 = ok; buffer overflow,
+ *     failed speculation or "this shard cannot run the one-pass arithmetic" otherwise).  est_scale =
+ *     1 / number of shards: how deep exact scores are computed ahead of time beside the scoring
+ *     kernel.  An empty shard is fine.               [barrier: scores + status of all shards visible]
+ *  2. cmx_union_kth: the GLOBAL k-th best approximate score of queries [q0, q1) = k-th largest of the
+ *     union of all shards' lists, read in place (score_parts[g] may be peer memory), written to every
+ *     kth_outs[o][q] (local or peer); ORs flag_parts[0..nflags) into *flag_any (device).
+ *                                                          [barrier: kth of all queries visible]
  *  3. cmx_search_end: exact fp32 rescoring of the rows with approx >= max_p kth_parts[p][q] -
- *     2*eps(q) only; D, I [nA*nq,k] then hold the shard's exact hits that can still belong to the
- *     global top-k (fewer than k: padded with -1), ready for cmx_merge_topk(_peers). */
-CMX_API int cmx_search_mixed_begin(cmx_index* ix, const float* P, const float* S, int64_t nq,
-                                   const double* alphas, int nA, int k, int64_t id_base,
-                                   float* scores_out, int* overflowed, void* stream);
+ *     2*eps(q) only; D, I [nq,k] then hold the shard's exact hits that can still belong to the global
+ *     top-k (fewer than k: padded with -1), ready for cmx_merge_topk(_peers).
+ *  After the step the caller reads *flag_any: non-zero on ANY shard is non-zero on ALL of them (every
+ *  shard ORs the same words), so all shards redo the step with cmx_search_mixed + merge together. */
+CMX_API int cmx_search_prepare(cmx_index* ix, const float* P, const float* S, int64_t nq,
+                               const double* alphas, int nA, const float** q_out, void* stream);
+CMX_API int cmx_index_export_bounds(cmx_index* ix, float* out2_dev, void* stream);
+CMX_API int cmx_search_begin(cmx_index* ix, const float* q, int64_t nq, int k, int64_t id_base,
+                             const float* const* bounds_parts, int nparts, float est_scale,
+                             float* scores_out, uint32_t* flag_out, void* stream);
 CMX_API int cmx_union_kth(const float* const* score_parts, int nparts, int64_t nq, int k, int64_t q0,
-                          int64_t q1, float* const* kth_outs, int nouts, int device, void* stream);
+                          int64_t q1, float* const* kth_outs, int nouts,
+                          const uint32_t* const* flag_parts, int nflags, uint32_t* flag_any,
+                          int device, void* stream);
 CMX_API int cmx_search_end(cmx_index* ix, const float* const* kth_parts, int nparts, float* D,
                            int64_t* I, void* stream);
+/* src [bytes] (device) -> every dsts[i] (device, usually peer memory): one read, ndst 128-bit stores
+ * per element over NVLink.  Used to replicate each rank's slice of the uploaded query vectors, so the
+ * 57 MB of P,S cross PCIe once per NODE instead of once per GPU.  Asynchronous. */
+CMX_API int cmx_peer_broadcast(const void* src, void* const* dsts, int ndst, int64_t bytes, int device,
+                               void* stream);
+/* Page-lock and device-map an existing host range (e.g. a POSIX shared-memory segment every rank
+ * maps): kernels may then write results straight into it (cmx_merge_topk_peers outputs,
+ * cmx_index_search / cmx_search_mixed host outputs).  *dev_ptr = the device-side alias. */
+CMX_API int cmx_host_register(void* p, int64_t bytes, void** dev_ptr);
+CMX_API int cmx_host_unregister(void* p);
+/* one process driving several GPUs: let `device` map the memory of `peer`. */
+CMX_API int cmx_enable_peer_access(int device, int peer);
 
 /* ---- k-way merge of per-shard results (multi-GPU) ---------------------------
  * new capability (BASELINE north_star (4)); the reference never shards.
@@ -157,7 +190,7 @@ CMX_API int cmx_merge_topk(const float* D_parts, const int64_t* I_parts, int npa
  * I_parts[g] are DEVICE pointers to part g's [nq,k] lists, each possibly resident on another
  * GPU and mapped into this process; the kernel reads them in place, merges queries
  * [q0, q1) and stores the merged rows into each of the nouts output buffers D_outs[o] /
- * I_outs[o] ([nq,k], local or peer).  The caller provides the cross-rank barriers before
+ * I_outs[o] ([nq,k]: local, peer, or the device alias of a registered host buffer).  The caller provides the cross-rank barriers before
  * (parts complete) and after (outputs complete).  Asynchronous on `stream` unlike the
  * other entry points: it returns once the kernel is enqueued.  nparts, nouts <= 16. */
 CMX_API int cmx_merge_topk_peers(const float* const* D_parts, const int64_t* const* I_parts, int nparts,

@@ -710,19 +710,27 @@ def test_two_phase_sharded_search_on_one_gpu(G):
         sh.set_precision("rescore")
         sh.add(X[bounds[g]:bounds[g + 1]])
         shards.append(sh)
-    eb = np.array([sh.error_bounds() for sh in shards]).max(axis=0)
-    for sh in shards:
-        sh.raise_error_bounds(float(eb[0]), float(eb[1]))
     nqt = len(alphas) * nq
+    # the asynchronous building blocks of include/cmx.h, driven from one stream (stream order = the barriers)
+    bnd = [torch.zeros((2,), dtype=torch.float32, device="cuda") for _ in range(G)]
+    flg = [torch.full((1,), 7, dtype=torch.int32, device="cuda") for _ in range(G)]
+    flag_any = torch.zeros((1,), dtype=torch.int32, device="cuda")
     asc = [torch.empty((nqt * k,), dtype=torch.float32, device="cuda") for _ in range(G)]
     for g, sh in enumerate(shards):
-        assert not sh.search_mixed_begin(Pt, St, alphas, k, int(bounds[g]), asc[g])
+        sh.export_bounds(bnd[g].data_ptr())
+    qp = [sh.search_prepare(Pt, St, alphas) for sh in shards]
+    for g, sh in enumerate(shards):
+        sh.search_begin(qp[g], nqt, k, int(bounds[g]), [b.data_ptr() for b in bnd], 1.0 / G, asc[g].data_ptr(), flg[g].data_ptr())
     kth = torch.empty((nqt,), dtype=torch.float32, device="cuda")
-    union_kth([a.data_ptr() for a in asc], nqt, k, 0, nqt, [kth.data_ptr()], 0)
+    union_kth([a.data_ptr() for a in asc], nqt, k, 0, nqt, [kth.data_ptr()], 0, [f.data_ptr() for f in flg], flag_any.data_ptr())
     Dp = torch.empty((G, nqt, k), dtype=torch.float32, device="cuda")
     Ip = torch.empty((G, nqt, k), dtype=torch.int64, device="cuda")
     for g, sh in enumerate(shards):
-        sh.search_end([kth.data_ptr()], Dp[g], Ip[g])
+        sh.search_end([kth.data_ptr()], Dp[g].data_ptr(), Ip[g].data_ptr())
+    torch.cuda.synchronize()
+    assert int(flag_any.item()) == 0 and all(int(f.item()) == 0 for f in flg)
+    # the margins came from the GLOBAL maxima: every shard saw the 3x rows of shard 0
+    assert max(float(b[0]) for b in bnd) > 2.5
     Dm, Im = merge_topk(Dp, Ip)
     assert torch.equal(Im.view(len(alphas), nq, k), I1) and torch.equal(Dm.view(len(alphas), nq, k), D1)
     # each shard returned only rows inside the global band: far fewer than k valid entries per query

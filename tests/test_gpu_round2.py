@@ -1,0 +1,259 @@
+"""GPU tests of the round-2 machinery: exact scores ahead of time (prescoring), speculative mid slabs,
+the asynchronous two-phase building blocks, pinned shared host results, the one-process multi-GPU index
+and the index.faiss reader on a device sink."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _unit(rng, n, d):
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+def _unit_cuda(n, d, seed):
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.nn.functional.normalize(torch.randn((n, d), generator=g, device="cuda"), dim=1)
+
+
+def _brute(X, Q, k):
+    """fp32 brute force on the GPU (torch, TF32 off), ties by ascending row via a stable sort."""
+    import torch
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        s = Q @ X.T
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    v, i = torch.topk(s, k, dim=1)
+    return v.cpu().numpy(), i.cpu().numpy()
+
+
+def test_prescoring_is_invisible_in_the_result():
+    """A last slab long enough to be cut into several scoring launches: the candidates found early get
+    their exact scores beside the next launch (prescore_kernel on a second stream).  Same (D, I), bit for
+    bit, as with all exact scores computed after the last tile -- and as the fp32 brute force."""
+    from cmx import _lib
+    from cmx.engine import Shard
+
+    N, d, nq, k = 1_000_000, 128, 300, 1000
+    X, Q = _unit_cuda(N, d, 11), _unit_cuda(nq, d, 12)
+    sh = Shard(d, 0)
+    sh.add(X)
+    D1, I1 = sh.search(Q, k, path="tensor")
+    st1 = sh.last_stats()
+    assert st1["reruns"] == 0 and st1["score_launches"] > st1["slabs"], st1  # the last slab ran as several launches
+    _lib.check(_lib.lib().cmx_debug_set_prescore(0))
+    try:
+        D0, I0 = sh.search(Q, k, path="tensor")
+        st0 = sh.last_stats()
+    finally:
+        _lib.check(_lib.lib().cmx_debug_set_prescore(1))
+    assert st0["score_launches"] == st0["slabs"]
+    import torch
+
+    assert torch.equal(I1, I0) and torch.equal(D1, D0)
+    Dr, Ir = _brute(X, Q, k)
+    rep = oracle.compare_topk(D1.cpu().numpy(), I1.cpu().numpy(), Dr, Ir, rtol=RTOL, atol=ATOL)
+    assert rep["ok"], rep
+    # repeated searches reuse the side stream / snapshots
+    D2, I2 = sh.search(Q, k, path="tensor")
+    assert torch.equal(I2, I1) and torch.equal(D2, D1)
+
+
+def test_speculative_mid_slab_equals_planned_slabs():
+    """k = 1000 over 3 M rows: dense slab, ONE speculative mid slab, speculative final slab (3 launches
+    groups) -- identical to the geometric plan's result."""
+    import torch
+
+    from cmx import _lib
+    from cmx.engine import Shard
+
+    N, d, nq, k = 3_000_000, 64, 200, 1000
+    X, Q = _unit_cuda(N, d, 21), _unit_cuda(nq, d, 22)
+    sh = Shard(d, 0)
+    sh.add(X)
+    D1, I1 = sh.search(Q, k, path="tensor")
+    st1 = sh.last_stats()
+    assert st1["slabs"] == 3 and st1["reruns"] == 0, st1
+    _lib.check(_lib.lib().cmx_debug_set_speculate(0))
+    try:
+        D0, I0 = sh.search(Q, k, path="tensor")
+        st0 = sh.last_stats()
+    finally:
+        _lib.check(_lib.lib().cmx_debug_set_speculate(1))
+    assert st0["slabs"] > st1["slabs"] and st0["reruns"] == 0
+    assert torch.equal(I1, I0) and torch.equal(D1, D0)
+
+
+def test_pending_two_phase_state_is_cancelled_by_other_calls():
+    import torch
+
+    from cmx.engine import Shard
+
+    rng = np.random.default_rng(5)
+    X, Q = _unit(rng, 20000, 64), _unit(rng, 40, 64)
+    sh = Shard(64, 0)
+    sh.add(X)
+    Qt = torch.from_numpy(Q).cuda()
+    bnd = torch.zeros((2,), dtype=torch.float32, device="cuda")
+    flag = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    asc = torch.empty((40 * 10,), dtype=torch.float32, device="cuda")
+    D = torch.empty((40, 10), dtype=torch.float32, device="cuda")
+    I = torch.empty((40, 10), dtype=torch.int64, device="cuda")
+    with pytest.raises(RuntimeError, match="pending"):
+        sh.search_end([], D.data_ptr(), I.data_ptr())
+    sh.export_bounds(bnd.data_ptr())
+    sh.search_begin(Qt.data_ptr(), 40, 10, 0, [bnd.data_ptr()], 1.0, asc.data_ptr(), flag.data_ptr())
+    sh.search(Q[:3], 5)  # reuses the workspace: the pending state must not survive
+    with pytest.raises(RuntimeError, match="pending"):
+        sh.search_end([], D.data_ptr(), I.data_ptr())
+    sh.search_begin(Qt.data_ptr(), 40, 10, 0, [bnd.data_ptr()], 1.0, asc.data_ptr(), flag.data_ptr())
+    sh.add(X[:10])
+    with pytest.raises(RuntimeError, match="pending"):
+        sh.search_end([], D.data_ptr(), I.data_ptr())
+    # a complete begin / end with no global cut == the plain search
+    sh.search_begin(Qt.data_ptr(), 40, 10, 0, [bnd.data_ptr()], 1.0, asc.data_ptr(), flag.data_ptr())
+    sh.search_end([], D.data_ptr(), I.data_ptr())
+    torch.cuda.synchronize()
+    D1, I1 = sh.search(Qt, 10, path="tensor")
+    assert int(flag.item()) == 0 and torch.equal(I, I1) and torch.equal(D, D1)
+
+
+def test_empty_and_unusable_shards_in_two_phase():
+    """An empty shard takes part in a two-phase step (all-padding lists); a shard that cannot run the one-pass
+    arithmetic raises no error but sets its status word, so that all shards fall back together."""
+    import torch
+
+    from cmx.engine import Shard, union_kth
+
+    rng = np.random.default_rng(6)
+    X, Q = _unit(rng, 9000, 64), _unit(rng, 17, 64)
+    Qt = torch.from_numpy(Q).cuda()
+    k = 20
+    full, empty, split = Shard(64, 0), Shard(64, 0), Shard(64, 0)
+    full.add(X)
+    split.add(X[:100])
+    split.set_precision("split")
+    shards = [full, empty, split]
+    bnd = [torch.zeros((2,), dtype=torch.float32, device="cuda") for _ in shards]
+    flg = [torch.zeros((1,), dtype=torch.int32, device="cuda") for _ in shards]
+    asc = [torch.empty((17 * k,), dtype=torch.float32, device="cuda") for _ in shards]
+    for sh, b in zip(shards, bnd):
+        sh.export_bounds(b.data_ptr())
+    for g, sh in enumerate(shards):
+        sh.search_begin(Qt.data_ptr(), 17, k, 0, [b.data_ptr() for b in bnd], 1.0 / 3, asc[g].data_ptr(), flg[g].data_ptr())
+    flag_any = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    kth = torch.empty((17,), dtype=torch.float32, device="cuda")
+    union_kth([a.data_ptr() for a in asc[:2]], 17, k, 0, 17, [kth.data_ptr()], 0, [f.data_ptr() for f in flg], flag_any.data_ptr())
+    D = torch.empty((3, 17, k), dtype=torch.float32, device="cuda")
+    I = torch.empty((3, 17, k), dtype=torch.int64, device="cuda")
+    for g, sh in enumerate(shards):
+        sh.search_end([kth.data_ptr()], D[g].data_ptr(), I[g].data_ptr())
+    torch.cuda.synchronize()
+    assert int(flg[0].item()) == 0 and int(flg[1].item()) == 0 and int(flg[2].item()) == 0x100
+    assert int(flag_any.item()) == 0x100
+    assert bool((I[1] == -1).all()) and bool((asc[1] == np.finfo(np.float32).min).all())
+    D1, I1 = full.search(Qt, k, path="tensor")
+    assert torch.equal(I[0], I1) and torch.equal(D[0], D1)  # shards 0 + 1 alone: the cut is shard 0's own k-th
+
+
+def test_finite_rows_with_overflowing_norm_use_split_precision():
+    """||x|| > 1.8e19 overflows the fp32 sum of squares of the error bound: the index reports an infinite
+    bound and searches in split precision instead of silently underestimating the margin."""
+    from cmx.engine import Shard
+
+    rng = np.random.default_rng(8)
+    X = _unit(rng, 5000, 64) * np.float32(3e19)
+    Q = _unit(rng, 40, 64)
+    sh = Shard(64, 0)
+    sh.set_precision("rescore")
+    sh.add(X)
+    nb, _ = sh.error_bounds()
+    assert np.isinf(nb)
+    D, I = sh.search(Q, 10, path="tensor")
+    Dr, Ir = oracle.flat_ip_search(X, Q, 10)
+    assert oracle.compare_topk(D, I, Dr, Ir, rtol=RTOL, atol=ATOL)["ok"]
+
+
+def test_shards_index_one_process(tmp_path):
+    """cmx.faiss.IndexShardsIP runs the SAME two-phase step as the torchrun path, one thread per shard over a
+    LocalFabric -- here three shards on one GPU (any GPU count >= 1): equals the single-index result bit for
+    bit, for a batch larger than one two-phase chunk too, and for host results in alternating pinned buffers."""
+    import cmx.faiss as faiss
+    from cmx.engine import Shard
+
+    rng = np.random.default_rng(9)
+    N, d, nq, k = 60000, 128, 150, 100
+    X, P, S = _unit(rng, N, d), _unit(rng, nq, d), _unit(rng, nq, d)
+    X[40000:40300] = X[200:500]  # ties across shards
+    one = Shard(d, 0)
+    one.add(X)
+    alphas = [0.0, 0.3, 1.0]
+    D1, I1 = one.search_mixed(P, S, alphas, k, path="tensor")
+    cpu = faiss.IndexFlatIP(d)
+    cpu.add(X)
+    sharded = faiss.index_cpu_to_gpus_list(cpu, gpus=[0, 0, 0])
+    Ds, Is = sharded.search_mixed(P, S, alphas, k)
+    assert sharded.two_phase_used
+    assert np.array_equal(Is, I1) and np.array_equal(Ds, D1)
+    Ds2, Is2 = sharded.search_mixed(P, S, alphas, k)  # the other pinned buffer; the first result is still intact
+    assert Ds2.ctypes.data != Ds.ctypes.data and np.array_equal(Is, I1) and np.array_equal(Is2, I1)
+    Dq, Iq = sharded.search(P, k)
+    assert np.array_equal(Iq, I1[0]) and np.array_equal(Dq, D1[0])
+    # 60 alphas x 150 queries = 9000 > 8192: two chunks of the two-phase pass
+    many = [i / 59.0 for i in range(60)]
+    Dm, Im = sharded.search_mixed(P, S, many, 10)
+    D0, I0 = one.search_mixed(P, S, many, 10, path="tensor")
+    assert np.array_equal(Im, I0) and np.array_equal(Dm, D0)
+    assert all(v.fallback_steps == 0 for v in sharded._views)
+
+
+def test_two_gpu_shards_one_process_if_available():
+    """Real multi-GPU, one process: peer access + event barriers between the devices' streams."""
+    import torch
+    import cmx.faiss as faiss
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(26)
+    N, d, nq, k = 400_000, 128, 500, 1000
+    X, P, S = _unit(rng, N, d), _unit(rng, nq, d), _unit(rng, nq, d)
+    cpu = faiss.IndexFlatIP(d)
+    cpu.add(X)
+    one = faiss.index_cpu_to_gpu(faiss.StandardGpuResources(), 0, cpu)
+    D1, I1 = one.search_mixed(P, S, [0.5, 0.9], k)
+    sharded = faiss.index_cpu_to_all_gpus(cpu, ngpu=min(4, torch.cuda.device_count()))
+    Ds, Is = sharded.search_mixed(P, S, [0.5, 0.9], k)
+    assert sharded.two_phase_used
+    assert np.array_equal(Is, np.asarray(I1)) and np.array_equal(Ds, np.asarray(D1))
+
+
+def test_index_fixture_streams_into_a_gpu_index(tmp_path):
+    """read_index_to_gpu on an index.faiss assembled with bare struct.pack (tests/test_host_logic.py)."""
+    import cmx.faiss as faiss
+    from test_host_logic import _faiss18_fixture
+
+    rng = np.random.default_rng(41)
+    n, d = 3000, 64
+    x = _unit(rng, n, d)
+    ids = (rng.permutation(100_000)[:n] + 5).astype(np.int64)
+    blob, _ = _faiss18_fixture(x, ids)
+    path = tmp_path / "index.faiss"
+    path.write_bytes(blob)
+    gidx = faiss.read_index_to_gpu(str(path), device=0)
+    assert gidx.ntotal == n and np.array_equal(gidx.id_map, ids)
+    assert np.array_equal(gidx.index.reconstruct_n(0, n), x)
+    Q = _unit(rng, 9, d)
+    D, I = gidx.search(Q, 7)
+    Dr, Ir = oracle.flat_ip_search(x, Q, 7, ids=ids)
+    assert oracle.compare_topk(D, I, Dr, Ir, rtol=RTOL, atol=ATOL)["ok"]

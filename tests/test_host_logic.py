@@ -284,6 +284,57 @@ def test_index_file_roundtrip(tmp_path):
         faiss.read_index(tmp_path / "trunc.faiss")
 
 
+def _faiss18_fixture(x, ids):
+    """An ``index.faiss`` assembled byte by byte with bare ``struct.pack`` in the field order of faiss 1.8's
+    index_write.cpp (write_index_header + the IxFI / IxMp branches) -- independent of cmx.io's writer:
+        fourcc "IxMp" | int32 d | int64 ntotal | int64 dummy | int64 dummy | uint8 is_trained | int32 metric_type
+        fourcc "IxFI" | <same header> | uint64 n_floats | n_floats x float32 (WRITEVECTOR(codes) in float units)
+        uint64 n_ids | n_ids x int64 (WRITEVECTOR(id_map))"""
+    import struct
+
+    n, d = x.shape
+
+    def header():
+        return struct.pack("<i", d) + struct.pack("<q", n) + struct.pack("<q", 1 << 20) + struct.pack("<q", 1 << 20) \
+            + struct.pack("<B", 1) + struct.pack("<i", 0)
+
+    flat = b"IxFI" + header() + struct.pack("<Q", n * d) + b"".join(struct.pack("<f", float(v)) for v in x.reshape(-1))
+    return b"IxMp" + header() + flat + struct.pack("<Q", n) + b"".join(struct.pack("<q", int(v)) for v in ids), flat
+
+
+def test_index_reader_against_independent_byte_fixture(tmp_path):
+    """read_index / inspect_index / stream_index_rows on a file this repository's writer never touched
+    (faiss is not installable here, so this cannot be a faiss-written file: parity for the format stays
+    'unpinned', but reader and writer no longer vouch for each other)."""
+    import cmx.faiss as faiss
+
+    rng = np.random.default_rng(31)
+    n, d = 53, 20
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ids = (rng.permutation(10_000)[:n] * 7 + 3).astype(np.int64)  # a non-identity, non-monotonic id_map
+    blob, flat_blob = _faiss18_fixture(x, ids)
+    path = tmp_path / "index.faiss"
+    path.write_bytes(blob)
+    info = cio.inspect_index(path)
+    assert info == {"kind": "IxMp", "d": d, "ntotal": n, "vec_offset": 4 + 33 + 4 + 33 + 8,
+                    "ids_offset": 4 + 33 + 4 + 33 + 8 + 4 * n * d + 8}
+    idx = faiss.read_index(str(path))
+    assert isinstance(idx, faiss.IndexIDMap) and idx.d == d and idx.ntotal == n
+    assert np.array_equal(idx.id_map, ids)
+    base = faiss.downcast_index(idx.index)
+    assert np.array_equal(base.reconstruct_n(0, n), x)
+    sink = faiss.IndexFlatIP(d)
+    assert cio.stream_index_rows(path, sink, 5, 40, chunk_rows=8).tolist() == ids[5:40].tolist()
+    assert np.array_equal(sink.reconstruct_n(0, 35), x[5:40])
+    # the nested flat index alone is a valid IxFI file
+    (tmp_path / "flat.faiss").write_bytes(flat_blob)
+    flat = faiss.read_index(tmp_path / "flat.faiss")
+    assert isinstance(flat, faiss.IndexFlatIP) and np.array_equal(flat.reconstruct_n(0, n), x)
+    # and the writer produces exactly these bytes
+    faiss.write_index(idx, tmp_path / "rewritten.faiss")
+    assert (tmp_path / "rewritten.faiss").read_bytes() == blob
+
+
 def test_index_file_validator_and_streaming_reader(tmp_path):
     """inspect_index checks the whole layout without loading vectors; stream_index_rows feeds any row
     range to a sink (a GPU index or one rank's shard in production, a host index here)."""
@@ -382,30 +433,47 @@ def _plan(n, k, cap, rescore=1, safe=0, spec=1):
     return [int(rows[i]) for i in range(min(ns.value, 4096))], ns.value, ss.value, sr.value
 
 
+def _plan_ranks(n, k, cap, rescore=1, safe=0, spec=1, nslabs=16):
+    from cmx import _lib
+
+    ranks = (ctypes.c_int * nslabs)()
+    _lib.check(_lib.lib().cmx_debug_plan_ranks(n, k, cap, rescore, safe, spec, ranks, nslabs))
+    return [int(v) for v in ranks]
+
+
 def test_slab_schedule_invariants():
     """Host logic of the tensor path's slab schedule: whole 256-row blocks, dense first slab,
-    geometric growth, speculative last slab only when its rank estimate is trustworthy, safe slabs bounded."""
+    geometric growth, speculative slabs only when their rank estimate is trustworthy, safe slabs bounded."""
     n = 8_841_823
     npad = (n + 255) // 256 * 256
+    # C2: dense slab, ONE speculative mid slab up to the row count where the final k'-th best is expected at
+    # rank 32 of the dense slab, then the rest of the corpus under a second guess -- 3 launches instead of 5
     rows, ns, ss, sr = _plan(n, 1000, 8192)
-    assert rows == [8192, 20736, 73728, 262144, npad - 364800] and ss == 4
-    seen = sum(rows[:4])
+    mid = 1341 * 8192 // 32 - 8192
+    assert rows == [8192, mid // 256 * 256, npad - 8192 - mid // 256 * 256] and ns == 3 and ss == 2
+    assert _plan_ranks(n, 1000, 8192)[:3] == [0, 96, sr]
+    seen = sum(rows[:2])
     r0 = 1341 * seen / npad
-    assert r0 >= 32 and sr == int(np.ceil(3 * r0)) and sr < 1000
+    assert r0 >= 32 and sr == int(np.ceil(3 * r0)) and sr < 750
     rows_g, ns_g, ss_g, _ = _plan(n, 1000, 8192, spec=0)
-    assert ss_g == -1 and ns_g == 7 and rows_g[:4] == rows[:4] and sum(rows_g) == npad
+    assert ss_g == -1 and ns_g == 7 and rows_g[:4] == [8192, 20736, 73728, 262144] and sum(rows_g) == npad
     for a, b in zip(rows_g[1:-1], rows_g[2:-1]):
         assert 3.0 < b / a < 3.7  # x(1 + (C - k') / 2k') per slab
-    # a 1.1 M-row shard of an 8-GPU search: guess after the second slab
+    # shards of a 2- and 4-GPU search: 3 launches as well
+    for g in (2, 4):
+        rows_s, ns_s, ss_s, sr_s = _plan(n // g, 1000, 8192)
+        assert ns_s == 3 and ss_s == 2 and rows_s[1] == rows[1] and 96 < sr_s < 750
+    # a 1.1 M-row shard of an 8-GPU search: a mid slab would not save a launch, the plan stays
+    # dense, one geometric slab, guess after the second slab
     rows8, ns8, ss8, sr8 = _plan(1_105_228, 1000, 8192)
-    assert ns8 == 3 and ss8 == 2 and 96 <= sr8 < 1000
+    assert ns8 == 3 and ss8 == 2 and rows8[:2] == [8192, 20736] and 96 <= sr8 < 1000
     # small k: the geometric plan is already 3-4 slabs and the rank estimate never qualifies
     assert _plan(n, 100, 8192)[2] == -1 and _plan(n, 10, 8192)[2] == -1
     # split precision plans on k itself
     rows_s, _, ss_s, sr_s = _plan(n, 1000, 8192, rescore=0)
     assert sum(rows_s) == npad and ss_s >= 1 and sr_s < 1000
     for r in (rows, rows_g, rows8, rows_s):
-        assert all(v % 256 == 0 and v > 0 for v in r) and r[0] == 8192
+        assert all(v % 256 == 0 and v > 0 for v in r) and r[0] == 8192 and sum(r) == ((sum(r) + 255) // 256) * 256
     # worst-case-safe schedule: no slab larger than the free room; tiny buffers get pieces of one block
     rows_safe, ns_safe, ss_safe, _ = _plan(100_000, 1000, 8192, rescore=0, safe=1)
     assert ss_safe == -1 and max(rows_safe[1:]) <= 8192 - 1000 and sum(rows_safe) == (100_000 + 255) // 256 * 256
