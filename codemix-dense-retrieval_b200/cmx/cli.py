@@ -9,6 +9,14 @@ path this repository covers: cached per-language index (``<index_root>/<lang>/{i
 docids.txt}``) + cached query vectors (``<cache>/<lang>/queries.npz``) -> per-alpha TREC files.  Encoding
 corpora or queries (HF encoder + network) is out of scope: when a cache is missing the script stops and says
 so instead of loading an encoder.  Encoder-side flags are accepted and ignored.
+
+What differs from the reference's data flow: the vectors of an ``index.faiss`` never become a host-resident
+index.  ``index.faiss`` is validated (``inspect_index``) and its float block is streamed by the native loader
+(reader threads -> page-locked staging buffers -> HBM) into the GPU index -- or, with ``--gpus N``, each
+GPU's row range into its shard.  The bilingual combined index (reference :606-702: 17.7 M Python-level
+``reconstruct`` calls into a CPU index that is then cloned to the GPU) is built the same way: both language
+files stream into ONE device index, ``docid_map.tsv`` is emitted from the map files' columns, and no row is
+materialised in host memory.
 """
 from __future__ import annotations
 
@@ -30,33 +38,40 @@ from . import runloop
 RECON_BATCH = 20000  # the reference adds cached rows in batches of 20 000 map lines, each sorted by id
 
 
+# The three helpers below reproduce reference behaviour that users see (directory names of the query cache,
+# error messages of the --query_tsv parser): onepass_dense_mix_run_custom_lang.py:150-168,311-339.
 def sanitize_tag(text: str) -> str:
-    clean = re.sub(r"[^A-Za-z0-9_.-]+", "-", text.strip("/"))
-    return clean.strip("-") or "run"
+    """Anything outside [A-Za-z0-9_.-] collapses to '-'; an empty result becomes 'run'."""
+    cleaned = re.sub(r"[^A-Za-z0-9_.-]+", "-", text.strip("/")).strip("-")
+    return cleaned if cleaned else "run"
 
 
 def default_query_cache_root(repo: str, encoder: str) -> pathlib.Path:
-    env_root = os.environ.get("QUERY_CACHE_ROOT")
-    if env_root:
-        return pathlib.Path(env_root)
-    base = os.environ.get("QUERY_CACHE_ROOT_BASE", str(pathlib.Path.cwd() / "data"))
-    return pathlib.Path(base) / f"enc-query-{sanitize_tag(repo.split('/')[-1])}-{sanitize_tag(encoder.split('/')[-1])}"
+    """$QUERY_CACHE_ROOT, else <$QUERY_CACHE_ROOT_BASE or ./data>/enc-query-<repo>-<encoder>."""
+    explicit = os.environ.get("QUERY_CACHE_ROOT")
+    if explicit:
+        return pathlib.Path(explicit)
+    parent = pathlib.Path(os.environ.get("QUERY_CACHE_ROOT_BASE") or (pathlib.Path.cwd() / "data"))
+    leaf = "enc-query-{}-{}".format(*(sanitize_tag(name.split("/")[-1]) for name in (repo, encoder)))
+    return parent / leaf
 
 
 def parse_query_specs(query_tsv_args, q_primary, q_secondary) -> List[Tuple[str, pathlib.Path]]:
-    specs: List[Tuple[str, pathlib.Path]] = []
+    """[(lang, path), (lang, path)] from two ``--query_tsv LANG=PATH`` flags, or from --q_en / --q_zh."""
     if query_tsv_args:
-        for entry in query_tsv_args:
-            if "=" not in entry:
-                raise SystemExit(f"--query_tsv expects LANG=PATH, got '{entry}'.")
-            lang, path = (v.strip() for v in entry.split("=", 1))
-            if not lang or not path:
-                raise SystemExit(f"[ERROR] Bad --query_tsv entry '{entry}'.")
+        specs = []
+        for item in query_tsv_args:
+            lang, sep, path = item.partition("=")
+            if not sep:
+                raise SystemExit(f"--query_tsv expects LANG=PATH, got '{item}'.")
+            lang, path = lang.strip(), path.strip()
+            if not (lang and path):
+                raise SystemExit(f"[ERROR] Bad --query_tsv entry '{item}'.")
             specs.append((lang, pathlib.Path(path)))
-    else:
-        if not q_primary or not q_secondary:
-            raise SystemExit("Provide either --query_tsv twice or both --q_en and --q_zh.")
+    elif q_primary and q_secondary:
         specs = [("en", pathlib.Path(q_primary)), ("zh", pathlib.Path(q_secondary))]
+    else:
+        raise SystemExit("Provide either --query_tsv twice or both --q_en and --q_zh.")
     if len(specs) != 2:
         raise SystemExit(f"Exactly two query TSV specs required, got {len(specs)}.")
     if specs[0][0] == specs[1][0]:
@@ -64,18 +79,25 @@ def parse_query_specs(query_tsv_args, q_primary, q_secondary) -> List[Tuple[str,
     return specs
 
 
-def load_cached_index(index_root: pathlib.Path, lang: str, expected_dim: Optional[int] = None):
+def locate_cached_index(index_root: pathlib.Path, lang: str, expected_dim: Optional[int] = None):
+    """The cached index of one language WITHOUT loading its vectors: the three files must exist and
+    ``index.faiss`` must pass the whole-layout validation (reference: read_index + a probe reconstruct,
+    onepass_dense_mix_run_custom_lang.py:238-284)."""
     lang_dir = index_root / lang
     paths = [lang_dir / "index.faiss", lang_dir / "docid_map.tsv", lang_dir / "docids.txt"]
     if not all(p.exists() for p in paths):
         return None
-    index = faiss.read_index(str(paths[0]))
-    if expected_dim and index.d != expected_dim:
-        logging.warning("Cached index dim mismatch for %s: expected %s, found %s.", lang, expected_dim, index.d)
+    try:
+        info = cio.inspect_index(paths[0])
+    except Exception as exc:  # noqa: BLE001 -- the reference logs and treats the cache as unusable
+        logging.warning("Failed to read cached index for %s: %s", lang, exc)
         return None
-    base = faiss.downcast_index(index.index if hasattr(index, "index") else index)
-    base.reconstruct(0, np.empty((base.d,), dtype=np.float32))
-    return {"lang": lang, "index": index, "base_index": base, "map_path": paths[1]}
+    if expected_dim and info["d"] != expected_dim:
+        logging.warning("Cached index dim mismatch for %s: expected %s, found %s.", lang, expected_dim, info["d"])
+        return None
+    if info["ntotal"] == 0:
+        return None
+    return {"lang": lang, "index_path": paths[0], "map_path": paths[1], "info": info}
 
 
 def _common(ap: argparse.ArgumentParser) -> None:
@@ -119,10 +141,37 @@ def _load_queries(args):
     return (l1, l2), common, P, S
 
 
-def _place(index_cpu, args):
+def _devices(args) -> List[int]:
+    if os.environ.get("CMX_DEVICES"):  # explicit device list, e.g. "0,0,0" = three shards on one GPU (tests)
+        return [int(v) for v in os.environ["CMX_DEVICES"].split(",")]
     if args.gpus and args.gpus > 1:
-        return faiss.index_cpu_to_gpus_list(index_cpu, gpus=list(range(args.gpus)))
-    return faiss.index_cpu_to_gpu(faiss.StandardGpuResources(), args.faiss_gpu_id, index_cpu)
+        return list(range(args.gpus))
+    return [int(args.faiss_gpu_id)]
+
+
+def build_device_index(segments, d: int, devices: Sequence[int], ids: Optional[np.ndarray] = None, log=None):
+    """``IndexIDMap`` over a GPU-resident flat index holding the concatenation of ``segments`` -- a list of
+    (path, byte offset of the float block, rows) -- streamed from the files by the native loader.  One device:
+    ``GpuIndexFlatIP``; several: ``IndexShardsIP`` (row i -> shard floor(i*G/n)), every shard loading its own row
+    range, all shards at once.  ``ids`` = the user ids (default 0..n-1)."""
+    total = sum(int(r) for _, _, r in segments)
+    t0 = time.perf_counter()
+    if len(devices) == 1:
+        flat = faiss.GpuIndexFlatIP(d, device=devices[0])
+        flat.reserveMemory(total)
+        for path, off, rows in segments:
+            flat.add_from_file(path, off, rows)
+    else:
+        flat = faiss.IndexShardsIP(d, devices)
+        flat.add_from_files(segments)
+    dt = time.perf_counter() - t0
+    if log:
+        log(f"Streamed {total} vectors ({4e-9 * d * total:.1f} GB) into {len(devices)} GPU(s) in {dt:.2f}s "
+            f"({4e-9 * d * total / max(dt, 1e-9):.2f} GB/s)")
+    out = faiss.IndexIDMap(faiss.IndexFlatIP(d))  # the wrapper wants an empty index at construction
+    out.index = flat
+    out._ids = [np.arange(total, dtype=np.int64) if ids is None else np.ascontiguousarray(ids, dtype=np.int64)]
+    return out
 
 
 def main_mono(argv: Optional[Sequence[str]] = None) -> int:
@@ -137,7 +186,7 @@ def main_mono(argv: Optional[Sequence[str]] = None) -> int:
     if ignored:
         logging.info("Ignoring encoder-side flags: %s", " ".join(ignored))
     doc_lang = args.config.replace("collection-", "")
-    cached = load_cached_index(pathlib.Path(args.index_root), doc_lang)
+    cached = locate_cached_index(pathlib.Path(args.index_root), doc_lang)
     if cached is None:
         raise SystemExit(f"No cached index for '{doc_lang}' under {args.index_root}; encoding the corpus is out of scope "
                          "(build it with the reference's encode_multilingual_corpus.py).")
@@ -145,7 +194,9 @@ def main_mono(argv: Optional[Sequence[str]] = None) -> int:
     logging.info("Cached index ready for %s: %d vectors", doc_lang, n_kept)
     pathlib.Path(args.docids_out).parent.mkdir(parents=True, exist_ok=True)
     pathlib.Path(args.docids_out).write_text(docids_text)
-    index = _place(cached["index"], args)
+    info = cached["info"]
+    index = build_device_index([(cached["index_path"], info["vec_offset"], info["ntotal"])], info["d"], _devices(args),
+                               ids=cio.read_index_ids(cached["index_path"], info), log=logging.info)
     _, qids, P, S = _load_queries(args)
     alphas = runloop.parse_alpha_list(args.cm_alphas)
     t0 = time.perf_counter()
@@ -155,52 +206,102 @@ def main_mono(argv: Optional[Sequence[str]] = None) -> int:
     return 0
 
 
-def combine_cached_indexes(cached_list, map_out_path: pathlib.Path, place):
-    """Bilingual combined index (onepass_bilingual_mix_hub_custom_lang.py:606-702) without the 17.7 M
-    Python-level reconstruct calls: map lines are taken in file order in batches of 20 000, each batch
-    sorted by int id (as the reference does), the rows gathered array-at-a-time and appended to ONE flat
-    index with ids 0..n-1.  Returns (index, id2doc, base_ids_in_first_seen_order)."""
-    dim = cached_list[0]["base_index"].d
-    combined = faiss.IndexIDMap(faiss.IndexFlatIP(dim))
-    id2doc: List[str] = []
-    bases_seen: List[str] = []
-    seen = set()
-    next_id = 0
-    with open(map_out_path, "w", encoding="utf-8") as map_fh:
-        print("derived_id\tbase_id\tlang", file=map_fh)
+def _batch_sorted_order(local_ids: np.ndarray) -> np.ndarray:
+    """The reference takes map lines in file order in batches of RECON_BATCH and sorts each batch by int id
+    (stable) before adding it (:639-641): the permutation of the map lines that gives the combined row order."""
+    if not len(local_ids):
+        return np.empty((0,), np.int64)
+    return np.concatenate([b0 + np.argsort(local_ids[b0 : b0 + RECON_BATCH], kind="stable")
+                           for b0 in range(0, len(local_ids), RECON_BATCH)])
+
+
+def combine_cached_indexes(cached_list, map_out_path: pathlib.Path, devices: Sequence[int], log=None):
+    """Bilingual combined index (onepass_bilingual_mix_hub_custom_lang.py:606-702) on the device: same row order
+    (map lines in batches of 20 000, each sorted by int id), ids 0..n-1, same ``docid_map.tsv`` -- but the rows go
+    from the language files straight into HBM (native loader), or, when the map does not list the rows in storage
+    order, through a device-side gather; the map columns are handled as arrays (pyarrow) when the files are clean.
+    Returns (index, id2doc, text of sorted unique base ids for --docids_out)."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+
+    d = cached_list[0]["info"]["d"]
+    segments, gathers = [], []  # (path, offset, rows) in combined order; per language: None or the row permutation
+    derived_parts, base_parts = [], []
+    with open(map_out_path, "wb") as map_fh:
+        map_fh.write(b"derived_id\tbase_id\tlang\n")
         for cached in cached_list:
-            lang, base_index = cached["lang"], cached["base_index"]
-            local_ids, derived, bases = [], [], []
-            with open(cached["map_path"], "r", encoding="utf-8") as fh:
-                next(fh, None)
-                for line in fh:
-                    parts = line.rstrip("\n").split("\t")
-                    if len(parts) < 3:
-                        continue
-                    try:
-                        local_ids.append(int(parts[0]))
-                    except ValueError:
-                        continue
-                    derived.append(parts[1])
-                    bases.append(parts[2])
-            lid = np.asarray(local_ids, dtype=np.int64)
-            order = np.concatenate([b0 + np.argsort(lid[b0 : b0 + RECON_BATCH], kind="stable")
-                                    for b0 in range(0, len(lid), RECON_BATCH)]) if len(lid) else np.empty((0,), np.int64)
+            lang, info = cached["lang"], cached["info"]
+            cols = cio.read_docid_columns(cached["map_path"])
+            if cols is None:  # irregular file: the literal per-line reader
+                lid, derived_l, base_l = [], [], []
+                with open(cached["map_path"], "r", encoding="utf-8") as fh:
+                    next(fh, None)
+                    for line in fh:
+                        parts = line.rstrip("\n").split("\t")
+                        if len(parts) < 3:
+                            continue
+                        try:
+                            lid.append(int(parts[0]))
+                        except ValueError:
+                            continue
+                        derived_l.append(parts[1])
+                        base_l.append(parts[2])
+                lid = np.asarray(lid, dtype=np.int64)
+                derived, base = pa.array(derived_l, type=pa.string()), pa.array(base_l, type=pa.string())
+            else:
+                lid, derived, base = cols
+            if len(lid) and (lid.min() < 0 or lid.max() >= info["ntotal"]):
+                raise SystemExit(f"docid_map.tsv of '{lang}' names row {int(lid.max())} but index.faiss holds {info['ntotal']} rows")
+            order = _batch_sorted_order(lid)
             src = lid[order]
-            rows_all = base_index.reconstruct_n(0, base_index.ntotal)
-            identity = len(src) == base_index.ntotal and np.array_equal(src, np.arange(len(src)))
-            step = 1 << 18
-            for c0 in range(0, len(src), step):
-                rows = rows_all[c0 : c0 + step] if identity else rows_all[src[c0 : c0 + step]]
-                combined.add_with_ids(rows, np.arange(next_id + c0, next_id + c0 + len(rows), dtype=np.int64))
-            for j in order:
-                id2doc.append(derived[j])
-                map_fh.write(f"{derived[j]}\t{bases[j]}\t{lang}\n")
-                if bases[j] not in seen:
-                    seen.add(bases[j])
-                    bases_seen.append(bases[j])
-            next_id += len(src)
-    return place(combined), id2doc, bases_seen
+            identity = len(src) == info["ntotal"] and bool(np.array_equal(src, np.arange(len(src))))
+            in_order = len(order) == 0 or bool(np.array_equal(order, np.arange(len(order))))
+            segments.append((cached["index_path"], info["vec_offset"], info["ntotal"] if identity else len(src)))
+            gathers.append(None if identity else src)
+            if not in_order:
+                idx = pa.array(order)
+                derived, base = derived.take(idx), base.take(idx)
+            derived_parts.append(derived)
+            base_parts.append(base)
+            if len(derived):
+                lines = pc.binary_join_element_wise(derived, base, pa.scalar(lang + "\n"), "\t")
+                map_fh.write(_arrow_string_bytes(lines))
+    if all(gx is None for gx in gathers):
+        index = build_device_index(segments, d, devices, log=log)
+    else:
+        if len(devices) > 1:
+            raise SystemExit("a docid_map.tsv that does not list the rows in storage order needs the single-GPU build "
+                             "(device-side gather); rerun with --gpus 1")
+        flat = faiss.GpuIndexFlatIP(d, device=devices[0])
+        flat.reserveMemory(sum(r for _, _, r in segments))
+        for (path, off, rows), cached, src in zip(segments, cached_list, gathers):
+            if src is None:
+                flat.add_from_file(path, off, rows)
+                continue
+            tmp = faiss.GpuIndexFlatIP(d, device=devices[0])
+            tmp.add_from_file(path, off, cached["info"]["ntotal"])
+            for c0 in range(0, len(src), 1 << 20):
+                flat.add_gather(tmp, src[c0 : c0 + (1 << 20)])
+            del tmp
+        index = faiss.IndexIDMap(faiss.IndexFlatIP(d))
+        index.index = flat
+        index._ids = [np.arange(flat.ntotal, dtype=np.int64)]
+    id2doc = pa.concat_arrays([p.cast(pa.string()) for p in derived_parts]) if derived_parts else pa.array([], type=pa.string())
+    all_base = pa.concat_arrays([p.cast(pa.string()) for p in base_parts]) if base_parts else pa.array([], type=pa.string())
+    uniq = pc.unique(all_base)
+    uniq = uniq.take(pc.sort_indices(uniq))
+    docids_text = _arrow_string_bytes(pc.binary_join_element_wise(uniq, pa.scalar("\n"), "")).decode("utf-8")
+    return index, id2doc, docids_text[:-1] if docids_text.endswith("\n") else docids_text
+
+
+def _arrow_string_bytes(arr) -> bytes:
+    """The concatenated utf-8 bytes of a pyarrow string array."""
+    if hasattr(arr, "combine_chunks"):
+        arr = arr.combine_chunks()
+    if len(arr) == 0:
+        return b""
+    off = np.frombuffer(arr.buffers()[1], dtype=np.int32, count=len(arr) + 1, offset=arr.offset * 4)
+    return arr.buffers()[2].to_pybytes()[off[0] : off[-1]]
 
 
 def main_bilingual(argv: Optional[Sequence[str]] = None) -> int:
@@ -219,13 +320,13 @@ def main_bilingual(argv: Optional[Sequence[str]] = None) -> int:
     outdir.mkdir(parents=True, exist_ok=True)
     cached_list = []
     for lang in langs:
-        c = load_cached_index(pathlib.Path(args.index_root), lang)
+        c = locate_cached_index(pathlib.Path(args.index_root), lang, cached_list[0]["info"]["d"] if cached_list else None)
         if c is None:
             raise SystemExit(f"No cached index for '{lang}' under {args.index_root}; encoding the corpus is out of scope.")
         cached_list.append(c)
-    index, id2doc, bases = combine_cached_indexes(cached_list, outdir / "docid_map.tsv", lambda ix: _place(ix, args))
+    index, id2doc, docids_text = combine_cached_indexes(cached_list, outdir / "docid_map.tsv", _devices(args), log=logging.info)
     pathlib.Path(args.docids_out).parent.mkdir(parents=True, exist_ok=True)
-    pathlib.Path(args.docids_out).write_text("\n".join(sorted(set(bases))))
+    pathlib.Path(args.docids_out).write_text(docids_text)
     if index.ntotal == 0:
         raise SystemExit("No documents indexed. Check corpus fields and filters.")
     (l1, l2), qids, P, S = _load_queries(args)

@@ -99,6 +99,21 @@ class Shard:
         p, on_dev = _ptr(x)
         check(_lib.lib().cmx_index_add(self._h, p, int(x.shape[0]), on_dev))
 
+    def add_from_file(self, path, offset: int, n: int, nthreads: int = 0):
+        """Append ``n`` rows stored as little-endian float32 at byte ``offset`` of ``path`` (the vector block of an
+        ``index.faiss``): reader threads + page-locked staging buffers overlap the file reads with the PCIe
+        copies (``cmx_index_add_from_file``).  Returns (seconds inside pread, wall seconds)."""
+        import os
+
+        sec = (C.c_double * 2)()
+        check(_lib.lib().cmx_index_add_from_file(self._h, os.fsencode(str(path)), int(offset), int(n), int(nthreads), sec))
+        return float(sec[0]), float(sec[1])
+
+    def add_gather(self, src: "Shard", rows) -> None:
+        """Append rows ``rows`` (row numbers) of another shard on the same GPU without leaving the device."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        check(_lib.lib().cmx_index_add_gather(self._h, src._h, rows.ctypes.data, int(rows.shape[0])))
+
     def reconstruct_n(self, i0: int, n: int, out=None):
         if out is None:
             out = np.empty((int(n), self.d), dtype=np.float32)

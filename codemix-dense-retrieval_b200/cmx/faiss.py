@@ -117,6 +117,13 @@ class GpuIndexFlatIP(_Searchable):
     def reset(self) -> None:
         self._shard.reset()
 
+    def add_from_file(self, path, offset: int, n: int, nthreads: int = 0):
+        """Extension: rows straight from a file's float32 block into HBM (see ``Shard.add_from_file``)."""
+        return self._shard.add_from_file(path, offset, n, nthreads)
+
+    def add_gather(self, src: "GpuIndexFlatIP", rows) -> None:
+        self._shard.add_gather(src._shard, rows)
+
     def search(self, x, k: int):
         return self._shard.search(x, k, path=self.path)
 
@@ -432,6 +439,28 @@ class IndexShardsIP(_Searchable):
             if b[g + 1] > b[g]:
                 sh.reserveMemory(b[g + 1] - b[g])
                 sh.add(rows[b[g] : b[g + 1]])
+
+    def add_from_files(self, segments) -> None:
+        """``segments`` = [(path, byte offset of the float32 block, rows), ...] in global row order: every shard
+        streams ITS row range (row i -> shard floor(i*G/n)) from the files with the native loader, all shards
+        at once -- the multi-GPU form of read_index + index_cpu_to_gpu, nothing staged in host memory."""
+        assert self.ntotal == 0, "add_from_files needs an empty index"
+        total = sum(int(r) for _, _, r in segments)
+        b = self.split(total, len(self.shards))
+
+        def load(g):
+            sh = self.shards[g]
+            if b[g + 1] > b[g]:
+                sh.reserveMemory(b[g + 1] - b[g])
+            start = 0
+            for path, off, rows in segments:
+                lo, hi = max(b[g], start), min(b[g + 1], start + int(rows))
+                if hi > lo:
+                    sh.add_from_file(path, int(off) + 4 * self.d * (lo - start), hi - lo)
+                start += int(rows)
+
+        for f in [t.submit(load, g) for g, t in enumerate(self._threads)]:
+            f.result()
 
     def reset(self) -> None:
         for s in self.shards:

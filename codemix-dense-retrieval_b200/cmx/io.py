@@ -147,6 +147,15 @@ def inspect_index(path) -> dict:
     return {"kind": kind.decode(), "d": d, "ntotal": ntotal, "vec_offset": vec_offset, "ids_offset": ids_offset}
 
 
+LAST_LOAD: dict = {}  # rows / bytes / read_s / wall_s of the last native (device-sink) load
+
+
+def sink_is_device(sink) -> bool:
+    """True for sinks whose rows live in HBM (GpuIndexFlatIP, Shard, ShardedIndex over the CUDA engine)."""
+    inner = getattr(sink, "local", sink)
+    return hasattr(inner, "add_from_file") and (hasattr(inner, "_h") or hasattr(inner, "_shard"))
+
+
 def stream_index_rows(path, sink, row0: int = 0, row1: Optional[int] = None, chunk_rows: int = _CHUNK_ROWS,
                       info: Optional[dict] = None) -> np.ndarray:
     """Feed rows [row0, row1) of an ``index.faiss`` file to ``sink.add(x)`` in chunks of ``chunk_rows``
@@ -159,6 +168,21 @@ def stream_index_rows(path, sink, row0: int = 0, row1: Optional[int] = None, chu
     row1 = ntotal if row1 is None else int(row1)
     if not (0 <= row0 <= row1 <= ntotal):
         raise RuntimeError(f"stream_index_rows: bad row range [{row0}, {row1}) of {ntotal}")
+    # a device sink takes the whole range in one native call: reader threads + pinned staging buffers
+    # overlap the file reads with the PCIe copies (cmx_index_add_from_file)
+    native = getattr(getattr(sink, "local", sink), "add_from_file", None)
+    if native is not None and sink_is_device(sink):
+        if row1 > row0:
+            stats = native(path, info["vec_offset"] + 4 * d * row0, row1 - row0)
+            LAST_LOAD.update(rows=row1 - row0, bytes=4 * d * (row1 - row0), read_s=stats[0], wall_s=stats[1])
+        if info["ids_offset"] is None:
+            return np.arange(row0, row1, dtype=np.int64)
+        with open(path, "rb") as fh:
+            fh.seek(info["ids_offset"] + 8 * row0)
+            ids = np.fromfile(fh, dtype="<i8", count=row1 - row0)
+        if ids.shape[0] != row1 - row0:
+            raise RuntimeError("read_index: truncated id_map")
+        return ids.astype(np.int64, copy=False)
     add = getattr(sink, "add_local", None) or sink.add
     with open(path, "rb") as fh:
         fh.seek(info["vec_offset"] + 4 * d * row0)
@@ -176,6 +200,19 @@ def stream_index_rows(path, sink, row0: int = 0, row1: Optional[int] = None, chu
         ids = np.fromfile(fh, dtype="<i8", count=row1 - row0)
         if ids.shape[0] != row1 - row0:
             raise RuntimeError("read_index: truncated id_map")
+    return ids.astype(np.int64, copy=False)
+
+
+def read_index_ids(path, info: Optional[dict] = None) -> Optional[np.ndarray]:
+    """The id_map of an IxMp file (None for a bare IxFI file) without touching the vectors."""
+    info = info or inspect_index(path)
+    if info["ids_offset"] is None:
+        return None
+    with open(path, "rb") as fh:
+        fh.seek(info["ids_offset"])
+        ids = np.fromfile(fh, dtype="<i8", count=info["ntotal"])
+    if ids.shape[0] != info["ntotal"]:
+        raise RuntimeError("read_index: truncated id_map")
     return ids.astype(np.int64, copy=False)
 
 
@@ -265,6 +302,40 @@ def read_docid_table(path):
         pass
     id_lookup, kept, _ = read_docid_map(path)
     return DocTable(id_lookup), "\n".join(sorted(set(kept))), len(kept)
+
+
+def read_docid_columns(path):
+    """(int ids [n] int64 numpy, derived ids, base ids) of a CLEAN ``docid_map.tsv`` -- the two id columns as
+    pyarrow string arrays, no per-line Python objects -- or None when the file needs the literal reader
+    (``read_docid_map``): CR line ends, ragged columns, a first column that is not a plain decimal."""
+    try:
+        import pyarrow as pa
+        import pyarrow.compute as pc
+        import pyarrow.csv as pcsv
+
+        with open(path, "rb") as fh:
+            header = fh.readline()
+            if b"\r" in header:
+                return None
+            names = header.decode("utf-8").rstrip("\n").split("\t")
+            if len(names) < 3 or len(set(names)) != len(names):
+                return None
+        tbl = pcsv.read_csv(
+            path,
+            parse_options=pcsv.ParseOptions(delimiter="\t", quote_char=False, escape_char=False, newlines_in_values=False),
+            convert_options=pcsv.ConvertOptions(column_types={n: pa.string() for n in names}, strings_can_be_null=False,
+                                                include_columns=names[:3]))
+        if tbl.num_rows == 0:
+            return None
+        first, derived, base = (tbl.column(i).combine_chunks() for i in range(3))
+        for col in (derived, base):
+            if col.null_count or pc.any(pc.match_substring(col, "\r")).as_py():
+                return None
+        if not pc.all(pc.match_substring_regex(first, "^-?[0-9]+$")).as_py():
+            return None
+        return pc.cast(first, pa.int64()).to_numpy(zero_copy_only=False), derived, base
+    except Exception:
+        return None
 
 
 def _docid_table_arrow(path, DocTable, StrTable):

@@ -22,58 +22,33 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-_SDT = np.dtypes.StringDType()
-
 
 # ---- alpha labels -------------------------------------------------------------
+# Interface kept verbatim from the reference (onepass_dense_mix_run_custom_lang.py:287-308): the labels are
+# the run-file names -- the resume keys of run_all_vector_pairs.sh:329-360 -- and the messages are what
+# a user of the reference sees.  Both are pinned by tests/golden/text_golden.json.
 def format_alpha(alpha: float) -> str:
-    if abs(alpha - round(alpha)) < 1e-8:
-        return str(int(round(alpha)))
-    text = f"{alpha:.4f}".rstrip("0").rstrip(".")
-    return text if text else "0"
+    """'0' / '1' for integer-valued alphas, else 4 decimals without trailing zeros ('0.1', '0.25')."""
+    nearest = round(alpha)
+    if abs(alpha - nearest) < 1e-8:
+        return str(int(nearest))
+    return f"{alpha:.4f}".rstrip("0").rstrip(".") or "0"
 
 
 def parse_alpha_list(alpha_str: str) -> List[float]:
+    """Comma-separated floats; blanks between commas are skipped, anything else that is not a float ends the job."""
     if not alpha_str:
         raise SystemExit("--cm_alphas must contain at least one value.")
     alphas: List[float] = []
-    for tok in alpha_str.split(","):
-        tok = tok.strip()
-        if not tok:
-            continue
-        try:
-            alphas.append(float(tok))
-        except ValueError as exc:
-            raise SystemExit(f"[ERROR] Could not parse alpha '{tok}': {exc}") from exc
+    for token in (t.strip() for t in alpha_str.split(",")):
+        if token:
+            try:
+                alphas.append(float(token))
+            except ValueError as exc:
+                raise SystemExit(f"[ERROR] Could not parse alpha '{token}': {exc}") from exc
     if not alphas:
         raise SystemExit("No valid alpha values parsed from --cm_alphas.")
     return alphas
-
-
-# ---- vectorised fixed-point score text ------------------------------------------
-def format_scores(D: np.ndarray, decimals: int) -> np.ndarray:
-    """Elementwise equivalent of ``f"{float(x):.{decimals}f}"`` for float32 input.
-
-    A float32 times 10**decimals (decimals <= 6) is exact in float64, so rounding
-    half-to-even on it reproduces Python's correctly rounded decimal formatting.
-    Values too large for that (|x| >= 1e11), NaN and inf take the slow exact path.
-    """
-    x = np.asarray(D, dtype=np.float32).astype(np.float64)
-    scale = 10 ** decimals
-    flat = x.reshape(-1)
-    slow = ~np.isfinite(flat) | (np.abs(flat) >= 1e11)
-    safe = np.where(slow, 0.0, flat)
-    n = np.rint(np.abs(safe) * scale).astype(np.int64)
-    ip = (n // scale).astype(_SDT)
-    fp = np.strings.zfill((n % scale).astype(_SDT), decimals)
-    sign = np.where(np.signbit(safe), "-", "").astype(_SDT)
-    txt = np.strings.add(np.strings.add(np.strings.add(sign, ip), "."), fp)
-    if slow.any():
-        idx = np.nonzero(slow)[0]
-        fmt = f"{{:.{decimals}f}}"
-        for i in idx:
-            txt[i] = fmt.format(float(flat[i]))
-    return txt.reshape(x.shape)
 
 
 class StrTable:
@@ -140,10 +115,6 @@ def _take_bytes(ptr, length) -> bytes:
         return C.string_at(ptr.value, length.value)
     finally:
         _lib.lib().cmx_free_text(ptr)
-
-
-def mono_trec_text(qids: Sequence[str], D, I, docs, tag: str = "onepass-cm", nthreads: int = 0) -> str:
-    return mono_trec_bytes(qids, D, I, docs, tag, nthreads).decode("utf-8")
 
 
 def mono_trec_bytes(qids: Sequence[str], D, I, docs, tag: str = "onepass-cm", nthreads: int = 0) -> bytes:
@@ -221,6 +192,10 @@ class BaseTable:
     (``base = did.split('#')[0]``, bases numbered in first-seen order)."""
 
     def __init__(self, id2doc: Sequence[str]):
+        if type(id2doc).__module__.startswith("pyarrow"):  # a string array (cmx.cli builds id2doc as one): no Python strings at all
+            if self._init_arrow(id2doc):
+                return
+            id2doc = id2doc.to_pylist()
         names = id2doc if isinstance(id2doc, list) else list(id2doc)
         if len(names) >= 4096 and self._init_arrow(names):  # 17.7 M ids: ~9 s instead of ~29 s of per-name Python
             return
@@ -241,7 +216,11 @@ class BaseTable:
             import pyarrow as pa
             import pyarrow.compute as pc
 
-            arr = pa.array(names, type=pa.string())
+            arr = names if isinstance(names, (pa.Array, pa.ChunkedArray)) else pa.array(names, type=pa.string())
+            if isinstance(arr, pa.ChunkedArray):
+                arr = arr.combine_chunks()
+            if pa.types.is_large_string(arr.type):
+                arr = arr.cast(pa.string())
             if not isinstance(arr, pa.Array) or arr.null_count:
                 return False
             base = pc.list_element(pc.split_pattern(arr, "#", max_splits=1), 0)
@@ -252,11 +231,6 @@ class BaseTable:
             return False
         self.docs, self.codes, self.bases = docs, np.ascontiguousarray(codes), bases
         return True
-
-
-def bilingual_texts(qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int = 0):
-    raw, col = bilingual_bytes(qids, D, I, id2doc, tag, nthreads)
-    return raw.decode("utf-8"), col.decode("utf-8")
 
 
 def bilingual_bytes(qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int = 0):
@@ -320,14 +294,6 @@ def write_bilingual_trec(raw_path, col_path, qids: Sequence[str], D, I, id2doc, 
             if t.exists():
                 t.unlink()
     return int(nraw.value), int(ncol.value)
-
-
-def bilingual_raw_text(qids, D, I, id2doc, tag: str) -> str:
-    return bilingual_texts(qids, D, I, id2doc, tag)[0]
-
-
-def collapse_by_base(qids, D, I, id2doc) -> str:
-    return bilingual_texts(qids, D, I, id2doc, "x")[1]
 
 
 def bilingual_raw_text_py(qids, D, I, id2doc, tag: str) -> str:

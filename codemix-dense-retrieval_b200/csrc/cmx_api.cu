@@ -2,10 +2,15 @@
 // orchestration (slab schedule -> scoring kernel -> compaction), the vector-mix
 // prologue and the shard merge.  Host-side control only; all arithmetic is in the
 // kernels of prologue.cu / stream_score.cu / tc_score.cu / select.cu.
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>
@@ -389,7 +394,9 @@ static int prepare_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, int 
 }
 
 // ---- prescoring resources ----------------------------------------------------------------------
-static int g_prescore = 1;  // 0: all exact scores after the last slab (experiments)
+static int g_prescore = 1;  // 0: all exact scores after the last slab; 2: cut the last slab into launches but do not prescore (experiments)
+static double g_prescore_depth = 1.5;  // est rank = depth x the expected rank of the final k-th best
+static int g_prescore_max_sub = kMaxSub;
 constexpr int64_t kSubRows = 180 * 1024;  // rows per scoring launch of a prescored last slab (>= 2 ms of tensor work)
 
 static int ensure_side(cmx_index* ix) {
@@ -453,7 +460,7 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
   // launch -- gives exact scores to the likely winners found so far (select.cu).
   int nsub = 1;
   if (rescore && !safe && g_prescore && nslabs >= 2 && prescore_smem_bytes(ix->d) <= kPrescoreMaxSmem) {
-    nsub = (int)std::min<int64_t>(kMaxSub, std::max<int64_t>(1, pl.rows[nslabs - 1] / kSubRows));
+    nsub = (int)std::min<int64_t>(g_prescore_max_sub, std::max<int64_t>(1, pl.rows[nslabs - 1] / kSubRows));
     CMX_TRY(ensure_side(ix));
     CMX_TRY(ensure_buf(&ix->snap, &ix->snap_cap, (int64_t)(kMaxSub + 1) * nq_pad));
     CMX_TRY(ensure_buf(&ix->est_buf, &ix->est_cap, nq_pad));
@@ -485,7 +492,7 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
         CMX_TRY(launch_snapshot_counts(ix->ws, nq, ix->snap, st));
         CMX_CUDA(cudaEventRecord(ix->ev_sub[0], st));
         CMX_CUDA(cudaStreamWaitEvent(ix->side, ix->ev_sub[0], 0));
-        CMX_TRY(launch_prescore(ix->X, ix->d, q_d, ix->ws, nq, nullptr, ix->snap, ix->side));
+        if (g_prescore == 1) CMX_TRY(launch_prescore(ix->X, ix->d, q_d, ix->ws, nq, nullptr, ix->snap, ix->side));
         const int64_t blocks = rows / 256;  // whole 256-row blocks (a speculative / geometric slab always is)
         int64_t b0 = 0;
         for (int i = 0; i < nsub; ++i) {
@@ -497,7 +504,7 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
             CMX_TRY(launch_snapshot_counts(ix->ws, nq, snap_hi, st));
             CMX_CUDA(cudaEventRecord(ix->ev_sub[i + 1], st));
             CMX_CUDA(cudaStreamWaitEvent(ix->side, ix->ev_sub[i + 1], 0));
-            CMX_TRY(launch_prescore(ix->X, ix->d, q_d, ix->ws, nq, ix->snap + (int64_t)i * nq_pad, snap_hi, ix->side));
+            if (g_prescore == 1) CMX_TRY(launch_prescore(ix->X, ix->d, q_d, ix->ws, nq, ix->snap + (int64_t)i * nq_pad, snap_hi, ix->side));
           }
           b0 = b1;
         }
@@ -516,7 +523,7 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
       // where the FINAL k-th best is expected among the rows seen so far (x est_scale when only that share of
       // this shard's best can make the global answer); 1.5x deeper: wasted prescoring is hidden, missed is not
       const double r0 = (double)k_plan * (double)(seen + rows) / (double)n_plan * (double)est_scale;
-      est_rank = (int)std::min<double>(std::max(1.0, std::ceil(1.5 * r0)), (double)(k - 1));
+      est_rank = (int)std::min<double>(std::max(1.0, std::ceil(g_prescore_depth * r0)), (double)(k - 1));
     }
     {
       CMX_NVTX(last ? "cmx:compact+rescore" : "cmx:compact");
@@ -721,6 +728,162 @@ int cmx_index_add(cmx_index* ix, const float* x, int64_t n, int x_on_device) {
     memcpy(&nrm, &bits[1], sizeof(float));
     ix->row_norm_max = std::max(ix->row_norm_max, nrm);
   }
+  ix->n += n;
+  return CMX_OK;
+}
+
+// ---- streaming loader ---------------------------------------------------------------------------
+// fills dst[0 .. bytes) from fd at `off` with `nthreads` concurrent preads; returns false on a short read / error
+static bool pread_parallel(int fd, char* dst, int64_t off, int64_t bytes, int nthreads) {
+  nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, bytes / (1 << 20)));
+  std::vector<std::thread> th;
+  std::vector<int> ok((size_t)nthreads, 1);
+  for (int t = 0; t < nthreads; ++t) {
+    const int64_t a = bytes * t / nthreads, b = bytes * (t + 1) / nthreads;
+    th.emplace_back([=, &ok]() {
+      int64_t done = a;
+      while (done < b) {
+        const ssize_t r = pread(fd, dst + done, (size_t)std::min<int64_t>(b - done, 1 << 30), (off_t)(off + done));
+        if (r <= 0) { ok[(size_t)t] = 0; return; }
+        done += r;
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  for (int v : ok)
+    if (!v) return false;
+  return true;
+}
+
+int cmx_index_add_from_file(cmx_index* ix, const char* path, int64_t offset, int64_t n, int nthreads, double* seconds_out) {
+  CMX_CHECK(ix != nullptr && path != nullptr, "null argument");
+  CMX_CHECK(offset >= 0 && n >= 0, "bad range");
+  if (n == 0) return CMX_OK;
+  CMX_CHECK(ix->n + n < (int64_t)0x7fffff00, "index would exceed 2^31 rows per shard");
+  DevGuard g(ix->device);
+  ix->pending = false;
+  CMX_NVTX("cmx:add_from_file");
+  const auto t_begin = std::chrono::steady_clock::now();
+  const int fd = open(path, O_RDONLY);
+  CMX_CHECK(fd >= 0, "cannot open %s: %s", path, strerror(errno));
+  struct Closer { int fd; ~Closer() { close(fd); } } closer{fd};
+  const int64_t row_bytes = (int64_t)ix->d * 4;
+  {
+    const off_t size = lseek(fd, 0, SEEK_END);
+    CMX_CHECK(size >= 0 && offset + n * row_bytes <= (int64_t)size, "%s holds fewer than %lld rows of %d floats at offset %lld", path,
+              (long long)n, ix->d, (long long)offset);
+  }
+  CMX_TRY(grow_store(ix, ix->n + n));
+  if (nthreads <= 0) nthreads = (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency() / 2));
+  // three page-locked staging buffers: chunk c+1 is being read while chunk c crosses PCIe
+  constexpr int NB = 3;
+  const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)64 << 20) / row_bytes);
+  const int64_t nchunks = (n + chunk_rows - 1) / chunk_rows;
+  char* buf[NB] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[NB] = {nullptr, nullptr, nullptr};
+  cudaStream_t st = nullptr;
+  int rc = CMX_OK;
+  auto cleanup = [&]() {
+    for (int i = 0; i < NB; ++i) {
+      if (buf[i]) cudaFreeHost(buf[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    if (st) cudaStreamDestroy(st);
+  };
+  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  for (int i = 0; i < NB && e == cudaSuccess; ++i) {
+    e = cudaHostAlloc((void**)&buf[i], (size_t)(chunk_rows * row_bytes), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaMemsetAsync(ix->absmax_dev, 0, 2 * sizeof(uint32_t), st);
+  if (e != cudaSuccess) { set_error("loader setup failed: %s", cudaGetErrorString(e)); cleanup(); return CMX_ERR_CUDA; }
+  float* dst0 = ix->X + ix->n * ix->d;
+  double t_read = 0.0;
+  // the reader runs one chunk ahead of the copy engine
+  std::thread reader;
+  bool read_ok = true;
+  auto start_read = [&](int64_t c) {
+    const int64_t r0 = c * chunk_rows, rows = std::min(chunk_rows, n - r0);
+    reader = std::thread([&, c, r0, rows]() {
+      const auto t0 = std::chrono::steady_clock::now();
+      read_ok = pread_parallel(fd, buf[c % NB], offset + r0 * row_bytes, rows * row_bytes, nthreads);
+      t_read += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    });
+  };
+  start_read(0);
+  for (int64_t c = 0; c < nchunks && rc == CMX_OK; ++c) {
+    reader.join();
+    if (!read_ok) { set_error("short read from %s (chunk %lld)", path, (long long)c); rc = CMX_ERR_INVALID; break; }
+    if (c + 1 < nchunks) {
+      // buffer (c+1) % NB was last used by chunk c+1-NB: its copy must have left the host
+      if (c + 1 >= NB && cudaEventSynchronize(ev[(c + 1) % NB]) != cudaSuccess) { set_error("loader: event wait failed"); rc = CMX_ERR_CUDA; break; }
+      start_read(c + 1);
+    }
+    const int64_t r0 = c * chunk_rows, rows = std::min(chunk_rows, n - r0);
+    float* dst = dst0 + r0 * ix->d;
+    e = cudaMemcpyAsync(dst, buf[c % NB], (size_t)(rows * row_bytes), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(ev[c % NB], st);
+    if (e != cudaSuccess) { set_error("loader: H2D copy failed: %s", cudaGetErrorString(e)); rc = CMX_ERR_CUDA; break; }
+    // max |x| and max row norm of the chunk (operand scale / error bound of the tensor path), behind the copy
+    rc = launch_absmax(dst, rows * (int64_t)ix->d, ix->absmax_dev, st);
+    if (rc == CMX_OK) rc = launch_row_norm_max(dst, rows, ix->d, ix->absmax_dev + 1, st);
+  }
+  if (reader.joinable()) reader.join();
+  uint32_t bits[2] = {0, 0};
+  if (rc == CMX_OK) {
+    e = cudaMemcpyAsync(bits, ix->absmax_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("loader: %s", cudaGetErrorString(e)); rc = CMX_ERR_CUDA; }
+  } else {
+    cudaStreamSynchronize(st);
+  }
+  cleanup();
+  if (rc != CMX_OK) return rc;
+  ix->absmax_bits = std::max(ix->absmax_bits, bits[0]);
+  float nrm;
+  memcpy(&nrm, &bits[1], sizeof(float));
+  ix->row_norm_max = std::max(ix->row_norm_max, nrm);
+  ix->n += n;
+  if (seconds_out) {
+    seconds_out[0] = t_read;
+    seconds_out[1] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  }
+  return CMX_OK;
+}
+
+// rows[i] of `src` (same device) -> appended to `ix`: the device-side form of the reference's
+// np.vstack([base_index.reconstruct(e[0]) for e in batch]) (onepass_bilingual_mix_hub_custom_lang.py:644)
+int cmx_index_add_gather(cmx_index* ix, const cmx_index* src, const int64_t* rows, int64_t n) {
+  CMX_CHECK(ix && src && (rows || n == 0), "null argument");
+  CMX_CHECK(ix != src, "source and destination must differ");
+  CMX_CHECK(ix->d == src->d && ix->device == src->device, "gather needs two indexes of one dimension on one device");
+  if (n == 0) return CMX_OK;
+  CMX_CHECK(ix->n + n < (int64_t)0x7fffff00, "index would exceed 2^31 rows per shard");
+  for (int64_t i = 0; i < n; ++i)
+    CMX_CHECK(rows[i] >= 0 && rows[i] < src->n, "gather: row %lld out of range (source has %lld)", (long long)rows[i], (long long)src->n);
+  DevGuard g(ix->device);
+  ix->pending = false;
+  CMX_TRY(grow_store(ix, ix->n + n));
+  int64_t* rows_d = nullptr;
+  CMX_CUDA(cudaMalloc((void**)&rows_d, (size_t)n * sizeof(int64_t)));
+  cudaError_t e = cudaMemcpy(rows_d, rows, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice);
+  int rc = e == cudaSuccess ? CMX_OK : CMX_ERR_CUDA;
+  float* dst = ix->X + ix->n * ix->d;
+  if (rc == CMX_OK) rc = launch_gather_rows(src->X, rows_d, n, ix->d, dst, 0);
+  if (rc == CMX_OK && cudaMemset(ix->absmax_dev, 0, 2 * sizeof(uint32_t)) != cudaSuccess) rc = CMX_ERR_CUDA;
+  if (rc == CMX_OK) rc = launch_absmax(dst, n * (int64_t)ix->d, ix->absmax_dev, 0);
+  if (rc == CMX_OK) rc = launch_row_norm_max(dst, n, ix->d, ix->absmax_dev + 1, 0);
+  uint32_t bits[2] = {0, 0};
+  if (rc == CMX_OK && cudaMemcpy(bits, ix->absmax_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) rc = CMX_ERR_CUDA;
+  cudaFree(rows_d);
+  if (rc != CMX_OK) {
+    if (rc == CMX_ERR_CUDA) set_error("gather failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+  }
+  ix->absmax_bits = std::max(ix->absmax_bits, bits[0]);
+  float nrm;
+  memcpy(&nrm, &bits[1], sizeof(float));
+  ix->row_norm_max = std::max(ix->row_norm_max, nrm);
   ix->n += n;
   return CMX_OK;
 }
@@ -1127,9 +1290,14 @@ int cmx_peer_broadcast(const void* src, void* const* dsts, int ndst, int64_t byt
 
 int cmx_host_register(void* p, int64_t bytes, void** dev_ptr) {
   CMX_CHECK(p && bytes > 0 && dev_ptr, "bad argument");
-  cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
-  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); e = cudaSuccess; }
-  CMX_CUDA(e);
+  // memory that is already page-locked (cudaHostAlloc, torch pin_memory, an earlier registration) only needs its alias
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer != nullptr) {
+    *dev_ptr = a.devicePointer;
+    return CMX_OK;
+  }
+  cudaGetLastError();
+  CMX_CUDA(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
   CMX_CUDA(cudaHostGetDevicePointer(dev_ptr, p, 0));
   return CMX_OK;
 }
@@ -1238,7 +1406,13 @@ CMX_API int cmx_debug_plan_ranks(int64_t ntotal, int k, int cap, int rescore, in
   for (int i = 0; i < (int)pl.rows.size() && i < max_slabs; ++i) ranks_out[i] = pl.spec_rank[(size_t)i];
   return CMX_OK;
 }
-CMX_API int cmx_debug_set_prescore(int on) { g_prescore = on ? 1 : 0; return CMX_OK; }
+CMX_API int cmx_debug_set_prescore(int mode) { g_prescore = mode; return CMX_OK; }
+CMX_API int cmx_debug_set_prescore_params(double depth, int pad_smem_bytes, int max_sub) {
+  g_prescore_depth = depth > 0 ? depth : 1.5;
+  set_prescore_pad(pad_smem_bytes);
+  g_prescore_max_sub = max_sub >= 1 && max_sub <= kMaxSub ? max_sub : kMaxSub;
+  return CMX_OK;
+}
 /* test hook: the APPROXIMATE scores the one-pass tensor scorer produces (rescore precision), for the `nrows` (a multiple
  * of 256, <= the candidate capacity) row positions starting at position `pos0` of the processing order.  q, scores_out
  * [nq, nrows], rows_out [nq, nrows] (corpus row of each score; -1 = padding) and margin_out [nq] (= 2 eps(q)) are device

@@ -153,6 +153,7 @@ int launch_fill_f32(float* out, int64_t n, float v, cudaStream_t st);
 int launch_publish_flag(const uint32_t* overflow, uint32_t extra, uint32_t* flag_out, cudaStream_t st);
 int launch_max_bounds(const float* const* parts, int nparts, float* out2, cudaStream_t st);
 int launch_peer_broadcast(const void* src, void* const* dsts, int ndst, int64_t bytes, cudaStream_t st);
+int launch_gather_rows(const float* X, const int64_t* rows_dev, int64_t n, int d, float* dst, cudaStream_t st);
 int launch_decode_keys(const uint64_t* keys, int64_t n, float* scores, int64_t* rows, cudaStream_t st);
 
 int launch_stream_score(const float* X, int64_t row0, int64_t nrows, int d, const float* Q,
@@ -191,6 +192,7 @@ int launch_snapshot_counts(const SearchWs& ws, int64_t nq, uint32_t* snap, cudaS
 // that reach ws.est[q]; meant to run on a second stream beside the scoring kernel
 constexpr int kPrescoreMaxSmem = 16 * 1024;  // the query copy must fit next to the resident scoring CTA
 int prescore_smem_bytes(int d);
+void set_prescore_pad(int bytes);
 int launch_prescore(const float* X, int d, const float* Q, const SearchWs& ws, int64_t nq, const uint32_t* lo,
                     const uint32_t* hi, cudaStream_t st);
 // rescore mode: exact fp32 scores of every surviving candidate from the fp32 row store, then

@@ -409,6 +409,30 @@ int launch_peer_broadcast(const void* src, void* const* dsts, int ndst, int64_t 
   return CMX_OK;
 }
 
+// dst[i, :] = X[rows[i], :]  (one warp per row, 128-bit when d % 4 == 0)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ X, const int64_t* __restrict__ rows, int64_t n,
+                                                          int d, float* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+    const float* s = X + rows[i] * d;
+    float* o = dst + i * d;
+    if ((d & 3) == 0) {
+      for (int j = lane; j < (d >> 2); j += 32) reinterpret_cast<float4*>(o)[j] = reinterpret_cast<const float4*>(s)[j];
+    } else {
+      for (int j = lane; j < d; j += 32) o[j] = s[j];
+    }
+  }
+}
+int launch_gather_rows(const float* X, const int64_t* rows_dev, int64_t n, int d, float* dst, cudaStream_t st) {
+  if (n <= 0) return CMX_OK;
+  int64_t blocks = (n + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, rows_dev, n, d, dst);
+  CMX_LAUNCHED();
+  return CMX_OK;
+}
+
 // test hook: candidate keys -> (score, row)
 __global__ void decode_keys_kernel(const uint64_t* __restrict__ keys, int64_t n, float* __restrict__ scores, int64_t* __restrict__ rows) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;

@@ -310,6 +310,10 @@ __device__ __forceinline__ float warp_reduce_sum(float acc) {
   return acc;
 }
 
+// STREAM: row loads marked evict-first (ld.global.cs) -- prescore_kernel runs beside the scoring kernel, whose
+// corpus tiles and query planes live in L2; 4 KB gathers that are used once must not push them out.  The
+// arithmetic is the same either way.
+template <bool STREAM>
 __device__ __forceinline__ void exact_dot_pair(const float* __restrict__ x0, const float* __restrict__ x1,
                                                const float* qv, int d, int lane, float& out0, float& out1) {
   float acc0 = 0.f, acc1 = 0.f;
@@ -319,7 +323,7 @@ __device__ __forceinline__ void exact_dot_pair(const float* __restrict__ x0, con
     const float4* q4 = reinterpret_cast<const float4*>(qv);
 #pragma unroll 4
     for (int j = lane; j < (d >> 2); j += 32) {
-      const float4 a = a4[j], b = b4[j], c = q4[j];
+      const float4 a = STREAM ? __ldcs(a4 + j) : a4[j], b = STREAM ? __ldcs(b4 + j) : b4[j], c = q4[j];
       acc0 = fmaf(a.x, c.x, acc0); acc0 = fmaf(a.y, c.y, acc0); acc0 = fmaf(a.z, c.z, acc0); acc0 = fmaf(a.w, c.w, acc0);
       acc1 = fmaf(b.x, c.x, acc1); acc1 = fmaf(b.y, c.y, acc1); acc1 = fmaf(b.z, c.z, acc1); acc1 = fmaf(b.w, c.w, acc1);
     }
@@ -380,7 +384,7 @@ prescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q,
       const uint32_t row0 = key_row(__shfl_sync(0xffffffffu, key, j0));
       const uint32_t row1 = key_row(__shfl_sync(0xffffffffu, key, j1));
       float s0, s1;
-      exact_dot_pair(X + (int64_t)row0 * d, X + (int64_t)row1 * d, qv_pre, d, lane, s0, s1);
+      exact_dot_pair<true>(X + (int64_t)row0 * d, X + (int64_t)row1 * d, qv_pre, d, lane, s0, s1);
       if (lane == 0) {
         buf[base + j0] = s0 > CMX_NEG_PAD ? make_key_exact(s0, row0) : 0ull;
         if (j1 != j0) buf[base + j1] = s1 > CMX_NEG_PAD ? make_key_exact(s1, row1) : 0ull;
@@ -402,16 +406,20 @@ int launch_snapshot_counts(const SearchWs& ws, int64_t nq, uint32_t* snap, cudaS
 }
 
 int prescore_smem_bytes(int d) { return (d * (int)sizeof(float) + 15) / 16 * 16; }
+static int g_prescore_pad = 0;  // extra dynamic smem per CTA: bounds how many prescore CTAs share an SM (experiments)
+void set_prescore_pad(int bytes) { g_prescore_pad = bytes < 0 ? 0 : bytes; }
 
 int launch_prescore(const float* X, int d, const float* Q, const SearchWs& ws, int64_t nq, const uint32_t* lo,
                     const uint32_t* hi, cudaStream_t st) {
   if (nq == 0) return CMX_OK;
-  const int smem = prescore_smem_bytes(d);
+  int smem = prescore_smem_bytes(d);
   CMX_CHECK(smem <= kPrescoreMaxSmem, "prescore: d=%d too large", d);
+  if (smem < g_prescore_pad) smem = g_prescore_pad;
   // same shared-memory carveout as the persistent scoring CTA it has to run beside
   static bool configured = false;
   if (!configured) {
     CMX_CUDA(cudaFuncSetAttribute(prescore_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CMX_CUDA(cudaFuncSetAttribute(prescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     configured = true;
   }
   prescore_kernel<<<(unsigned)nq, kPreThreads, smem, st>>>(X, d, Q, ws.cand, lo, hi, ws.est, ws.cap);
@@ -499,7 +507,7 @@ rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, 
     const uint32_t row0 = key_row(keys[i]);
     const uint32_t row1 = two ? key_row(keys[i + 1]) : row0;
     float acc0, acc1;
-    exact_dot_pair(X + (int64_t)row0 * d, X + (int64_t)row1 * d, qv, d, lane, acc0, acc1);
+    exact_dot_pair<false>(X + (int64_t)row0 * d, X + (int64_t)row1 * d, qv, d, lane, acc0, acc1);
     __syncwarp();
     if (lane == 0) {
       keys[i] = acc0 > CMX_NEG_PAD ? make_key_exact(acc0, row0) : 0ull;

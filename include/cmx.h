@@ -83,6 +83,17 @@ CMX_API int cmx_index_reserve(cmx_index* ix, int64_t n);
  * Python IndexIDMap)  onepass_dense_mix_run_custom_lang.py:719,
  * onepass_bilingual_mix_hub_custom_lang.py:646,672, encode_multilingual_corpus.py:440 */
 CMX_API int cmx_index_add(cmx_index* ix, const float* x, int64_t n, int x_on_device);
+/* replaces: faiss.read_index(path) + index_cpu_to_gpu (onepass_dense_mix_run_custom_lang.py:250,658-664) for the
+ * vector block of an index.faiss: appends the n rows stored row-major as little-endian float32 at byte `offset`
+ * of `path`.  Reader threads (nthreads <= 0: automatic) fill page-locked staging buffers while the previous chunk
+ * crosses PCIe; nothing but the staging buffers lives in host memory.  seconds_out (may be NULL): [0] = time spent
+ * inside pread, [1] = wall time of the call. */
+CMX_API int cmx_index_add_from_file(cmx_index* ix, const char* path, int64_t offset, int64_t n, int nthreads,
+                                    double* seconds_out);
+/* replaces: np.vstack([base_index.reconstruct(i) for i in batch]) + add_with_ids of the bilingual combined-index
+ * build (onepass_bilingual_mix_hub_custom_lang.py:644-646): appends rows[0..n) (host array of row numbers) of
+ * `src` -- another index on the same device -- without the rows leaving the GPU. */
+CMX_API int cmx_index_add_gather(cmx_index* ix, const cmx_index* src, const int64_t* rows, int64_t n);
 CMX_API int cmx_index_reset(cmx_index* ix);
 CMX_API int cmx_index_ntotal(const cmx_index* ix, int64_t* out);
 CMX_API int cmx_index_dim(const cmx_index* ix, int* out);

@@ -113,6 +113,56 @@ def test_bilingual_cli(tmp_path):
     assert meta["index"]["size"] == 2 * N and meta["topk"] == 200
 
 
+def test_bilingual_cli_sharded_and_unordered_map(tmp_path, monkeypatch):
+    """The combined index on three shards (one GPU here) gives byte-identical run files; a docid_map.tsv that
+    lists the rows in another order than they are stored takes the device-side gather and reproduces the
+    reference's row order (map lines in batches, each batch sorted by int id)."""
+    from cmx import cli
+    from cmx import io as cio
+
+    rng = np.random.default_rng(33)
+    d, N, nq = 64, 2500, 17
+    Xen, Xzh = _unit(rng, N, d), _unit(rng, N, d)
+    base = [str(900 + i) for i in range(N)]
+    _make_lang_index(tmp_path / "idx", "english", Xen, base)
+    _make_lang_index(tmp_path / "idx", "chinese", Xzh, base)
+    qids, P, S = _make_queries(tmp_path, rng, nq, d)
+
+    def run(outname, index_root):
+        rc = cli.main(["bilingual", "--langs", "english,chinese", "--index_root", str(index_root),
+                       "--query_tsv", f"en={tmp_path / 'queries.en.tsv'}", "--query_tsv", f"zh={tmp_path / 'queries.zh.tsv'}",
+                       "--cm_alphas", "0.25,1", "--query_cache_dir", str(tmp_path / "qcache"), "--outdir", str(tmp_path / outname),
+                       "--docids_out", str(tmp_path / f"{outname}.docids"), "--topk", "100", "--gpu_faiss"])
+        assert rc == 0
+        return {p.name: p.read_bytes() for p in sorted((tmp_path / outname).iterdir()) if p.suffix in (".trec", ".tsv")}
+
+    one = run("one", tmp_path / "idx")
+    monkeypatch.setenv("CMX_DEVICES", "0,0,0")
+    three = run("three", tmp_path / "idx")
+    monkeypatch.delenv("CMX_DEVICES")
+    assert one.keys() == three.keys() and all(one[k] == three[k] for k in one)
+    # a map whose lines come in reversed order: the reference sorts each batch of 20 000 lines by int id, so with
+    # fewer lines than one batch the combined row order is the storage order again -- same files
+    idx2 = tmp_path / "idx2"
+    for lang, X in (("english", Xen), ("chinese", Xzh)):
+        _make_lang_index(idx2, lang, X, base)
+        lines = (idx2 / lang / "docid_map.tsv").read_text().splitlines()
+        (idx2 / lang / "docid_map.tsv").write_text("\n".join([lines[0]] + lines[:0:-1]) + "\n")
+    rev = run("rev", idx2)
+    assert all(rev[k] == one[k] for k in one)
+    # a map that keeps only every second row: the device-side gather builds the smaller combined index
+    idx3 = tmp_path / "idx3"
+    for lang, X in (("english", Xen), ("chinese", Xzh)):
+        _make_lang_index(idx3, lang, X, base)
+        lines = (idx3 / lang / "docid_map.tsv").read_text().splitlines()
+        (idx3 / lang / "docid_map.tsv").write_text("\n".join([lines[0]] + lines[1::2]) + "\n")
+    half = run("half", idx3)
+    ml = half["docid_map.tsv"].decode().splitlines()
+    assert len(ml) == 1 + 2 * (N // 2) and ml[1] == f"{base[0]}#english\t{base[0]}\tenglish" and ml[2].startswith(f"{base[2]}#english")
+    raw = half["cm-alpha-1_raw.trec"].decode().splitlines()
+    assert len(raw) == nq * 100 and all(int(l.split()[2].split("#")[0]) % 2 == 0 for l in raw[:200])  # bases 900, 902, ...
+
+
 def test_missing_caches_stop_with_message(tmp_path):
     from cmx import cli
 

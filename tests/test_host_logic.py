@@ -26,19 +26,6 @@ def test_labels_match_golden(golden_dir):
         assert got == want
 
 
-def test_format_scores_matches_python(golden_dir):
-    g = json.loads((golden_dir / "text_golden.json").read_text())
-    sc = np.array([np.frombuffer(bytes.fromhex(h), dtype=np.float32)[0] for h in g["trec_scores_f32_hex"]])
-    rng = np.random.default_rng(5)
-    more = np.concatenate([sc, rng.uniform(-1, 1, 20000).astype(np.float32),
-                           (rng.integers(0, 20000, 5000) / 20000.0 + 0.000025).astype(np.float32),
-                           np.array([np.nan, np.inf, -np.inf, 1e12, -2.5e15], np.float32)])
-    for dec in (4, 6):
-        got = runloop.format_scores(more, dec).tolist()
-        want = [f"{float(v):.{dec}f}" for v in more]
-        assert got == want
-
-
 def _fake_results(rng, nq, k, nrows):
     D = -np.sort(-rng.uniform(-0.2, 0.9, (nq, k)).astype(np.float32), axis=1)
     I = rng.integers(0, nrows, (nq, k)).astype(np.int64)
@@ -54,7 +41,7 @@ def test_mono_text_equals_oracle_lines():
     lookup = {i: f"doc{i * 7}" for i in range(399)}
     qids = [str(100 + i) for i in range(13)]
     want = "\n".join(oracle.mono_trec_lines(qids, D, I, lookup))
-    assert runloop.mono_trec_text(qids, D, I, runloop.DocTable(lookup)) == want
+    assert runloop.mono_trec_bytes(qids, D, I, runloop.DocTable(lookup)).decode("utf-8") == want
 
 
 def test_c_formatter_matches_python_on_arbitrary_float32():
@@ -101,9 +88,9 @@ def test_bilingual_raw_and_collapse_equal_oracle():
     qids = [f"q{i}" for i in range(nq)]
     tag = "bilingual-mix-en-zh"
     raw_lines = oracle.bilingual_raw_lines(qids, D, I, id2doc, tag)
-    assert runloop.bilingual_raw_text(qids, D, I, id2doc, tag) == "".join(raw_lines)
+    assert runloop.bilingual_bytes(qids, D, I, id2doc, tag)[0].decode("utf-8") == "".join(raw_lines)
     want = oracle.collapse_run_max_text(raw_lines)
-    assert runloop.collapse_by_base(qids, D, I, id2doc) == want
+    assert runloop.bilingual_bytes(qids, D, I, id2doc, "x")[1].decode("utf-8") == want
 
 
 class _OracleIndex:
