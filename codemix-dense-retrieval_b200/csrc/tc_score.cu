@@ -38,6 +38,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // fp16 elements = 128 bytes = one swizzle-128B row
 constexpr int TC_THREADS = 192;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB per Q plane tile
+constexpr int TC_TILE_SLOTS = 4;               // depth of the tile-id ring of the dynamic scheduler
 
 // ---- PTX wrappers -------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -386,6 +387,11 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  // tile-id ring (dynamic scheduler): full[TC_TILE_SLOTS], empty[TC_TILE_SLOTS], then the ids
+  auto tid_full_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + 5 + i); };
+  auto tid_empty_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + 5 + TC_TILE_SLOTS + i); };
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 8u * (2 * STAGES + 5 + 2 * TC_TILE_SLOTS));
+  static_assert(8 * (2 * STAGES + 5 + 2 * TC_TILE_SLOTS) + 4 * TC_TILE_SLOTS <= 256, "barrier block overflows its 256 bytes");
   uint8_t* epi_smem = smem_raw + (bar_base - smem_u32(smem_raw)) + 256;  // after the barrier block
 
   const int warp = threadIdx.x >> 5;
@@ -394,6 +400,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int i = 0; i < TC_TILE_SLOTS; ++i) { mbar_init(tid_full_bar(i), 1); mbar_init(tid_empty_bar(i), 5); }  // consumers: MMA thread + 4 epilogue warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmQhi); tma_prefetch_desc(&tmQlo);
     tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
@@ -410,19 +417,35 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
 
   const int mtiles = p.mtiles;
 
+  // Dynamic tile scheduler.  Tiles are handed out in order (m fastest) from ONE global counter: a CTA that is
+  // slowed down -- by a co-resident prescore CTA, a power-management hiccup, an expensive epilogue -- simply takes
+  // fewer tiles instead of holding everybody back (a static round-robin assignment makes the launch as slow as its
+  // slowest SM), and the tiles in flight at any moment are ~gridDim consecutive ones, so the CTAs share the same 1-3
+  // corpus tiles through L2 without the progress throttle the static version needed.  The producer publishes each
+  // tile id to the MMA thread and the epilogue warps through a small ring; -1 ends the launch.
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int slot = 0;
+      uint32_t sphase = 0;
       const uint64_t pol_q = (p.flags & 1) ? kL2EvictLast : kL2EvictNormal;
       const uint64_t pol_b = (p.flags & 2) ? kL2EvictFirst : kL2EvictNormal;
-      for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+      unsigned long long t_next = atomicAdd(p.done, 1ull);
+      for (;;) {
+        const int64_t t = (int64_t)t_next;
+        const bool live = t < p.ntiles;
+        mbar_wait(tid_empty_bar(slot), sphase ^ 1u);
+        tile_ring[slot] = live ? (int)t : -1;
+        mbar_arrive(tid_full_bar(slot));  // release: the id is visible to whoever sees this phase complete
+        if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
+        if (!live) break;
+        t_next = atomicAdd(p.done, 1ull);  // the next id travels while this tile's loads are issued
         const int m = (int)(t % mtiles);
         const int64_t n = t / mtiles;
         const int32_t qrow = m * TC_BM;
         const int32_t brow = (int32_t)perm_row(p, p.row0 + n * BN);
-        throttle_wait(p.done, t, p.window);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
@@ -444,7 +467,14 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+      int slot = 0;
+      uint32_t sphase = 0;
+      for (;;) {
+        mbar_wait(tid_full_bar(slot), sphase);
+        const int t = tile_ring[slot];
+        mbar_arrive(tid_empty_bar(slot));
+        if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
+        if (t < 0) break;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -487,7 +517,15 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
     int nst = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    int slot = 0;
+    uint32_t sphase = 0;
+    for (;;) {
+      mbar_wait(tid_full_bar(slot), sphase);
+      const int64_t t = tile_ring[slot];
+      __syncwarp();  // every lane has its copy before the slot goes back to the producer
+      if (lane == 0) mbar_arrive(tid_empty_bar(slot));
+      if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
+      if (t < 0) break;
       const int m = (int)(t % mtiles);
       const int64_t n = t / mtiles;
       const int64_t q = (int64_t)m * TC_BM + lane_base + lane;
@@ -507,7 +545,6 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));  // TMEM buffer back to the MMA warp ...
-      if (threadIdx.x == 64 && p.window > 0) throttle_tile_done(p.done);
       epilogue_flush(p, stg, nst, q, inv, tile_row0);  // ... before the atomic round trip
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -1094,11 +1131,13 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   }
   p.mtiles = pair ? (int)((nq + 255) / 256) : (int)((nq + TC_BM - 1) / TC_BM);
   p.ntiles = pair ? (int64_t)p.mtiles * ((nrows + 255) / 256) : (int64_t)p.mtiles * ((nrows + bn - 1) / bn);
-  if (g_tc_window > 0 && progress != nullptr) {
-    CMX_CUDA(cudaMemsetAsync(progress, 0, sizeof(unsigned long long), st));
-    p.done = progress;
-    p.window = (long long)g_tc_window * (pair ? sm_count / 2 : sm_count);  // iterations of slack
-  }
+  // single-CTA kernel: `progress` is the tile counter of its dynamic scheduler; pair kernel: the progress
+  // counter of its throttle (static round-robin tiles)
+  CMX_CHECK(progress != nullptr, "tensor path: no tile counter");
+  CMX_CUDA(cudaMemsetAsync(progress, 0, sizeof(unsigned long long), st));
+  p.done = progress;
+  if (pair && g_tc_window > 0) p.window = (long long)g_tc_window * (sm_count / 2);  // iterations of slack
+  if (pair && g_tc_window <= 0) p.done = nullptr;
   if (pair) {
     if (split) return launch_tc_pair<3, 3>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
     return launch_tc_pair<6, 1>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);

@@ -258,8 +258,18 @@ void format_bilingual(const BiArgs& a, int nthreads, std::vector<Part>& raw, std
       return (dx > dy) - (dx < dy);
     };
     std::vector<Grp> groups;
-    std::unordered_map<int32_t, int> slot;
+    // base code -> group slot: open addressing over thread-local arrays, emptied per query by bumping a stamp --
+    // no allocation inside the loop (a std::unordered_map here made 8 threads slower than 1: one malloc per hit)
+    size_t tab_size = 64;
+    while (tab_size < 2 * (size_t)a.k) tab_size <<= 1;
+    const size_t tab_mask = tab_size - 1;
+    std::vector<int32_t> tab_code(tab_size);
+    std::vector<int> tab_slot(tab_size);
+    std::vector<uint32_t> tab_stamp(tab_size, 0u);
+    uint32_t stamp = 0;
     std::vector<int> order;
+    groups.reserve((size_t)a.k);
+    order.reserve((size_t)a.k);
     for (int64_t r = q0; r < q1; ++r) {
       const size_t qlen = (size_t)a.q.len(r);
       const size_t fixed = qlen + 4 + 1 + 12 + 1 + kMaxFixed + 1 + tag_len + 1;
@@ -267,7 +277,7 @@ void format_bilingual(const BiArgs& a, int nthreads, std::vector<Part>& raw, std
       const float* Dr = a.D + r * a.k;
       const char* qs = a.q.ptr(r);
       groups.clear();
-      slot.clear();
+      if (++stamp == 0u) { std::fill(tab_stamp.begin(), tab_stamp.end(), 0u); stamp = 1; }
       for (int j = 0; j < a.k; ++j) {
         if (j + kAhead < a.k) { const int64_t f = Ir[j + kAhead]; if (f >= 0 && f < a.dt.n) { __builtin_prefetch(a.dt.off + f); __builtin_prefetch(a.base_code + f); } }
         if (j + kAhead / 2 < a.k) { const int64_t f = Ir[j + kAhead / 2]; if (f >= 0 && f < a.dt.n) __builtin_prefetch(a.dt.buf + a.dt.off[f]); }
@@ -292,12 +302,15 @@ void format_bilingual(const BiArgs& a, int nthreads, std::vector<Part>& raw, std
         const bool neg = std::signbit(sc);  // the sign survives the text round trip even for -0.000000
         const int32_t code = a.base_code[ix];
         const Grp cand{code, small ? (int64_t)std::nearbyint(ax * 1e6) : 0, neg, !small, sc};
-        auto it = slot.find(code);
-        if (it == slot.end()) {
-          slot.emplace(code, (int)groups.size());
+        size_t h = ((uint32_t)code * 2654435761u) & tab_mask;
+        while (tab_stamp[h] == stamp && tab_code[h] != code) h = (h + 1) & tab_mask;
+        if (tab_stamp[h] != stamp) {
+          tab_stamp[h] = stamp;
+          tab_code[h] = code;
+          tab_slot[h] = (int)groups.size();
           groups.push_back(cand);
         } else {
-          Grp& g = groups[(size_t)it->second];
+          Grp& g = groups[(size_t)tab_slot[h]];
           if (cmp(cand, g) > 0) g = cand;
         }
       }
