@@ -395,8 +395,14 @@ static int prepare_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, int 
 
 // ---- prescoring resources ----------------------------------------------------------------------
 static int g_prescore = 1;  // 0: all exact scores after the last slab; 2: cut the last slab into launches but do not prescore (experiments)
-static double g_prescore_depth = 1.5;  // est rank = depth x the expected rank of the final k-th best
+// est rank = depth x the expected rank of the final k-th best.  Measured at C2 on a power-capped B200
+// (profiles/r02_prescore_experiments.md): the chip runs at its power limit while scoring, so work moved beside the
+// scoring kernel is paid for in clock -- hiding all of the rescoring (depth 1.5) slows scoring by as much as it saves;
+// depth ~0.75 (the surest winners only) is a small net gain, and only when the last slab is long.
+static double g_prescore_depth = 0.75;
+constexpr int64_t kPrescoreMinRows = 2 << 20;  // shorter last slabs: not worth the extra launches and selects
 static int g_prescore_max_sub = kMaxSub;
+static int64_t g_prescore_min_rows = kPrescoreMinRows;
 constexpr int64_t kSubRows = 180 * 1024;  // rows per scoring launch of a prescored last slab (>= 2 ms of tensor work)
 
 static int ensure_side(cmx_index* ix) {
@@ -459,7 +465,8 @@ static int search_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, float
   // cursors are snapshotted, and prescore_kernel -- on a second stream, beside the next scoring
   // launch -- gives exact scores to the likely winners found so far (select.cu).
   int nsub = 1;
-  if (rescore && !safe && g_prescore && nslabs >= 2 && prescore_smem_bytes(ix->d) <= kPrescoreMaxSmem) {
+  if (rescore && !safe && g_prescore && nslabs >= 2 && pl.rows[nslabs - 1] >= g_prescore_min_rows &&
+      prescore_smem_bytes(ix->d) <= kPrescoreMaxSmem) {
     nsub = (int)std::min<int64_t>(g_prescore_max_sub, std::max<int64_t>(1, pl.rows[nslabs - 1] / kSubRows));
     CMX_TRY(ensure_side(ix));
     CMX_TRY(ensure_buf(&ix->snap, &ix->snap_cap, (int64_t)(kMaxSub + 1) * nq_pad));
@@ -1407,8 +1414,9 @@ CMX_API int cmx_debug_plan_ranks(int64_t ntotal, int k, int cap, int rescore, in
   return CMX_OK;
 }
 CMX_API int cmx_debug_set_prescore(int mode) { g_prescore = mode; return CMX_OK; }
+CMX_API int cmx_debug_set_prescore_min_rows(int64_t rows) { g_prescore_min_rows = rows < 0 ? kPrescoreMinRows : rows; return CMX_OK; }
 CMX_API int cmx_debug_set_prescore_params(double depth, int pad_smem_bytes, int max_sub) {
-  g_prescore_depth = depth > 0 ? depth : 1.5;
+  g_prescore_depth = depth > 0 ? depth : 0.75;
   set_prescore_pad(pad_smem_bytes);
   g_prescore_max_sub = max_sub >= 1 && max_sub <= kMaxSub ? max_sub : kMaxSub;
   return CMX_OK;

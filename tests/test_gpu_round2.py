@@ -49,25 +49,29 @@ def test_prescoring_is_invisible_in_the_result():
     X, Q = _unit_cuda(N, d, 11), _unit_cuda(nq, d, 12)
     sh = Shard(d, 0)
     sh.add(X)
-    D1, I1 = sh.search(Q, k, path="tensor")
-    st1 = sh.last_stats()
-    assert st1["reruns"] == 0 and st1["score_launches"] > st1["slabs"], st1  # the last slab ran as several launches
-    _lib.check(_lib.lib().cmx_debug_set_prescore(0))
+    L = _lib.lib()
+    _lib.check(L.cmx_debug_set_prescore_min_rows(0))       # the default only prescores beside last slabs of >= 2 M rows
+    _lib.check(L.cmx_debug_set_prescore_params(1.5, 0, 8))  # deep: most of the final top-k is prescored
     try:
+        D1, I1 = sh.search(Q, k, path="tensor")
+        st1 = sh.last_stats()
+        _lib.check(L.cmx_debug_set_prescore_params(0.75, 0, 8))
+        Dd, Id = sh.search(Q, k, path="tensor")
+        _lib.check(L.cmx_debug_set_prescore(0))
         D0, I0 = sh.search(Q, k, path="tensor")
         st0 = sh.last_stats()
     finally:
-        _lib.check(_lib.lib().cmx_debug_set_prescore(1))
+        _lib.check(L.cmx_debug_set_prescore(1))
+        _lib.check(L.cmx_debug_set_prescore_params(0.75, 0, 8))
+        _lib.check(L.cmx_debug_set_prescore_min_rows(-1))
+    assert st1["reruns"] == 0 and st1["score_launches"] > st1["slabs"], st1  # the last slab ran as several launches
     assert st0["score_launches"] == st0["slabs"]
     import torch
 
-    assert torch.equal(I1, I0) and torch.equal(D1, D0)
+    assert torch.equal(I1, I0) and torch.equal(D1, D0) and torch.equal(Id, I0) and torch.equal(Dd, D0)
     Dr, Ir = _brute(X, Q, k)
     rep = oracle.compare_topk(D1.cpu().numpy(), I1.cpu().numpy(), Dr, Ir, rtol=RTOL, atol=ATOL)
     assert rep["ok"], rep
-    # repeated searches reuse the side stream / snapshots
-    D2, I2 = sh.search(Q, k, path="tensor")
-    assert torch.equal(I2, I1) and torch.equal(D2, D1)
 
 
 def test_speculative_mid_slab_equals_planned_slabs():
