@@ -904,8 +904,18 @@ tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_co
     }
   } else {
     // ===================== epilogue: one corpus row per thread =====================
+    // Survivors of one query (= one TMEM column) are counted with warp ballots; the four epilogue warps pool
+    // their counts in shared memory, ONE thread per query reserves room in the query's buffer with one global
+    // atomicAdd for the whole 128-row tile, and the keys are then stored at deterministic offsets.  (The first
+    // version issued a dependent atomicAdd per warp and column with a survivor: fine at the ~1e-4 pass rates of
+    // a last slab, but at the 1 % of a k = 1000 mid slab the serialised round trips took three times the tile's
+    // HBM time.)  The TMEM buffer goes back to the MMA warp as soon as the columns are in registers.
     const int lane_base = (warp & 3) * 32;
+    const int ew = warp & 3;  // epilogue warp number = TMEM lane quarter
     const float inv = p.q_inv_scale[0] * p.b_inv_scale;
+    uint32_t* wcnt = reinterpret_cast<uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 512);  // [4][32]
+    uint32_t* gbase = wcnt + 128;                                                                  // [32]
+    volatile uint32_t* tile_any = gbase + 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -922,34 +932,64 @@ tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_co
         if (CW == 16) tmem_ld_x16(taddr_row + (uint32_t)(c * CW), v);
         else tmem_ld_x32(taddr_row + (uint32_t)(c * CW), v);
         tmem_ld_wait();
+        if (c == NQ / CW - 1) {  // last chunk in registers: the accumulator buffer is free
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if (p.dense) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const int qj = c * CW + j;
+            if (qj < p.nq) {  // warp-uniform
+              const float sc = __uint_as_float(v[j]) * inv;
+              p.cand[(int64_t)qj * p.cap + slot] = (rvalid && sc > CMX_NEG_PAD) ? make_key(sc, (uint32_t)grow) : 0ull;
+            }
+          }
+          continue;
+        }
+        // A. per-column survivor ballots of this warp; lane j keeps the count of column j
+        uint32_t mine = 0, pass_bits = 0;
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
           const int qj = c * CW + j;
-          if (qj < p.nq) {  // warp-uniform
-            const float raw = __uint_as_float(v[j]);
-            if (p.dense) {
-              const float s = raw * inv;
-              p.cand[(int64_t)qj * p.cap + slot] = (rvalid && s > CMX_NEG_PAD) ? make_key(s, (uint32_t)grow) : 0ull;
-            } else {
-              const bool pass = rvalid && raw > tau_s[qj];
-              const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
-              if (ballot) {
-                const int leader = __ffs(ballot) - 1;
-                uint32_t base = 0;
-                if (lane == leader) base = atomicAdd(&p.cnt[qj], (uint32_t)__popc(ballot));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (pass) {
-                  const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
-                  if (pos < (uint32_t)p.cap) p.cand[(int64_t)qj * p.cap + pos] = make_key(raw * inv, (uint32_t)grow);
-                }
+          const bool pass = qj < p.nq && rvalid && __uint_as_float(v[j]) > tau_s[qj];
+          const uint32_t b = __ballot_sync(0xffffffffu, pass);
+          if (lane == j) mine = (uint32_t)__popc(b);
+          pass_bits |= pass ? (1u << j) : 0u;
+        }
+        if (lane < CW) wcnt[ew * 32 + lane] = mine;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // B. one thread per query reserves room for the whole tile
+        if (ew == 0) {
+          uint32_t total = 0;
+          if (lane < CW) total = wcnt[lane] + wcnt[32 + lane] + wcnt[64 + lane] + wcnt[96 + lane];
+          uint32_t base = 0;
+          if (total) base = atomicAdd(&p.cnt[c * CW + lane], total);
+          if (lane < CW) gbase[lane] = base;
+          const uint32_t any = __ballot_sync(0xffffffffu, total != 0);
+          if (lane == 0) *tile_any = any;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // C. store the keys: offset = tile base + the lower warps' counts + the lower lanes of this warp
+        const uint32_t any = *tile_any;
+        if (any) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            if ((any >> j) & 1u) {  // CTA-uniform
+              const bool pass = (pass_bits >> j) & 1u;
+              const uint32_t b = __ballot_sync(0xffffffffu, pass);
+              if (pass) {
+                uint32_t pos = gbase[j] + __popc(b & ((1u << lane) - 1u));
+                for (int w = 0; w < ew; ++w) pos += wcnt[w * 32 + j];
+                const int qj = c * CW + j;
+                if (pos < (uint32_t)p.cap) p.cand[(int64_t)qj * p.cap + pos] = make_key(__uint_as_float(v[j]) * inv, (uint32_t)grow);
               }
             }
           }
         }
+        if (NQ / CW > 1) asm volatile("bar.sync 1, 128;" ::: "memory");  // wcnt / gbase are reused by the next chunk
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -1052,8 +1092,9 @@ static int launch_tc_small(const __half* Bhi, const __half* Blo, int64_t plane_r
     tb_lo = tb_hi;
   }
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * ((128 * TC_BK * 2) + (NQ * TC_BK * 2));
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + NQ * sizeof(float);
-  static_assert((size_t)STAGES * STAGE_BYTES + 1024 + 256 + NQ * sizeof(float) <= 227 * 1024, "stage ring exceeds shared memory");
+  // 1024 alignment slack | 512 barriers + thresholds | 1024 survivor counts of the epilogue
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 512 + 1024;
+  static_assert((size_t)STAGES * STAGE_BYTES + 1024 + 512 + 1024 <= 227 * 1024, "stage ring exceeds shared memory");
   CMX_CUDA(cudaFuncSetAttribute(tc_score_small_kernel<NQ, STAGES, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.mtiles = 1;
   p.ntiles = (p.nrows + 127) / 128;
