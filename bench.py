@@ -679,9 +679,11 @@ def run_cmx(a) -> None:
         extras = {}
         if world == 1:
             extras["C4_small_batch"] = small_batch_configs(index, P, S, d, peaks, timer)
-            ms11, _ = timer.run(lambda: index.search_mixed(P, S, SWEEP11, k), 2, 1)
-            extras["C4_sweep11"] = {"workload": f"11 alphas x {nq} queries over {N} x {d}, k={k}, one fused call",
-                                    "ms_per_job": ms11, "queries_per_s": 11 * nq / (ms11 / 1e3)}
+        fb0 = index.fallback_steps
+        ms11, _ = timer.run(lambda: index.search_mixed(P, S, SWEEP11, k), 2, 1)
+        extras["C4_sweep11"] = {"workload": f"11 alphas x {nq} queries over {N} x {d}, k={k}, one fused call", "n_gpus": world,
+                                "ms_per_job": ms11, "queries_per_s": 11 * nq / (ms11 / 1e3),
+                                "two_phase": (index.two_phase_used and index.fallback_steps == fb0) if world > 1 else None}
         del index
         torch.cuda.empty_cache()
         if world == 1:

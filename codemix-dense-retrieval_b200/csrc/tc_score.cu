@@ -913,9 +913,10 @@ tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_co
     const int lane_base = (warp & 3) * 32;
     const int ew = warp & 3;  // epilogue warp number = TMEM lane quarter
     const float inv = p.q_inv_scale[0] * p.b_inv_scale;
-    uint32_t* wcnt = reinterpret_cast<uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 512);  // [4][32]
-    uint32_t* gbase = wcnt + 128;                                                                  // [32]
-    volatile uint32_t* tile_any = gbase + 32;
+    // two sets of {wcnt[4][32], gbase[32], any}, alternating per chunk: a warp that is already counting the next
+    // chunk (it cannot be further ahead: the next barrier needs everybody) must not disturb one still storing this one
+    uint32_t* pool = reinterpret_cast<uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 512);
+    uint32_t set = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -948,6 +949,10 @@ tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_co
           }
           continue;
         }
+        uint32_t* wcnt = pool + set * 192;           // [4][32]
+        uint32_t* gbase = wcnt + 128;                // [32]
+        volatile uint32_t* tile_any = gbase + 32;
+        set ^= 1u;
         // A. per-column survivor ballots of this warp; lane j keeps the count of column j
         uint32_t mine = 0, pass_bits = 0;
 #pragma unroll
@@ -988,7 +993,6 @@ tc_score_small_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_co
             }
           }
         }
-        if (NQ / CW > 1) asm volatile("bar.sync 1, 128;" ::: "memory");  // wcnt / gbase are reused by the next chunk
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -1092,9 +1096,9 @@ static int launch_tc_small(const __half* Bhi, const __half* Blo, int64_t plane_r
     tb_lo = tb_hi;
   }
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * ((128 * TC_BK * 2) + (NQ * TC_BK * 2));
-  // 1024 alignment slack | 512 barriers + thresholds | 1024 survivor counts of the epilogue
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 512 + 1024;
-  static_assert((size_t)STAGES * STAGE_BYTES + 1024 + 512 + 1024 <= 227 * 1024, "stage ring exceeds shared memory");
+  // 1024 alignment slack | 512 barriers + thresholds | 2 x 776 B survivor counts of the epilogue
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 512 + 2048;
+  static_assert((size_t)STAGES * STAGE_BYTES + 1024 + 512 + 2048 <= 227 * 1024, "stage ring exceeds shared memory");
   CMX_CUDA(cudaFuncSetAttribute(tc_score_small_kernel<NQ, STAGES, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.mtiles = 1;
   p.ntiles = (p.nrows + 127) / 128;
