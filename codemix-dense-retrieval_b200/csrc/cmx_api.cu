@@ -394,12 +394,15 @@ static int prepare_pass(cmx_index* ix, const float* q_d, int64_t nq, int k, int 
 }
 
 // ---- prescoring resources ----------------------------------------------------------------------
-static int g_prescore = 1;  // 0: all exact scores after the last slab; 2: cut the last slab into launches but do not prescore (experiments)
-// est rank = depth x the expected rank of the final k-th best.  Measured at C2 on a power-capped B200
-// (profiles/r02_prescore_experiments.md): the chip runs at its power limit while scoring, so work moved beside the
-// scoring kernel is paid for in clock -- hiding all of the rescoring (depth 1.5) slows scoring by as much as it saves;
-// depth ~0.75 (the surest winners only) is a small net gain, and only when the last slab is long.
-static double g_prescore_depth = 0.75;
+// Prescoring is OFF by default (mode 0).  Measured at C2 on power-capped B200s (profiles/r02_prescore_experiments.md):
+// the chip runs at its power limit while scoring, so work moved beside the scoring kernel is paid for in clock --
+// hiding all of the rescoring (depth 1.5) slows scoring by as much as it saves, the surest winners only (depth
+// 0.75) nets ~1.5 ms of 112 -- inside the box-to-box noise, and it lengthens the scoring launches the roofline is
+// computed on.  Kept selectable (cmx_debug_set_prescore) with its bit-identity test: on a part that is not
+// power-limited the overlap is worth the full 5-6 ms.
+// mode 1: on; 2: cut the last slab into launches but do not prescore (experiments).
+static int g_prescore = 0;
+static double g_prescore_depth = 0.75;  // est rank = depth x the expected rank of the final k-th best
 constexpr int64_t kPrescoreMinRows = 2 << 20;  // shorter last slabs: not worth the extra launches and selects
 static int g_prescore_max_sub = kMaxSub;
 static int64_t g_prescore_min_rows = kPrescoreMinRows;

@@ -50,7 +50,8 @@ def test_prescoring_is_invisible_in_the_result():
     sh = Shard(d, 0)
     sh.add(X)
     L = _lib.lib()
-    _lib.check(L.cmx_debug_set_prescore_min_rows(0))       # the default only prescores beside last slabs of >= 2 M rows
+    _lib.check(L.cmx_debug_set_prescore(1))                # off by default (profiles/r02_prescore_experiments.md)
+    _lib.check(L.cmx_debug_set_prescore_min_rows(0))       # and only beside last slabs of >= 2 M rows
     _lib.check(L.cmx_debug_set_prescore_params(1.5, 0, 8))  # deep: most of the final top-k is prescored
     try:
         D1, I1 = sh.search(Q, k, path="tensor")
@@ -61,7 +62,7 @@ def test_prescoring_is_invisible_in_the_result():
         D0, I0 = sh.search(Q, k, path="tensor")
         st0 = sh.last_stats()
     finally:
-        _lib.check(L.cmx_debug_set_prescore(1))
+        _lib.check(L.cmx_debug_set_prescore(0))
         _lib.check(L.cmx_debug_set_prescore_params(0.75, 0, 8))
         _lib.check(L.cmx_debug_set_prescore_min_rows(-1))
     assert st1["reruns"] == 0 and st1["score_launches"] > st1["slabs"], st1  # the last slab ran as several launches
