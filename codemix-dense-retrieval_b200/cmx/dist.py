@@ -241,6 +241,7 @@ class ShardedIndex:
         self.two_phase = True
         self.two_phase_used = False
         self.fallback_steps = 0  # steps redone without the two-phase cut (status word set on some shard)
+        self.last_status = 0     # OR of the shards' status words of the last two-phase step (0 = clean)
         self.profile = False
         self.timing = {}
         self._t_last = 0.0
@@ -389,6 +390,7 @@ class ShardedIndex:
             merge_topk_peers(D_ptrs, I_ptrs, nqt, k, (nqt * r) // G, (nqt * (r + 1)) // G, outs_D, outs_I, dev)
             fab.barrier(0)  # every shard's slice has landed in every output
             flag = int(flag_any.item())  # the step's only host synchronisation
+            self.last_status = flag
             tm("merge")
             done = flag == 0
             if done:

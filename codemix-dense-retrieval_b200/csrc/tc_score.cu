@@ -432,16 +432,20 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       uint32_t sphase = 0;
       const uint64_t pol_q = (p.flags & 1) ? kL2EvictLast : kL2EvictNormal;
       const uint64_t pol_b = (p.flags & 2) ? kL2EvictFirst : kL2EvictNormal;
-      unsigned long long t_next = atomicAdd(p.done, 1ull);
+      const bool dyn = p.window == 0;  // window > 0: static round-robin tiles + progress throttle (round-1 scheduler, kept for A/B)
+      unsigned long long t_next = dyn ? atomicAdd(p.done, 1ull) : (unsigned long long)blockIdx.x;
       for (;;) {
         const int64_t t = (int64_t)t_next;
         const bool live = t < p.ntiles;
-        mbar_wait(tid_empty_bar(slot), sphase ^ 1u);
-        tile_ring[slot] = live ? (int)t : -1;
-        mbar_arrive(tid_full_bar(slot));  // release: the id is visible to whoever sees this phase complete
-        if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
+        if (dyn) {
+          mbar_wait(tid_empty_bar(slot), sphase ^ 1u);
+          tile_ring[slot] = live ? (int)t : -1;
+          mbar_arrive(tid_full_bar(slot));  // release: the id is visible to whoever sees this phase complete
+          if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
+        }
         if (!live) break;
-        t_next = atomicAdd(p.done, 1ull);  // the next id travels while this tile's loads are issued
+        if (dyn) t_next = atomicAdd(p.done, 1ull);  // the next id travels while this tile's loads are issued
+        else { t_next = (unsigned long long)(t + gridDim.x); throttle_wait(p.done, t, p.window); }
         const int m = (int)(t % mtiles);
         const int64_t n = t / mtiles;
         const int32_t qrow = m * TC_BM;
@@ -469,12 +473,19 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       uint32_t acc_phase = 0;
       int slot = 0;
       uint32_t sphase = 0;
+      const bool dyn = p.window == 0;
+      int64_t t_static = blockIdx.x;
       for (;;) {
-        mbar_wait(tid_full_bar(slot), sphase);
-        const int t = tile_ring[slot];
-        mbar_arrive(tid_empty_bar(slot));
-        if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
-        if (t < 0) break;
+        if (dyn) {
+          mbar_wait(tid_full_bar(slot), sphase);
+          const int t = tile_ring[slot];
+          mbar_arrive(tid_empty_bar(slot));
+          if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
+          if (t < 0) break;
+        } else {
+          if (t_static >= p.ntiles) break;
+          t_static += gridDim.x;
+        }
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -519,13 +530,22 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
     uint32_t acc_phase = 0;
     int slot = 0;
     uint32_t sphase = 0;
+    const bool dyn = p.window == 0;
+    int64_t t_static = blockIdx.x;
     for (;;) {
-      mbar_wait(tid_full_bar(slot), sphase);
-      const int64_t t = tile_ring[slot];
-      __syncwarp();  // every lane has its copy before the slot goes back to the producer
-      if (lane == 0) mbar_arrive(tid_empty_bar(slot));
-      if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
-      if (t < 0) break;
+      int64_t t;
+      if (dyn) {
+        mbar_wait(tid_full_bar(slot), sphase);
+        t = tile_ring[slot];
+        __syncwarp();  // every lane has its copy before the slot goes back to the producer
+        if (lane == 0) mbar_arrive(tid_empty_bar(slot));
+        if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
+        if (t < 0) break;
+      } else {
+        t = t_static;
+        if (t >= p.ntiles) break;
+        t_static += gridDim.x;
+      }
       const int m = (int)(t % mtiles);
       const int64_t n = t / mtiles;
       const int64_t q = (int64_t)m * TC_BM + lane_base + lane;
@@ -545,6 +565,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));  // TMEM buffer back to the MMA warp ...
+      if (!dyn && threadIdx.x == 64) throttle_tile_done(p.done);
       epilogue_flush(p, stg, nst, q, inv, tile_row0);  // ... before the atomic round trip
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -1183,6 +1204,7 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   p.done = progress;
   if (pair && g_tc_window > 0) p.window = (long long)g_tc_window * (sm_count / 2);  // iterations of slack
   if (pair && g_tc_window <= 0) p.done = nullptr;
+  if (!pair && (g_tc_flags & 256)) p.window = (long long)(g_tc_window > 0 ? g_tc_window : 3) * sm_count;  // A/B: static tiles + throttle
   if (pair) {
     if (split) return launch_tc_pair<3, 3>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
     return launch_tc_pair<6, 1>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
