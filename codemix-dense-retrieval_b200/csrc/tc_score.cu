@@ -417,12 +417,13 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
 
   const int mtiles = p.mtiles;
 
-  // Dynamic tile scheduler.  Tiles are handed out in order (m fastest) from ONE global counter: a CTA that is
-  // slowed down -- by a co-resident prescore CTA, a power-management hiccup, an expensive epilogue -- simply takes
-  // fewer tiles instead of holding everybody back (a static round-robin assignment makes the launch as slow as its
-  // slowest SM), and the tiles in flight at any moment are ~gridDim consecutive ones, so the CTAs share the same 1-3
-  // corpus tiles through L2 without the progress throttle the static version needed.  The producer publishes each
-  // tile id to the MMA thread and the epilogue warps through a small ring; -1 ends the launch.
+  // Two tile schedulers (p.window selects).  Static (default): tile t = blockIdx + i * gridDim, m fastest, with the
+  // progress throttle of TcParams.  Dynamic (p.window == 0): tiles are handed out in order from ONE global counter;
+  // the producer publishes each tile id to the MMA thread and the epilogue warps through a small ring, -1 ends the
+  // launch.  A CTA that is slowed down (a co-resident prescore CTA) then takes fewer tiles instead of holding
+  // everybody back -- with prescoring on that cut its cost from +10 ms to +1..5 ms per C2 step -- but when nothing
+  // shares the SMs the static order is 3 % faster (all CTAs of the dynamic order hit the same 2-3 corpus tiles in
+  // L2 at the same moment), so static stays the default (profiles/r02_scheduler_ab.md).
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -1204,7 +1205,10 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
   p.done = progress;
   if (pair && g_tc_window > 0) p.window = (long long)g_tc_window * (sm_count / 2);  // iterations of slack
   if (pair && g_tc_window <= 0) p.done = nullptr;
-  if (!pair && (g_tc_flags & 256)) p.window = (long long)(g_tc_window > 0 ? g_tc_window : 3) * sm_count;  // A/B: static tiles + throttle
+  // single-CTA kernel: static round-robin tiles + progress throttle by default; flag 512 selects the dynamic
+  // scheduler (window = 0).  Measured alternating in one process (profiles/r02_scheduler_ab.md): static is 3 %
+  // faster when nothing shares the SMs; dynamic only pays off beside prescoring, which is off by default.
+  if (!pair && !(g_tc_flags & 512)) p.window = (long long)(g_tc_window > 0 ? g_tc_window : 3) * sm_count;
   if (pair) {
     if (split) return launch_tc_pair<3, 3>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);
     return launch_tc_pair<6, 1>(tq_hi, tq_lo, tb_hi, tb_lo, p, st, sm_count);

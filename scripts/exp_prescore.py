@@ -23,6 +23,7 @@ configs = [(0, 1.5, 0, 8), (2, 1.5, 0, 8), (1, 1.5, 0, 8), (1, 1.0, 0, 8), (1, 1
 if len(sys.argv) > 1:
     configs = [tuple(float(v) if i == 1 else int(v) for i, v in enumerate(c.split(","))) for c in sys.argv[1:]]
 ref = None
+_lib.check(L.cmx_debug_set_tensor_flags(512))  # prescoring is measured with the dynamic tile scheduler (see profiles/r02_prescore_experiments.md)
 for mode, depth, pad, msub in configs:
     _lib.check(L.cmx_debug_set_prescore(mode))
     _lib.check(L.cmx_debug_set_prescore_params(depth, pad, msub))

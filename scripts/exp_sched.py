@@ -12,9 +12,9 @@ sh = Shard(d, 0); sh.reserve(rows); bench.fill_rows(sh.add, 0, rows, d, dev, row
 P, S = bench.make_queries(nq, d, dev)
 _lib.set_profiling(True)
 L = _lib.lib()
-res = {0: [], 256: []}
+res = {512: [], 0: []}
 for rnd in range(5):
-    for flag in (0, 256):
+    for flag in (512, 0):
         _lib.check(L.cmx_debug_set_tensor_flags(flag))
         sh.search_mixed(P, S, [0.5], k)
         sc = tot = 0.0
@@ -23,7 +23,8 @@ for rnd in range(5):
             e0.record(); sh.search_mixed(P, S, [0.5], k); e1.record(); torch.cuda.synchronize()
             sc += sh.last_stats()["score_ms"]; tot += e0.elapsed_time(e1)
         res[flag].append((tot / 4, sc / 4))
-for flag, name in ((0, "dynamic"), (256, "static+throttle")):
+_lib.check(L.cmx_debug_set_tensor_flags(0))
+for flag, name in ((512, "dynamic"), (0, "static+throttle")):
     t = [a for a, _ in res[flag]]; s = [b for _, b in res[flag]]
     print(json.dumps({"scheduler": name, "rows": rows, "ms_per_step": [round(v, 2) for v in t], "score_ms": [round(v, 2) for v in s],
                       "median_ms": round(statistics.median(t), 2), "median_score_ms": round(statistics.median(s), 2)}), flush=True)
