@@ -51,7 +51,8 @@ def default_query_cache_root(repo: str, encoder: str) -> pathlib.Path:
     explicit = os.environ.get("QUERY_CACHE_ROOT")
     if explicit:
         return pathlib.Path(explicit)
-    parent = pathlib.Path(os.environ.get("QUERY_CACHE_ROOT_BASE") or (pathlib.Path.cwd() / "data"))
+    # (the reference's default base is the directory of its script; a drop-in has no such directory: cwd/data)
+    parent = pathlib.Path(os.environ.get("QUERY_CACHE_ROOT_BASE", str(pathlib.Path.cwd() / "data")))
     leaf = "enc-query-{}-{}".format(*(sanitize_tag(name.split("/")[-1]) for name in (repo, encoder)))
     return parent / leaf
 

@@ -15,7 +15,9 @@ written into this repository -- only the inputs and the outputs it produced.
 is the one external symbol ``safe_mix`` needs; its published definition is
 ``torch.nn.functional.normalize(embeddings, p=2, dim=1)`` and is bound as such.
 
-Outputs (committed): tests/golden/mix_golden.npz, tests/golden/text_golden.json
+Outputs (committed): tests/golden/mix_golden.npz, tests/golden/text_golden.json and -- ``--cli`` --
+tests/golden/cli_golden.json (the user-visible helpers of the run scripts: cache directory names, the
+--query_tsv parser and its messages).
 """
 
 from __future__ import annotations
@@ -167,5 +169,47 @@ def main():
     print("wrote", OUT / "mix_golden.npz", OUT / "text_golden.json")
 
 
+def main_cli():
+    import os
+    import re
+    import sys
+
+    ns = _load_functions(MONO, ["sanitize_tag", "default_query_cache_root", "parse_query_specs"])
+    ns.update({"re": re, "os": os, "__file__": "/nonexistent/script.py"})
+    tags = ["unicamp-dl/mmarco", "BAAI/bge-m3", "/a b/c//", "---", "", "Qwen/Qwen3-Embedding-8B", "é–x y.z_", "//", "a/b/"]
+    out = {"sanitize_tag": {"in": tags, "out": [ns["sanitize_tag"](t) for t in tags]}}
+    roots = []
+    for env in ({}, {"QUERY_CACHE_ROOT": "/data/qc"}, {"QUERY_CACHE_ROOT_BASE": "/mnt/base"}, {"QUERY_CACHE_ROOT_BASE": ""}):
+        for k in ("QUERY_CACHE_ROOT", "QUERY_CACHE_ROOT_BASE"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        for repo, enc in (("unicamp-dl/mmarco", "BAAI/bge-m3"), ("x/y z", "intfloat/multilingual-e5-large")):
+            if not env:  # the reference's default base is its own script directory: only the leaf is comparable
+                roots.append({"env": env, "repo": repo, "encoder": enc, "leaf": ns["default_query_cache_root"](repo, enc).name})
+            else:
+                roots.append({"env": env, "repo": repo, "encoder": enc, "path": str(ns["default_query_cache_root"](repo, enc))})
+    for k in ("QUERY_CACHE_ROOT", "QUERY_CACHE_ROOT_BASE"):
+        os.environ.pop(k, None)
+    out["default_query_cache_root"] = roots
+    specs_in = [(["en=a.tsv", "zh=b.tsv"], None, None), ([" hi = /x/y.tsv ", "en=/z"], None, None), (None, "q.en", "q.zh"),
+                (None, "q.en", None), (None, None, None), (["en"], None, None), (["=x", "zh=y"], None, None), (["en=", "zh=y"], None, None),
+                (["en=a"], None, None), (["en=a", "zh=b", "de=c"], None, None), (["en=a", "en=b"], None, None), ([], "a", "b"),
+                (["a=b=c", "d=e"], None, None)]
+    res = []
+    for args in specs_in:
+        try:
+            res.append([[lang, str(path)] for lang, path in ns["parse_query_specs"](*args)])
+        except SystemExit as exc:
+            res.append({"SystemExit": str(exc)})
+    out["parse_query_specs"] = {"in": [list(a) for a in specs_in], "out": res}
+    (OUT / "cli_golden.json").write_text(json.dumps(out, indent=1), encoding="utf-8")
+    print("wrote", OUT / "cli_golden.json")
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+
+    if "--cli" in sys.argv:
+        main_cli()
+    else:
+        main()

@@ -26,6 +26,50 @@ def test_labels_match_golden(golden_dir):
         assert got == want
 
 
+def test_cli_helpers_match_golden(golden_dir, monkeypatch):
+    """sanitize_tag / default_query_cache_root / parse_query_specs (rewritten here) against outputs of the
+    reference's own functions (tests/golden/make_golden.py --cli): cache directory names and parser messages
+    are what a user of the reference sees."""
+    import pathlib as pl
+
+    from cmx import cli
+
+    g = json.loads((golden_dir / "cli_golden.json").read_text())
+    assert [cli.sanitize_tag(t) for t in g["sanitize_tag"]["in"]] == g["sanitize_tag"]["out"]
+    for case in g["default_query_cache_root"]:
+        for k in ("QUERY_CACHE_ROOT", "QUERY_CACHE_ROOT_BASE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in case["env"].items():
+            monkeypatch.setenv(k, v)
+        got = cli.default_query_cache_root(case["repo"], case["encoder"])
+        if "leaf" in case:
+            assert got.name == case["leaf"] and got.parent == pl.Path.cwd() / "data"
+        else:
+            assert str(got) == case["path"]
+    for args, want in zip(g["parse_query_specs"]["in"], g["parse_query_specs"]["out"]):
+        try:
+            got = [[lang, str(path)] for lang, path in cli.parse_query_specs(*args)]
+        except SystemExit as exc:
+            got = {"SystemExit": str(exc)}
+        assert got == want, (args, got, want)
+
+
+def test_batch_sorted_order_is_the_reference_row_order():
+    """combine_cached_indexes: map lines in batches of 20 000, each batch sorted by int id (stable)."""
+    from cmx import cli
+
+    rng = np.random.default_rng(3)
+    lid = rng.permutation(50_000).astype(np.int64)
+    lid[100] = lid[7]  # a repeated id keeps file order inside its batch
+    order = cli._batch_sorted_order(lid)
+    want = []
+    for b0 in range(0, len(lid), cli.RECON_BATCH):
+        batch = sorted(range(b0, min(b0 + cli.RECON_BATCH, len(lid))), key=lambda i: lid[i])
+        want.extend(batch)
+    assert order.tolist() == want
+    assert cli._batch_sorted_order(np.empty((0,), np.int64)).shape == (0,)
+
+
 def _fake_results(rng, nq, k, nrows):
     D = -np.sort(-rng.uniform(-0.2, 0.9, (nq, k)).astype(np.float32), axis=1)
     I = rng.integers(0, nrows, (nq, k)).astype(np.int64)
