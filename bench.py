@@ -667,6 +667,9 @@ def run_cmx(a) -> None:
                                     "peak is a copy (read+write) figure, a read-only stream can exceed it",
                     "kernel_ms_per_step": per_step_score_ms, "peak_source": peaks["source"]}
 
+    mem = index.local.memory()
+    memory_gb = {k2: round(v / 1e9, 3) for k2, v in mem.items()}
+    memory_gb["ratio_to_faiss_flat"] = round((mem["store"] + mem["planes"]) / max(1, mem["faiss_flat"]), 3)
     engine_info = {"path": "tensor" if used_tensor else "stream", "precision": a.precision if used_tensor else "fp32",
                    "slabs": stats["slabs"], "reruns": stats["reruns"], "score_launches_per_step": acc["launches"] / a.steps,
                    "exchange": index.exchange_used if world > 1 else None,
@@ -742,6 +745,7 @@ def run_cmx(a) -> None:
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "select_ms_per_step": acc["select"] / a.steps,
+        "memory_gb_per_gpu": memory_gb,
         "self_check": ok,
         "parity_check": parity,
         "extra_configs": extras,

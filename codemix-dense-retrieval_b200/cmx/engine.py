@@ -85,6 +85,13 @@ class Shard:
         check(_lib.lib().cmx_index_ntotal(self._h, C.byref(n)))
         return int(n.value)
 
+    def memory(self) -> dict:
+        """Device bytes: fp32 row store, fp16 operand plane(s), search workspace, and what a FAISS flat index of the
+        same rows would hold (ntotal * d * 4)."""
+        out = (C.c_int64 * 4)()
+        check(_lib.lib().cmx_index_memory(self._h, out))
+        return {"store": int(out[0]), "planes": int(out[1]), "workspace": int(out[2]), "faiss_flat": int(out[3])}
+
     def reserve(self, n: int) -> None:
         check(_lib.lib().cmx_index_reserve(self._h, int(n)))
 

@@ -928,6 +928,18 @@ int cmx_index_raise_error_bounds(cmx_index* ix, const float* in2) {
   return CMX_OK;
 }
 
+int cmx_index_memory(const cmx_index* ix, int64_t* out4) {
+  CMX_CHECK(ix && out4, "null argument");
+  const int64_t h = (int64_t)sizeof(__half), f = (int64_t)sizeof(float);
+  out4[0] = ix->cap_rows * ix->d * f;                                                    // fp32 row store
+  out4[1] = (ix->Bhi ? ix->plane_cap : 0) * ix->d_pad * h + (ix->Blo ? ix->lo_cap : 0) * ix->d_pad * h;  // fp16 operand plane(s)
+  out4[2] = ix->cand_cap_elems * 8 + ix->tau_cap * f + ix->cnt_cap * 4 + ix->margin_cap * f + ix->snap_cap * 4 + ix->est_cap * f +
+            ix->q_cap * f + ix->p_cap * f + ix->s_cap * f + (ix->qhi_cap + ix->qlo_cap) * h + ix->D_cap * f + ix->I_cap * 8 +
+            ix->flags_cap;                                                                 // search workspace
+  out4[3] = ix->n * ix->d * f;                                                           // what a FAISS flat index of these rows holds
+  return CMX_OK;
+}
+
 int cmx_index_ntotal(const cmx_index* ix, int64_t* out) {
   CMX_CHECK(ix && out, "null argument");
   *out = ix->n;

@@ -96,6 +96,9 @@ CMX_API int cmx_index_add_from_file(cmx_index* ix, const char* path, int64_t off
 CMX_API int cmx_index_add_gather(cmx_index* ix, const cmx_index* src, const int64_t* rows, int64_t n);
 CMX_API int cmx_index_reset(cmx_index* ix);
 CMX_API int cmx_index_ntotal(const cmx_index* ix, int64_t* out);
+/* device bytes held by the index: out4 = {fp32 row store, fp16 operand plane(s), search workspace, ntotal*d*4 = what
+ * a FAISS flat index of the same rows holds}.  Default precision: store + one plane = 1.5x a FAISS flat index. */
+CMX_API int cmx_index_memory(const cmx_index* ix, int64_t* out4);
 CMX_API int cmx_index_dim(const cmx_index* ix, int* out);
 CMX_API int cmx_index_device(const cmx_index* ix, int* out);
 /* replaces: base_index.reconstruct(i[, out])  onepass_dense_mix_run_custom_lang.py:268-269,

@@ -243,6 +243,30 @@ def test_two_gpu_shards_one_process_if_available():
     assert np.array_equal(Is, np.asarray(I1)) and np.array_equal(Ds, np.asarray(D1))
 
 
+def test_memory_accounting_is_bounded():
+    """Default precision = fp32 store + ONE fp16 plane = 1.5x a FAISS flat index (+ a workspace that does not grow
+    with the corpus); the split precision adds the second plane (2x)."""
+    from cmx.engine import Shard
+
+    N, d = 200_000, 1024
+    X = _unit_cuda(N, d, 31)
+    Q = _unit_cuda(700, d, 32)
+    sh = Shard(d, 0)
+    sh.reserve(N)
+    sh.add(X)
+    m0 = sh.memory()
+    assert m0["store"] == m0["faiss_flat"] == N * d * 4 and m0["planes"] == 0  # planes are built by the first tensor-path search
+    sh.search(Q, 1000, path="tensor")
+    m1 = sh.memory()
+    assert m1["planes"] == N * d * 2 and (m1["store"] + m1["planes"]) == 1.5 * m1["faiss_flat"]
+    ws = m1["workspace"]
+    assert 700 * 8192 * 8 <= ws <= 700 * 8192 * 8 + 64 * (1 << 20)  # candidate buffers dominate: [nq, 8192] keys
+    sh.set_precision("split")
+    sh.search(Q, 1000, path="tensor")
+    m2 = sh.memory()
+    assert m2["planes"] == 2 * N * d * 2 and m2["workspace"] <= ws + 16 * (1 << 20)
+
+
 def test_index_fixture_streams_into_a_gpu_index(tmp_path):
     """read_index_to_gpu on an index.faiss assembled with bare struct.pack (tests/test_host_logic.py)."""
     import cmx.faiss as faiss
