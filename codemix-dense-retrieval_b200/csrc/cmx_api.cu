@@ -99,7 +99,7 @@ struct cmx_index {
   uint32_t* q_absmax = nullptr;
   float* margin_buf = nullptr;
   unsigned long long* progress = nullptr;  // tile-progress counter of the tensor kernels
-  // two-phase (sharded) search state between cmx_search_mixed_begin and cmx_search_end
+  // two-phase (sharded) search state between cmx_search_begin and cmx_search_end
   bool pending = false;  // cleared by every entry point that touches the workspace or the row store
   int64_t pend_nq = 0, pend_id_base = 0;
   int pend_k = 0;
