@@ -104,6 +104,7 @@ class SymmFabric:
         self.rank = dist.get_rank(group)
         self.device = torch.device("cuda", device)
         self._hdl = None
+        self._bar_buf = None
         self._shm_serial = 0
 
     def alloc(self, dtype, numel: int):
@@ -111,11 +112,16 @@ class SymmFabric:
 
         t = symm_mem.empty((max(1, int(numel)),), dtype=dtype, device=self.device)
         hdl = symm_mem.rendezvous(t, self.group)
-        if self._hdl is None:
-            self._hdl = hdl
         return t, [int(p) for p in hdl.buffer_ptrs]
 
     def barrier(self, channel: int = 0) -> None:
+        if self._hdl is None:
+            # the barrier's signal pads belong to an allocation: a dedicated one that lives as long as the fabric (the
+            # search buffers are re-allocated when the batch shape changes)
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self._bar_buf = symm_mem.empty((64,), dtype=torch.float32, device=self.device)
+            self._hdl = symm_mem.rendezvous(self._bar_buf, self.group)
         self._hdl.barrier(channel=channel)  # a kernel on the current stream: no host synchronisation
 
     def all_ok(self, ok: bool) -> bool:
