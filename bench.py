@@ -674,7 +674,8 @@ def run_cmx(a) -> None:
                    "slabs": stats["slabs"], "reruns": stats["reruns"], "score_launches_per_step": acc["launches"] / a.steps,
                    "exchange": index.exchange_used if world > 1 else None,
                    "two_phase_rescore": index.two_phase_used if world > 1 else None,
-                   "fallback_steps": index.fallback_steps if world > 1 else None}
+                   "fallback_steps": index.fallback_steps if world > 1 else None,
+                   "fallback_chunks": index.fallback_chunks if world > 1 else None}
     # ---- the other BASELINE configs (untimed w.r.t. the headline) ----
     extras = None
     headline_shape = (N, d, nq, k) == (N_FULL, D_FULL, NQ_FULL, K_FULL) and a.path == "auto"
@@ -682,11 +683,12 @@ def run_cmx(a) -> None:
         extras = {}
         if world == 1:
             extras["C4_small_batch"] = small_batch_configs(index, P, S, d, peaks, timer)
-        fb0 = index.fallback_steps
+        fb0, fc0 = index.fallback_steps, index.fallback_chunks
         ms11, _ = timer.run(lambda: index.search_mixed(P, S, SWEEP11, k), 2, 1)
         extras["C4_sweep11"] = {"workload": f"11 alphas x {nq} queries over {N} x {d}, k={k}, one fused call", "n_gpus": world,
                                 "ms_per_job": ms11, "queries_per_s": 11 * nq / (ms11 / 1e3),
-                                "two_phase": (index.two_phase_used and index.fallback_steps == fb0) if world > 1 else None}
+                                "two_phase": (index.two_phase_used and index.fallback_steps == fb0) if world > 1 else None,
+                                "chunks_redone": (index.fallback_chunks - fc0) if world > 1 else None}
         del index
         torch.cuda.empty_cache()
         if world == 1:

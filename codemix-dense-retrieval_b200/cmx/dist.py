@@ -248,6 +248,7 @@ class ShardedIndex:
         self.two_phase_used = False
         self.fallback_steps = 0  # steps redone without the two-phase cut (status word set on some shard)
         self.last_status = 0     # OR of the shards' status words of the last two-phase step (0 = clean)
+        self.fallback_chunks = 0  # 8192-query chunks redone because a shard's buffer overflowed / a speculation missed
         self.profile = False
         self.timing = {}
         self._t_last = 0.0
@@ -376,18 +377,21 @@ class ShardedIndex:
             self.local.export_bounds(bounds_ptrs[r])
             if upload is not None:
                 upload(b)
+            nchunks = (nqt + QUERY_CHUNK - 1) // QUERY_CHUNK
+            if flag_any.numel() < nchunks:
+                flag_any = b["flag_any"] = torch.zeros((nchunks,), dtype=torch.int32, device=fab.device)
             flag_any.zero_()
             fab.barrier(0)  # error bounds (and uploaded query slices) of every shard are visible
             q_ptr = prepare(b)
             _, as_ptrs = b["ascore"]
             _, kth_ptrs = b["kth"]
             tm("prologue")
-            for c0 in range(0, nqt, QUERY_CHUNK):
-                nqc = min(QUERY_CHUNK, nqt - c0)
+            chunks = [(c0, min(QUERY_CHUNK, nqt - c0)) for c0 in range(0, nqt, QUERY_CHUNK)]
+            for ci, (c0, nqc) in enumerate(chunks):
                 self.local.search_begin(q_ptr + 4 * self.d * c0, nqc, k, self.row0, bounds_ptrs, 1.0 / G, as_ptrs[r], flag_ptrs[r])
                 tm("begin")
                 fab.barrier(1)  # every shard's approximate top-k scores and status word are visible
-                union_kth(as_ptrs, nqc, k, (nqc * r) // G, (nqc * (r + 1)) // G, kth_ptrs, dev, flag_ptrs, flag_any.data_ptr())
+                union_kth(as_ptrs, nqc, k, (nqc * r) // G, (nqc * (r + 1)) // G, kth_ptrs, dev, flag_ptrs, flag_any.data_ptr() + 4 * ci)
                 fab.barrier(0)  # the global k-th scores of all queries have landed
                 tm("union_kth")
                 self.local.search_end([kth_ptrs[r]], D_ptrs[r] + 4 * k * c0, I_ptrs[r] + 8 * k * c0)
@@ -395,12 +399,38 @@ class ShardedIndex:
             fab.barrier(1)  # every shard's exact lists are complete and visible
             merge_topk_peers(D_ptrs, I_ptrs, nqt, k, (nqt * r) // G, (nqt * (r + 1)) // G, outs_D, outs_I, dev)
             fab.barrier(0)  # every shard's slice has landed in every output
-            flag = int(flag_any.item())  # the step's only host synchronisation
-            self.last_status = flag
+            flags = flag_any[:nchunks].tolist()  # the step's only host synchronisation
+            self.last_status = 0
+            for f in flags:
+                self.last_status |= int(f)
             tm("merge")
-            done = flag == 0
-            if done:
+            bad = [ci for ci, f in enumerate(flags) if f]
+            if any(int(flags[ci]) & 0x100 for ci in bad):
+                bad = None  # a shard cannot run the one-pass arithmetic at all: the whole step goes the plain way
+            if bad is not None:
+                done = True
                 self.two_phase_used = True
+                if bad:
+                    # Some shard overflowed a candidate buffer / missed a speculation in these chunks (every shard sees the
+                    # same words): only they are redone -- plain per-shard search of the chunk (its own reruns) into the
+                    # same lists, then the merge of the chunk's queries.
+                    self.fallback_chunks += len(bad)
+                    err = None
+                    try:
+                        for ci in bad:
+                            c0, nqc = chunks[ci]
+                            self.local.search_ptr(q_ptr + 4 * self.d * c0, nqc, k, self.row0, D_ptrs[r] + 4 * k * c0,
+                                                  I_ptrs[r] + 8 * k * c0, self.path)
+                    except Exception as exc:  # noqa: BLE001
+                        err = exc
+                    if not fab.all_ok(err is None):
+                        raise RuntimeError(f"sharded search failed on a shard (this shard: {err!r})")
+                    fab.barrier(1)
+                    for ci in bad:
+                        c0, nqc = chunks[ci]
+                        merge_topk_peers(D_ptrs, I_ptrs, nqt, k, c0 + (nqc * r) // G, c0 + (nqc * (r + 1)) // G, outs_D, outs_I, dev)
+                    fab.barrier(0)
+                    torch.cuda.current_stream(fab.device).synchronize()
             else:
                 self.fallback_steps += 1
         if not done:

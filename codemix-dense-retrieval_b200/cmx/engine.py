@@ -241,6 +241,11 @@ class Shard:
         arr = (C.c_void_p * len(kth_ptrs))(*[int(p) for p in kth_ptrs])
         check(_lib.lib().cmx_search_end(self._h, arr, len(kth_ptrs), int(D_ptr), int(I_ptr), _stream(self.device)))
 
+    def search_ptr(self, q_ptr: int, nq: int, k: int, id_base: int, D_ptr: int, I_ptr: int, path="auto") -> None:
+        """``search`` on raw device addresses (queries [nq, d], outputs [nq, k]): the per-chunk fallback of the sharded step."""
+        check(_lib.lib().cmx_index_search(self._h, int(q_ptr), int(nq), int(k), int(D_ptr), int(I_ptr), 1, int(id_base),
+                                          _PATHS[path], _stream(self.device)))
+
     def last_stats(self) -> dict:
         st = _lib.SearchStats()
         check(_lib.lib().cmx_index_last_stats(self._h, C.byref(st)))

@@ -245,18 +245,24 @@ struct SlabPlan {
 //
 // Speculative slabs (spec = true; tensor path, whose block order makes every prefix a uniform
 // sample).  Once `seen` rows are in, the k-th best of the first T >= seen rows is expected near the
-// r0 = k seen/T -th best so far.  A slab covering rows [seen, T) may therefore be filtered at the 3x
-// deeper rank R = 3 r0: ~3k survivors per query whatever T is (+-3k/sqrt(R), far inside the buffer),
-// while the chance that fewer than k of the T rows clear it is P(Poisson(r0) >= 3 r0) < 1e-12 at
-// r0 >= kSpecMinRank.  The compaction after the slab VERIFIES the guess per query (k-th best >=
-// threshold + margin); a miss only costs a rerun with spec = false.  Two uses:
+// r0 = k seen/T -th best so far.  A slab covering rows [seen, T) may therefore be filtered at the deeper
+// rank R = kSpecDepth r0: ~kSpecDepth k survivors per query whatever T is, while the chance that fewer
+// than k of the T rows clear it is P(Poisson(r0) >= R).  The compaction after the slab VERIFIES the guess
+// per query (k-th best >= threshold + margin); a miss only costs a rerun with spec = false.  Two uses:
 //   final: T = N as soon as r0 >= kSpecMinRank -- the rest of the corpus in ONE slab;
 //   mid:   otherwise the largest T with r0 = kSpecMinRank, if that beats the geometric slab -- at
 //          k = 1000 the dense slab of 8 192 rows is followed by one slab of 335 k rows instead of
 //          three geometric ones (20 k, 74 k, 262 k) and their compactions.
-// The Poisson figure assumes independent rows; if a query's best rows come in clumps of c adjacent
-// rows (passages of one document) the effective rank is r0/c -- at r0 >= 32 and c = 3 a miss is still
-// < 1e-7 per query, and a miss is never wrong, only a second pass.
+// kSpecDepth balances two tails (r0 >= 32, buffers of 8192 keys, k' = 1341 resident):
+//   guess too HIGH (rerun):      P(Poisson(r0) >= 2.5 r0) < 1e-13 per query
+//   guess too LOW (buffer overflow, rerun): the sample holds R rows above the threshold where the corpus rate
+//       predicts >= 1.85 R:  P(Poisson(1.85 R) <= R) ~ 1e-9 at R = 80
+// Round 1 used depth 3: overflow needed only 1.57 R, P ~ 2e-7 per (query, shard) -- an 8-GPU 11-alpha job
+// (614 k pairs) hit it (shard 6, alpha 0.7, query 2722: 125 sample rows above the threshold where 197 were due,
+// 7 292 survivors: scripts/diag_emulate.py).  The Poisson figures assume independent rows; if a query's best
+// rows come in clumps of c adjacent rows (passages of one document) the effective rank is r0/c -- at r0 >= 32
+// and c = 3 a miss is still < 1e-5 per query, and neither tail is ever wrong, only a second pass.
+constexpr double kSpecDepth = 2.5;
 constexpr double kSpecMinRank = 32.0;
 static int g_speculate = 1;  // 0: planned geometric slabs only (experiments)
 
@@ -269,16 +275,16 @@ static SlabPlan plan_slabs_one(int64_t N, int k, int cap, int align, bool safe, 
   while (seen < N) {
     const double g = (double)seen * (double)room / (2.0 * (double)k);  // geometric slab
     if (spec && !safe && g_speculate && seen > 0) {
-      const int rank_min = (int)std::ceil(3.0 * kSpecMinRank);
+      const int rank_min = (int)std::ceil(kSpecDepth * kSpecMinRank);
       const double r0 = (double)k * (double)seen / (double)N;  // expected rank of the final k-th best
       // final: worth it only if the geometric plan still needs two or more slabs
-      if (r0 >= kSpecMinRank && std::ceil(3.0 * r0) < (double)k_out && 3.0 * r0 < 0.75 * k && (double)(N - seen) > g) {
-        push(N - seen, (int)std::ceil(3.0 * r0));
+      if (r0 >= kSpecMinRank && std::ceil(kSpecDepth * r0) < (double)k_out && kSpecDepth * r0 < 0.75 * k && (double)(N - seen) > g) {
+        push(N - seen, (int)std::ceil(kSpecDepth * r0));
         break;
       }
       // mid: up to the row count T at which r0 = kSpecMinRank
       const int64_t T = (int64_t)((double)k * (double)seen / kSpecMinRank);
-      if (mid && r0 < kSpecMinRank && rank_min < k_out && 3.0 * kSpecMinRank < 0.75 * k && 4.5 * k <= cap &&
+      if (mid && r0 < kSpecMinRank && rank_min < k_out && kSpecDepth * kSpecMinRank < 0.75 * k && 4.5 * k <= cap &&
           T - seen > (int64_t)(1.5 * g)) {
         push(std::min(round_dn(T - seen), N - seen), rank_min);
         continue;
@@ -1186,6 +1192,10 @@ int cmx_search_mixed(cmx_index* ix, const float* P, const float* S, int64_t nq, 
   return CMX_OK;
 }
 
+// test hook: the (skip+1)-th cmx_search_begin from now publishes `bits` on top of its own status word
+static std::atomic<int> g_inject_skip{-1};
+static unsigned g_inject_bits = 0;
+
 // ---- sharded (two-phase) search: asynchronous building blocks ------------------------------------
 int cmx_search_prepare(cmx_index* ix, const float* P, const float* S, int64_t nq, const double* alphas, int nA,
                        const float** q_out, void* stream) {
@@ -1252,7 +1262,9 @@ int cmx_search_begin(cmx_index* ix, const float* q, int64_t nq, int k, int64_t i
     ix->bounds_from_dev = false;
     CMX_TRY(rc);
     CMX_TRY(launch_export_scores(ix->ws, nq, k, scores_out, st));
-    CMX_TRY(launch_publish_flag(ix->ws.overflow, 0u, flag_out, st));
+    unsigned extra = 0u;
+    if (g_inject_skip.load() >= 0 && g_inject_skip.fetch_sub(1) == 0) extra = g_inject_bits;
+    CMX_TRY(launch_publish_flag(ix->ws.overflow, extra, flag_out, st));
   }
   ix->pending = true;
   ix->pend_skip = !usable;  // flagged: cmx_search_end is a no-op, the step is redone without the two-phase cut
@@ -1428,6 +1440,7 @@ CMX_API int cmx_debug_plan_ranks(int64_t ntotal, int k, int cap, int rescore, in
   for (int i = 0; i < (int)pl.rows.size() && i < max_slabs; ++i) ranks_out[i] = pl.spec_rank[(size_t)i];
   return CMX_OK;
 }
+CMX_API int cmx_debug_inject_begin_status(int skip, unsigned bits) { g_inject_bits = bits; g_inject_skip.store(skip); return CMX_OK; }
 CMX_API int cmx_debug_set_prescore(int mode) { g_prescore = mode; return CMX_OK; }
 CMX_API int cmx_debug_set_prescore_min_rows(int64_t rows) { g_prescore_min_rows = rows < 0 ? kPrescoreMinRows : rows; return CMX_OK; }
 CMX_API int cmx_debug_set_prescore_params(double depth, int pad_smem_bytes, int max_sub) {

@@ -41,6 +41,14 @@ for mode, prec in (("allgather", "rescore"), ("p2p", "rescore"), ("allgather", "
             Dm, Im = idx.search_mixed(P, S, many, 50)
             res["many"] = (Dm.clone(), Im.clone())
             info["many"] = (idx.two_phase_used, idx.fallback_steps)
+            # a candidate-buffer overflow reported by ONE rank in the SECOND chunk: only that chunk is redone, by everybody
+            from cmx import _lib
+            if rank == world - 1:
+                _lib.check(_lib.lib().cmx_debug_inject_begin_status(1, 1))
+            fc0 = idx.fallback_chunks
+            Dj, Ij = idx.search_mixed(P, S, many, 50)
+            checks["chunk_fallback"] = bool(idx.fallback_chunks == fc0 + 1 and idx.fallback_steps == 0 and idx.last_status == 1
+                                            and torch.equal(Dj, res["many"][0]) and torch.equal(Ij, res["many"][1]))
     del idx
 ok = True
 ok1 = True

@@ -220,7 +220,14 @@ def test_shards_index_one_process(tmp_path):
     Dm, Im = sharded.search_mixed(P, S, many, 10)
     D0, I0 = one.search_mixed(P, S, many, 10, path="tensor")
     assert np.array_equal(Im, I0) and np.array_equal(Dm, D0)
-    assert all(v.fallback_steps == 0 for v in sharded._views)
+    assert all(v.fallback_steps == 0 and v.fallback_chunks == 0 for v in sharded._views)
+    # one shard reports a buffer overflow in one chunk: every shard redoes that chunk only, same answer
+    from cmx import _lib
+
+    _lib.check(_lib.lib().cmx_debug_inject_begin_status(4, 1))  # the 5th begin of the 6 (3 shards x 2 chunks)
+    Dm2, Im2 = sharded.search_mixed(P, S, many, 10)
+    assert np.array_equal(Im2, I0) and np.array_equal(Dm2, D0)
+    assert all(v.fallback_chunks == 1 and v.fallback_steps == 0 and v.last_status == 1 for v in sharded._views)
 
 
 def test_two_gpu_shards_one_process_if_available():

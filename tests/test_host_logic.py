@@ -482,10 +482,10 @@ def test_slab_schedule_invariants():
     rows, ns, ss, sr = _plan(n, 1000, 8192)
     mid = 1341 * 8192 // 32 - 8192
     assert rows == [8192, mid // 256 * 256, npad - 8192 - mid // 256 * 256] and ns == 3 and ss == 2
-    assert _plan_ranks(n, 1000, 8192)[:3] == [0, 96, sr]
+    assert _plan_ranks(n, 1000, 8192)[:3] == [0, 80, sr]
     seen = sum(rows[:2])
     r0 = 1341 * seen / npad
-    assert r0 >= 32 and sr == int(np.ceil(3 * r0)) and sr < 750
+    assert r0 >= 32 and sr == int(np.ceil(2.5 * r0)) and sr < 750
     rows_g, ns_g, ss_g, _ = _plan(n, 1000, 8192, spec=0)
     assert ss_g == -1 and ns_g == 7 and rows_g[:4] == [8192, 20736, 73728, 262144] and sum(rows_g) == npad
     for a, b in zip(rows_g[1:-1], rows_g[2:-1]):
@@ -493,11 +493,11 @@ def test_slab_schedule_invariants():
     # shards of a 2- and 4-GPU search: 3 launches as well
     for g in (2, 4):
         rows_s, ns_s, ss_s, sr_s = _plan(n // g, 1000, 8192)
-        assert ns_s == 3 and ss_s == 2 and rows_s[1] == rows[1] and 96 < sr_s < 750
+        assert ns_s == 3 and ss_s == 2 and rows_s[1] == rows[1] and 80 < sr_s < 750
     # a 1.1 M-row shard of an 8-GPU search: a mid slab would not save a launch, the plan stays
     # dense, one geometric slab, guess after the second slab
     rows8, ns8, ss8, sr8 = _plan(1_105_228, 1000, 8192)
-    assert ns8 == 3 and ss8 == 2 and rows8[:2] == [8192, 20736] and 96 <= sr8 < 1000
+    assert ns8 == 3 and ss8 == 2 and rows8[:2] == [8192, 20736] and 80 <= sr8 < 1000
     # small k: the geometric plan is already 3-4 slabs and the rank estimate never qualifies
     assert _plan(n, 100, 8192)[2] == -1 and _plan(n, 10, 8192)[2] == -1
     # split precision plans on k itself
