@@ -17,6 +17,11 @@
 namespace cmx {
 
 constexpr int kSelThreads = 512;
+// rescore_kernel: 52 registers = 2 CTAs per SM.  Forcing 3 (40 registers, fewer loads in flight per warp) measured
+// 0.5 ms SLOWER per C2 step in a same-box A/B (5.9 vs 6.4 ms for the final compaction + rescoring).
+#ifndef RESCORE_MIN_CTAS
+#define RESCORE_MIN_CTAS 2
+#endif
 
 __global__ void ws_init_kernel(float* tau, float* spec, uint32_t* cnt, uint32_t* overflow, int64_t nq, int64_t nq_pad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -443,7 +448,7 @@ int launch_prescore(const float* X, int d, const float* Q, const SearchWs& ws, i
 // dynamic smem: cap/2 keys | next_pow2(k) keys | d floats (the query): 44 KB at k = 1000,
 // d = 1024, so four 512-thread CTAs share an SM and the row gathers of one hide the select
 // phase of another.
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __launch_bounds__(kSelThreads, RESCORE_MIN_CTAS)
 rescore_kernel(const float* __restrict__ X, int d, const float* __restrict__ Q, const uint64_t* __restrict__ cand,
                const uint32_t* __restrict__ cnt, uint32_t* __restrict__ overflow, const float* __restrict__ margin,
                const RescoreCut cut, int cap, int k, int topn, float* __restrict__ D, int64_t* __restrict__ I,
