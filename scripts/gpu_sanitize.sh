@@ -4,6 +4,9 @@
 # radix-select kernels) and synccheck.  Run under gpurun on ONE GPU:
 #     gpurun --timeout 2400 -- 'bash scripts/gpu_sanitize.sh'
 # Logs land in gpurun_out/sanitize_<tool>.log; the summary line of each tool is echoed at the end.
+# NOTE (round 2): this pool answers `compute-sanitizer is closed on this pool and stays closed` (rc 86,
+# profiles/r02_sanitizer_closed_on_pool.txt); the substitute that does run is
+# tests/test_gpu_round2.py::test_repeated_runs_are_bit_identical_across_kernel_variants.
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
 SAN=/usr/local/cuda/bin/compute-sanitizer

@@ -250,6 +250,49 @@ def test_two_gpu_shards_one_process_if_available():
     assert np.array_equal(Is, np.asarray(I1)) and np.array_equal(Ds, np.asarray(D1))
 
 
+def test_repeated_runs_are_bit_identical_across_kernel_variants():
+    """compute-sanitizer (racecheck / synccheck) is closed on this GPU pool, so the hand-rolled mbarrier / TMEM
+    pipelines are checked the way a race would show up: the same search repeated under every scheduling variant --
+    static and dynamic tile order, single-CTA and CTA-pair scorer, tile widths 256 / 128, prescoring on / off, both
+    small-batch widths -- must give bit-identical (D, I) every time."""
+    import torch
+
+    from cmx import _lib
+    from cmx.engine import Shard
+
+    L = _lib.lib()
+    N, d, k = 600_000, 256, 500
+    X = _unit_cuda(N, d, 51)
+    sh = Shard(d, 0)
+    sh.add(X)
+    for nq in (700, 24):
+        Q = _unit_cuda(nq, d, 52 + nq)
+        ref = None
+        variants = [dict(), dict(flags=512), dict(pair=1), dict(tile=128), dict(prescore=1), dict(flags=512, prescore=1)]
+        try:
+            for rep in range(3):
+                for v in variants:
+                    _lib.check(L.cmx_debug_set_tensor_flags(v.get("flags", 0)))
+                    _lib.check(L.cmx_debug_set_tensor_pair(v.get("pair", -1)))
+                    _lib.check(L.cmx_debug_set_tensor_tile(v.get("tile", 256)))
+                    _lib.check(L.cmx_debug_set_prescore(v.get("prescore", 0)))
+                    _lib.check(L.cmx_debug_set_prescore_min_rows(0 if v.get("prescore") else -1))
+                    D, I = sh.search(Q, k, path="tensor")
+                    assert sh.last_stats()["reruns"] == 0
+                    if ref is None:
+                        ref = (D.clone(), I.clone())
+                    else:
+                        assert torch.equal(I, ref[1]) and torch.equal(D, ref[0]), (nq, rep, v)
+        finally:
+            _lib.check(L.cmx_debug_set_tensor_flags(0))
+            _lib.check(L.cmx_debug_set_tensor_pair(-1))
+            _lib.check(L.cmx_debug_set_tensor_tile(256))
+            _lib.check(L.cmx_debug_set_prescore(0))
+            _lib.check(L.cmx_debug_set_prescore_min_rows(-1))
+        Dr, Ir = _brute(X, Q, k)
+        assert oracle.compare_topk(ref[0].cpu().numpy(), ref[1].cpu().numpy(), Dr, Ir, rtol=RTOL, atol=ATOL)["ok"]
+
+
 def test_memory_accounting_is_bounded():
     """Default precision = fp32 store + ONE fp16 plane = 1.5x a FAISS flat index (+ a workspace that does not grow
     with the corpus); the split precision adds the second plane (2x)."""
