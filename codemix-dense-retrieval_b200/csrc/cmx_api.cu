@@ -637,6 +637,125 @@ static bool mapped_host_outputs(float* D, int64_t* I, float** Dm, int64_t** Im) 
   return true;
 }
 
+// ---- streaming loader ---------------------------------------------------------------------------
+// fills dst[0 .. bytes) from fd at `off` with `nthreads` concurrent preads; returns false on a short read / error
+static bool pread_parallel(int fd, char* dst, int64_t off, int64_t bytes, int nthreads) {
+  nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, bytes / (1 << 20)));
+  std::vector<std::thread> th;
+  std::vector<int> ok((size_t)nthreads, 1);
+  for (int t = 0; t < nthreads; ++t) {
+    const int64_t a = bytes * t / nthreads, b = bytes * (t + 1) / nthreads;
+    th.emplace_back([=, &ok]() {
+      int64_t done = a;
+      while (done < b) {
+        const ssize_t r = pread(fd, dst + done, (size_t)std::min<int64_t>(b - done, 1 << 30), (off_t)(off + done));
+        if (r <= 0) { ok[(size_t)t] = 0; return; }
+        done += r;
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  for (int v : ok)
+    if (!v) return false;
+  return true;
+}
+
+// dst[0 .. bytes) = src[0 .. bytes) with `nthreads` concurrent memcpys (pageable host memory -> page-locked staging)
+static bool memcpy_parallel(char* dst, const char* src, int64_t bytes, int nthreads) {
+  nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, bytes / (4 << 20)));
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) {
+    const int64_t a = bytes * t / nthreads, b = bytes * (t + 1) / nthreads;
+    th.emplace_back([=]() { memcpy(dst + a, src + a, (size_t)(b - a)); });
+  }
+  for (auto& x : th) x.join();
+  return true;
+}
+
+// Appends n rows produced chunk by chunk by `fill(buf, first_row, rows)` (host threads writing a page-locked
+// staging buffer): three buffers, the producer one chunk ahead of the copy engine, max |x| and max row norm of each
+// chunk computed behind its copy.  Shared by the file loader and by add() of large pageable host arrays.
+template <typename Fill>
+static int stream_rows_into_store(cmx_index* ix, int64_t n, Fill fill, const char* what, double* seconds_out) {
+  const auto t_begin = std::chrono::steady_clock::now();
+  const int64_t row_bytes = (int64_t)ix->d * 4;
+  CMX_TRY(grow_store(ix, ix->n + n));
+  constexpr int NB = 3;
+  const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)64 << 20) / row_bytes);
+  const int64_t nchunks = (n + chunk_rows - 1) / chunk_rows;
+  char* buf[NB] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[NB] = {nullptr, nullptr, nullptr};
+  cudaStream_t st = nullptr;
+  int rc = CMX_OK;
+  auto cleanup = [&]() {
+    for (int i = 0; i < NB; ++i) {
+      if (buf[i]) cudaFreeHost(buf[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    if (st) cudaStreamDestroy(st);
+  };
+  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  for (int i = 0; i < NB && i < nchunks && e == cudaSuccess; ++i) {
+    e = cudaHostAlloc((void**)&buf[i], (size_t)(std::min(chunk_rows, n) * row_bytes), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaMemsetAsync(ix->absmax_dev, 0, 2 * sizeof(uint32_t), st);
+  if (e != cudaSuccess) { set_error("%s: setup failed: %s", what, cudaGetErrorString(e)); cleanup(); return CMX_ERR_CUDA; }
+  float* dst0 = ix->X + ix->n * ix->d;
+  double t_fill = 0.0;
+  std::thread producer;
+  bool fill_ok = true;
+  auto start_fill = [&](int64_t c) {
+    const int64_t r0 = c * chunk_rows, rows = std::min(chunk_rows, n - r0);
+    producer = std::thread([&, c, r0, rows]() {
+      const auto t0 = std::chrono::steady_clock::now();
+      fill_ok = fill(buf[c % NB], r0, rows);
+      t_fill += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    });
+  };
+  start_fill(0);
+  for (int64_t c = 0; c < nchunks && rc == CMX_OK; ++c) {
+    producer.join();
+    if (!fill_ok) { set_error("%s: short read (chunk %lld)", what, (long long)c); rc = CMX_ERR_INVALID; break; }
+    if (c + 1 < nchunks) {
+      // buffer (c+1) % NB was last used by chunk c+1-NB: its copy must have left the host
+      if (c + 1 >= NB && cudaEventSynchronize(ev[(c + 1) % NB]) != cudaSuccess) { set_error("%s: event wait failed", what); rc = CMX_ERR_CUDA; break; }
+      start_fill(c + 1);
+    }
+    const int64_t r0 = c * chunk_rows, rows = std::min(chunk_rows, n - r0);
+    float* dst = dst0 + r0 * ix->d;
+    e = cudaMemcpyAsync(dst, buf[c % NB], (size_t)(rows * row_bytes), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(ev[c % NB], st);
+    if (e != cudaSuccess) { set_error("%s: H2D copy failed: %s", what, cudaGetErrorString(e)); rc = CMX_ERR_CUDA; break; }
+    // max |x| and max row norm of the chunk (operand scale / error bound of the tensor path), behind the copy
+    rc = launch_absmax(dst, rows * (int64_t)ix->d, ix->absmax_dev, st);
+    if (rc == CMX_OK) rc = launch_row_norm_max(dst, rows, ix->d, ix->absmax_dev + 1, st);
+  }
+  if (producer.joinable()) producer.join();
+  uint32_t bits[2] = {0, 0};
+  if (rc == CMX_OK) {
+    e = cudaMemcpyAsync(bits, ix->absmax_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); rc = CMX_ERR_CUDA; }
+  } else {
+    cudaStreamSynchronize(st);
+  }
+  cleanup();
+  if (rc != CMX_OK) return rc;
+  ix->absmax_bits = std::max(ix->absmax_bits, bits[0]);
+  float nrm;
+  memcpy(&nrm, &bits[1], sizeof(float));
+  ix->row_norm_max = std::max(ix->row_norm_max, nrm);
+  ix->n += n;
+  if (seconds_out) {
+    seconds_out[0] = t_fill;
+    seconds_out[1] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  }
+  return CMX_OK;
+}
+
+static int default_io_threads() { return (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency() / 2)); }
+
 static void stats_begin(cmx_index* ix, int64_t nq) {
   memset(&ix->stats, 0, sizeof(ix->stats));
   ix->stats.nq = nq;
@@ -729,6 +848,22 @@ int cmx_index_add(cmx_index* ix, const float* x, int64_t n, int x_on_device) {
   CMX_CHECK(ix->n + n < (int64_t)0x7fffff00, "index would exceed 2^31 rows per shard");
   DevGuard g(ix->device);
   ix->pending = false;
+  if (!x_on_device && n * (int64_t)ix->d * 4 >= ((int64_t)256 << 20)) {
+    // a large host array (index_cpu_to_gpu of a read_index'ed corpus): cudaMemcpy from pageable memory is staged by
+    // the driver at a few GB/s; parallel memcpys into page-locked buffers overlapped with the H2D copies are not
+    cudaPointerAttributes a;
+    const bool pinned = cudaPointerGetAttributes(&a, x) == cudaSuccess && a.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned) {
+      const int64_t row_bytes = (int64_t)ix->d * 4;
+      const int nthreads = default_io_threads();
+      const char* src = reinterpret_cast<const char*>(x);
+      CMX_NVTX("cmx:add(host, staged)");
+      return stream_rows_into_store(
+          ix, n, [=](char* buf, int64_t r0, int64_t rows) { return memcpy_parallel(buf, src + r0 * row_bytes, rows * row_bytes, nthreads); },
+          "add", nullptr);
+    }
+  }
   CMX_TRY(grow_store(ix, ix->n + n));
   float* dst = ix->X + ix->n * ix->d;
   CMX_CUDA(cudaMemcpy(dst, x, (size_t)n * ix->d * sizeof(float), x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
@@ -748,29 +883,6 @@ int cmx_index_add(cmx_index* ix, const float* x, int64_t n, int x_on_device) {
   return CMX_OK;
 }
 
-// ---- streaming loader ---------------------------------------------------------------------------
-// fills dst[0 .. bytes) from fd at `off` with `nthreads` concurrent preads; returns false on a short read / error
-static bool pread_parallel(int fd, char* dst, int64_t off, int64_t bytes, int nthreads) {
-  nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, bytes / (1 << 20)));
-  std::vector<std::thread> th;
-  std::vector<int> ok((size_t)nthreads, 1);
-  for (int t = 0; t < nthreads; ++t) {
-    const int64_t a = bytes * t / nthreads, b = bytes * (t + 1) / nthreads;
-    th.emplace_back([=, &ok]() {
-      int64_t done = a;
-      while (done < b) {
-        const ssize_t r = pread(fd, dst + done, (size_t)std::min<int64_t>(b - done, 1 << 30), (off_t)(off + done));
-        if (r <= 0) { ok[(size_t)t] = 0; return; }
-        done += r;
-      }
-    });
-  }
-  for (auto& x : th) x.join();
-  for (int v : ok)
-    if (!v) return false;
-  return true;
-}
-
 int cmx_index_add_from_file(cmx_index* ix, const char* path, int64_t offset, int64_t n, int nthreads, double* seconds_out) {
   CMX_CHECK(ix != nullptr && path != nullptr, "null argument");
   CMX_CHECK(offset >= 0 && n >= 0, "bad range");
@@ -779,7 +891,6 @@ int cmx_index_add_from_file(cmx_index* ix, const char* path, int64_t offset, int
   DevGuard g(ix->device);
   ix->pending = false;
   CMX_NVTX("cmx:add_from_file");
-  const auto t_begin = std::chrono::steady_clock::now();
   const int fd = open(path, O_RDONLY);
   CMX_CHECK(fd >= 0, "cannot open %s: %s", path, strerror(errno));
   struct Closer { int fd; ~Closer() { close(fd); } } closer{fd};
@@ -789,82 +900,10 @@ int cmx_index_add_from_file(cmx_index* ix, const char* path, int64_t offset, int
     CMX_CHECK(size >= 0 && offset + n * row_bytes <= (int64_t)size, "%s holds fewer than %lld rows of %d floats at offset %lld", path,
               (long long)n, ix->d, (long long)offset);
   }
-  CMX_TRY(grow_store(ix, ix->n + n));
-  if (nthreads <= 0) nthreads = (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency() / 2));
-  // three page-locked staging buffers: chunk c+1 is being read while chunk c crosses PCIe
-  constexpr int NB = 3;
-  const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)64 << 20) / row_bytes);
-  const int64_t nchunks = (n + chunk_rows - 1) / chunk_rows;
-  char* buf[NB] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev[NB] = {nullptr, nullptr, nullptr};
-  cudaStream_t st = nullptr;
-  int rc = CMX_OK;
-  auto cleanup = [&]() {
-    for (int i = 0; i < NB; ++i) {
-      if (buf[i]) cudaFreeHost(buf[i]);
-      if (ev[i]) cudaEventDestroy(ev[i]);
-    }
-    if (st) cudaStreamDestroy(st);
-  };
-  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-  for (int i = 0; i < NB && e == cudaSuccess; ++i) {
-    e = cudaHostAlloc((void**)&buf[i], (size_t)(chunk_rows * row_bytes), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
-  }
-  if (e == cudaSuccess) e = cudaMemsetAsync(ix->absmax_dev, 0, 2 * sizeof(uint32_t), st);
-  if (e != cudaSuccess) { set_error("loader setup failed: %s", cudaGetErrorString(e)); cleanup(); return CMX_ERR_CUDA; }
-  float* dst0 = ix->X + ix->n * ix->d;
-  double t_read = 0.0;
-  // the reader runs one chunk ahead of the copy engine
-  std::thread reader;
-  bool read_ok = true;
-  auto start_read = [&](int64_t c) {
-    const int64_t r0 = c * chunk_rows, rows = std::min(chunk_rows, n - r0);
-    reader = std::thread([&, c, r0, rows]() {
-      const auto t0 = std::chrono::steady_clock::now();
-      read_ok = pread_parallel(fd, buf[c % NB], offset + r0 * row_bytes, rows * row_bytes, nthreads);
-      t_read += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    });
-  };
-  start_read(0);
-  for (int64_t c = 0; c < nchunks && rc == CMX_OK; ++c) {
-    reader.join();
-    if (!read_ok) { set_error("short read from %s (chunk %lld)", path, (long long)c); rc = CMX_ERR_INVALID; break; }
-    if (c + 1 < nchunks) {
-      // buffer (c+1) % NB was last used by chunk c+1-NB: its copy must have left the host
-      if (c + 1 >= NB && cudaEventSynchronize(ev[(c + 1) % NB]) != cudaSuccess) { set_error("loader: event wait failed"); rc = CMX_ERR_CUDA; break; }
-      start_read(c + 1);
-    }
-    const int64_t r0 = c * chunk_rows, rows = std::min(chunk_rows, n - r0);
-    float* dst = dst0 + r0 * ix->d;
-    e = cudaMemcpyAsync(dst, buf[c % NB], (size_t)(rows * row_bytes), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaEventRecord(ev[c % NB], st);
-    if (e != cudaSuccess) { set_error("loader: H2D copy failed: %s", cudaGetErrorString(e)); rc = CMX_ERR_CUDA; break; }
-    // max |x| and max row norm of the chunk (operand scale / error bound of the tensor path), behind the copy
-    rc = launch_absmax(dst, rows * (int64_t)ix->d, ix->absmax_dev, st);
-    if (rc == CMX_OK) rc = launch_row_norm_max(dst, rows, ix->d, ix->absmax_dev + 1, st);
-  }
-  if (reader.joinable()) reader.join();
-  uint32_t bits[2] = {0, 0};
-  if (rc == CMX_OK) {
-    e = cudaMemcpyAsync(bits, ix->absmax_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { set_error("loader: %s", cudaGetErrorString(e)); rc = CMX_ERR_CUDA; }
-  } else {
-    cudaStreamSynchronize(st);
-  }
-  cleanup();
-  if (rc != CMX_OK) return rc;
-  ix->absmax_bits = std::max(ix->absmax_bits, bits[0]);
-  float nrm;
-  memcpy(&nrm, &bits[1], sizeof(float));
-  ix->row_norm_max = std::max(ix->row_norm_max, nrm);
-  ix->n += n;
-  if (seconds_out) {
-    seconds_out[0] = t_read;
-    seconds_out[1] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
-  }
-  return CMX_OK;
+  if (nthreads <= 0) nthreads = default_io_threads();
+  return stream_rows_into_store(
+      ix, n, [=](char* buf, int64_t r0, int64_t rows) { return pread_parallel(fd, buf, offset + r0 * row_bytes, rows * row_bytes, nthreads); },
+      path, seconds_out);
 }
 
 // rows[i] of `src` (same device) -> appended to `ix`: the device-side form of the reference's

@@ -20,11 +20,17 @@ for base in ("/dev/shm", "/tmp"):
         gb = 4e-9 * rows * d
         if base == "/tmp":  # drop the page cache if we may, so the second pass reads the disk
             os.system("sync; echo 3 > /proc/sys/vm/drop_caches 2>/dev/null")
-        for label in ("native", "native_again", "numpy_chunks"):
+        for label in ("native", "native_again", "numpy_chunks", "host_index_to_gpu"):
             t0 = time.perf_counter()
             if label.startswith("native"):
                 g = faiss.read_index_to_gpu(str(path), 0)
                 extra = dict(cio.LAST_LOAD)
+            elif label == "host_index_to_gpu":  # the reference's own flow: read_index (host) + index_cpu_to_gpu
+                cpu = faiss.read_index(str(path))
+                t_read = time.perf_counter() - t0
+                g = faiss.index_cpu_to_gpu(faiss.StandardGpuResources(), 0, cpu)
+                extra = {"read_index_s": round(t_read, 3)}
+                del cpu
             else:
                 info = cio.inspect_index(path)
                 flat = faiss.GpuIndexFlatIP(d, device=0); flat.reserveMemory(rows)

@@ -293,6 +293,33 @@ def test_repeated_runs_are_bit_identical_across_kernel_variants():
         assert oracle.compare_topk(ref[0].cpu().numpy(), ref[1].cpu().numpy(), Dr, Ir, rtol=RTOL, atol=ATOL)["ok"]
 
 
+def test_large_pageable_add_is_staged_and_exact():
+    """add() of a large pageable host array (index_cpu_to_gpu of a read_index'ed corpus) goes through the page-locked
+    staging pipeline (parallel memcpy + overlapped H2D); the stored rows and the corpus statistics are the same as for
+    the direct copy of a device tensor."""
+    import torch
+
+    from cmx.engine import Shard
+
+    rng = np.random.default_rng(61)
+    n, d = 300_000, 256  # 307 MB > the 256 MB switch, several 64 MB chunks with a ragged last one
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X[12345] *= 7.0
+    a, b = Shard(d, 0), Shard(d, 0)
+    a.add(X)                          # pageable numpy: staged
+    b.add(torch.from_numpy(X).cuda())  # device tensor: one D2D copy
+    assert a.ntotal == b.ntotal == n
+    assert a.error_bounds() == b.error_bounds()
+    for i0 in (0, 65535, 131072, n - 1000):
+        assert np.array_equal(a.reconstruct_n(i0, 1000), X[i0:i0 + 1000])
+    Q = _unit(rng, 50, d)
+    Da, Ia = a.search(Q, 20)
+    Db, Ib = b.search(Q, 20)
+    assert np.array_equal(Ia, Ib) and np.array_equal(Da, Db)
+    a.add(X[:10])                     # small adds keep the direct path and append after the staged rows
+    assert a.ntotal == n + 10 and np.array_equal(a.reconstruct_n(n, 10), X[:10])
+
+
 def test_memory_accounting_is_bounded():
     """Default precision = fp32 store + ONE fp16 plane = 1.5x a FAISS flat index (+ a workspace that does not grow
     with the corpus); the split precision adds the second plane (2x)."""
