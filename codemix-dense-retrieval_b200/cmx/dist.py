@@ -451,7 +451,7 @@ class ShardedIndex:
         return result
 
     def _run(self, nA, nq, k, prepare, run_local, host_out=None, upload=None):
-        if self._p2p_ok():
+        if self._p2p_ok() and nA * nq > 0:
             try:
                 return self._step_p2p(nA, nq, k, prepare, run_local, host_out, upload)
             except Exception as exc:  # symmetric memory unavailable: keep the NCCL exchange
@@ -503,6 +503,8 @@ class ShardedIndex:
         each merge kernel writes its slice of (D, I) into the shared pinned buffer ``out``."""
         k = int(k)
         nA, nq = len(alphas), int(P_h.shape[0])
+        if nA * nq == 0:
+            return torch.empty((nA, nq, k), dtype=torch.float32), torch.empty((nA, nq, k), dtype=torch.int64)
         if out is None:
             out = self.host_output(nA, nq, k)
         if self.world == 1:

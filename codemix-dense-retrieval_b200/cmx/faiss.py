@@ -534,8 +534,10 @@ class IndexShardsIP(_Searchable):
         P = _as_f32_2d(P.detach().cpu() if _is_torch(P) else P, self.d, "P")
         S = _as_f32_2d(S.detach().cpu() if _is_torch(S) else S, self.d, "S")
         assert tuple(P.shape) == tuple(S.shape)
-        self._ensure_views()
         shape = (len(alphas), int(P.shape[0]), int(k))
+        if shape[0] == 0 or shape[1] == 0:
+            return np.empty(shape, np.float32), np.empty(shape, np.int64)
+        self._ensure_views()
 
         def step(rank, view):
             out = self._host_out(rank, view, shape)

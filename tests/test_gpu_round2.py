@@ -215,6 +215,10 @@ def test_shards_index_one_process(tmp_path):
     assert Ds2.ctypes.data != Ds.ctypes.data and np.array_equal(Is, I1) and np.array_equal(Is2, I1)
     Dq, Iq = sharded.search(P, k)
     assert np.array_equal(Iq, I1[0]) and np.array_equal(Dq, D1[0])
+    De, Ie = sharded.search(P[:0], k)  # no queries: nothing to do, no collective
+    assert De.shape == (0, k) and Ie.shape == (0, k)
+    D2q, I2q = sharded.search(P[:2], k)  # fewer queries than shards: some merge slices are empty
+    assert np.array_equal(I2q, I1[0][:2]) and np.array_equal(D2q, D1[0][:2])
     # 60 alphas x 150 queries = 9000 > 8192: two chunks of the two-phase pass
     many = [i / 59.0 for i in range(60)]
     Dm, Im = sharded.search_mixed(P, S, many, 10)
