@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
     L.cmx_index_reset.argtypes = [vp]
     L.cmx_index_add_from_file.argtypes = [vp, C.c_char_p, i64, i64, i32, vp]
     L.cmx_index_add_gather.argtypes = [vp, vp, vp, i64]
+    L.cmx_read_file.argtypes = [C.c_char_p, i64, i64, vp, i32]
     L.cmx_index_ntotal.argtypes = [vp, C.POINTER(i64)]
     L.cmx_index_memory.argtypes = [vp, vp]
     L.cmx_index_dim.argtypes = [vp, C.POINTER(i32)]
@@ -120,7 +121,7 @@ def lib() -> C.CDLL:
     L.cmx_debug_block_perm.argtypes = [i64]
     L.cmx_debug_block_perm.restype = C.c_uint64
     for name in (
-        "cmx_device_count cmx_index_create cmx_index_free cmx_index_reserve cmx_index_add cmx_index_reset cmx_index_add_from_file cmx_index_add_gather "
+        "cmx_device_count cmx_index_create cmx_index_free cmx_index_reserve cmx_index_add cmx_index_reset cmx_index_add_from_file cmx_index_add_gather cmx_read_file "
         "cmx_index_ntotal cmx_index_memory cmx_index_dim cmx_index_device cmx_index_reconstruct cmx_index_data cmx_index_search "
         "cmx_mix_normalize cmx_search_mixed cmx_search_prepare cmx_index_export_bounds cmx_search_begin cmx_search_end cmx_union_kth cmx_peer_broadcast cmx_host_register cmx_host_unregister cmx_enable_peer_access cmx_debug_plan_ranks cmx_debug_set_prescore cmx_debug_inject_begin_status cmx_debug_set_prescore_params cmx_debug_set_prescore_min_rows cmx_debug_approx_scores cmx_merge_topk cmx_merge_topk_peers cmx_trec_mono cmx_trec_bilingual cmx_trec_mono_file cmx_trec_bilingual_file cmx_index_last_stats cmx_set_profiling "
         "cmx_index_set_cand_capacity cmx_index_error_bounds cmx_index_raise_error_bounds cmx_index_set_precision cmx_set_default_precision cmx_debug_set_tensor_tile cmx_debug_set_stream_variant cmx_debug_set_tensor_flags cmx_debug_set_tensor_pair cmx_debug_set_tensor_small cmx_debug_set_tensor_window cmx_debug_set_block_order cmx_debug_set_speculate cmx_debug_set_mapped_outputs cmx_debug_plan_slabs"

@@ -231,6 +231,27 @@ def read_index_to_gpu(path, device: int = 0):
     return out
 
 
+def _read_block(fh, count: int) -> np.ndarray:
+    """``count`` little-endian float32 values at the file position of ``fh``; large blocks with concurrent preads
+    (``cmx_read_file``: several GB/s from page cache or a striped disk instead of one sequential read)."""
+    if count * 4 >= (64 << 20):
+        import os
+
+        from . import _lib
+
+        rows = np.empty((count,), dtype="<f4")
+        pos = fh.tell()
+        if os.fstat(fh.fileno()).st_size - pos < 4 * count:
+            raise RuntimeError("read_index: truncated vector block")
+        _lib.check(_lib.lib().cmx_read_file(os.fsencode(fh.name), pos, 4 * count, rows.ctypes.data, 0))
+        fh.seek(pos + 4 * count)
+        return rows
+    rows = np.fromfile(fh, dtype="<f4", count=count)
+    if rows.shape[0] != count:
+        raise RuntimeError("read_index: truncated vector block")
+    return rows
+
+
 def _read_flat(fh, F, fourcc_read: bool = False):
     if not fourcc_read:
         fourcc = fh.read(4)
@@ -244,9 +265,7 @@ def _read_flat(fh, F, fourcc_read: bool = False):
     if count != ntotal * d:
         raise RuntimeError(f"read_index: vector block holds {count} floats, expected {ntotal}*{d}")
     flat = F.IndexFlatIP(d)
-    rows = np.fromfile(fh, dtype="<f4", count=count)
-    if rows.shape[0] != count:
-        raise RuntimeError("read_index: truncated vector block")
+    rows = _read_block(fh, count)
     if ntotal:
         flat._blocks = [rows.reshape(ntotal, d)]
         flat._n = ntotal

@@ -928,6 +928,17 @@ int cmx_index_add_from_file(cmx_index* ix, const char* path, int64_t offset, int
       path, seconds_out);
 }
 
+int cmx_read_file(const char* path, int64_t offset, int64_t bytes, void* dst, int nthreads) {
+  CMX_CHECK(path && dst && offset >= 0 && bytes >= 0, "bad argument");
+  if (bytes == 0) return CMX_OK;
+  const int fd = open(path, O_RDONLY);
+  CMX_CHECK(fd >= 0, "cannot open %s: %s", path, strerror(errno));
+  const bool ok = pread_parallel(fd, (char*)dst, offset, bytes, nthreads > 0 ? nthreads : default_io_threads());
+  close(fd);
+  CMX_CHECK(ok, "short read from %s (%lld bytes at offset %lld)", path, (long long)bytes, (long long)offset);
+  return CMX_OK;
+}
+
 // rows[i] of `src` (same device) -> appended to `ix`: the device-side form of the reference's
 // np.vstack([base_index.reconstruct(e[0]) for e in batch]) (onepass_bilingual_mix_hub_custom_lang.py:644)
 int cmx_index_add_gather(cmx_index* ix, const cmx_index* src, const int64_t* rows, int64_t n) {

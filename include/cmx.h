@@ -90,6 +90,10 @@ CMX_API int cmx_index_add(cmx_index* ix, const float* x, int64_t n, int x_on_dev
  * inside pread, [1] = wall time of the call. */
 CMX_API int cmx_index_add_from_file(cmx_index* ix, const char* path, int64_t offset, int64_t n, int nthreads,
                                     double* seconds_out);
+/* host-side helper of faiss.read_index (onepass_dense_mix_run_custom_lang.py:250): `bytes` of `path` at `offset` into
+ * host memory `dst` with nthreads concurrent preads (<= 0: automatic) -- 36 GB of vectors in seconds, not in the
+ * ~9 s of one sequential read.  No GPU involved. */
+CMX_API int cmx_read_file(const char* path, int64_t offset, int64_t bytes, void* dst, int nthreads);
 /* replaces: np.vstack([base_index.reconstruct(i) for i in batch]) + add_with_ids of the bilingual combined-index
  * build (onepass_bilingual_mix_hub_custom_lang.py:644-646): appends rows[0..n) (host array of row numbers) of
  * `src` -- another index on the same device -- without the rows leaving the GPU. */
