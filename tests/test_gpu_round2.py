@@ -324,6 +324,30 @@ def test_large_pageable_add_is_staged_and_exact():
     assert a.ntotal == n + 10 and np.array_equal(a.reconstruct_n(n, 10), X[:10])
 
 
+def test_mixed_query_norms_in_one_batch_stay_exact():
+    """The query planes of a batch share ONE power-of-two scale: a large-norm query makes the fp16 residual -- and so
+    the margin -- of a small-norm query in the same batch relatively wide.  That may cost candidates (or, past half a
+    buffer, the fall-back to split precision) but never exactness: every query gets the same (D, I) as when it is
+    searched alone."""
+    from cmx.engine import Shard
+
+    rng = np.random.default_rng(71)
+    X = _unit(rng, 120_000, 128)
+    Q = _unit(rng, 96, 128)
+    Q *= np.float32(10.0) ** rng.uniform(-3, 3, size=(96, 1)).astype(np.float32)  # norms over six decades
+    sh = Shard(128, 0)
+    sh.add(X)
+    k = 100
+    D, I = sh.search(Q, k, path="tensor")
+    st = sh.last_stats()
+    Dr, Ir = oracle.flat_ip_search(X, Q, k)
+    rep = oracle.compare_topk(D, I, Dr, Ir, rtol=RTOL, atol=0.0)  # purely relative: scores span 1e-4 .. 1e2
+    assert rep["ok"], (rep, st)
+    for i in (int(np.argmin(np.linalg.norm(Q, axis=1))), int(np.argmax(np.linalg.norm(Q, axis=1))), 17):
+        Di, Ii = sh.search(Q[i:i + 1], k, path="tensor")
+        assert np.array_equal(Ii[0], I[i]) and np.array_equal(Di[0], D[i])
+
+
 def test_memory_accounting_is_bounded():
     """Default precision = fp32 store + ONE fp16 plane = 1.5x a FAISS flat index (+ a workspace that does not grow
     with the corpus); the split precision adds the second plane (2x)."""
