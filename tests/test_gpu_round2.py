@@ -345,7 +345,10 @@ def test_mixed_query_norms_in_one_batch_stay_exact():
     assert rep["ok"], (rep, st)
     for i in (int(np.argmin(np.linalg.norm(Q, axis=1))), int(np.argmax(np.linalg.norm(Q, axis=1))), 17):
         Di, Ii = sh.search(Q[i:i + 1], k, path="tensor")
-        assert np.array_equal(Ii[0], I[i]) and np.array_equal(Di[0], D[i])
+        if st["reruns"] == 0:  # both ran the one-pass arithmetic + exact rescoring: bit-identical
+            assert np.array_equal(Ii[0], I[i]) and np.array_equal(Di[0], D[i])
+        else:                  # the batch fell back to split precision: equal within the parity tolerance
+            assert oracle.compare_topk(Di, Ii, D[i:i + 1], I[i:i + 1], rtol=RTOL, atol=0.0)["ok"]
 
 
 def test_memory_accounting_is_bounded():
