@@ -262,9 +262,43 @@ def bilingual_bytes(qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int =
     return _take_bytes(raw, nraw), _take_bytes(col, ncol)
 
 
-def write_bilingual_trec(raw_path, col_path, qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int = 0):
+def collapse_max_device(D, I, codes_dev, ndocs: int):
+    """Collapse-by-base-id (fuse = max) of one alpha's (D, I) [nq, k] on the GPU (``cmx_collapse_max``): D, I are CUDA
+    tensors or pinned host tensors (read in place through their device alias), ``codes_dev`` the int32 base code of
+    every corpus row on the device.  Returns host numpy arrays (codes [nq,k], val6 [nq,k], counts [nq]) for
+    ``write_bilingual_trec(..., groups=...)``, or None when a score cannot be carried exactly on the device."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+    from .engine import host_register
+
+    nq, k = int(D.shape[0]), int(D.shape[1])
+    dev = codes_dev.device
+
+    def ptr(t):
+        if t.is_cuda:
+            return int(t.data_ptr())
+        assert t.is_pinned(), "host results must be page-locked to be read by the kernel in place"
+        return host_register(t.data_ptr(), t.numel() * t.element_size())
+
+    code = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    val6 = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+    needs_host = C.c_int(0)
+    _lib.check(_lib.lib().cmx_collapse_max(ptr(D), ptr(I), nq, k, int(codes_dev.data_ptr()), int(ndocs), int(code.data_ptr()),
+                                           int(val6.data_ptr()), int(cnt.data_ptr()), C.byref(needs_host), dev.index,
+                                           int(torch.cuda.current_stream(dev).cuda_stream)))
+    if needs_host.value:
+        return None
+    return code.cpu().numpy(), val6.cpu().numpy(), cnt.cpu().numpy()
+
+
+def write_bilingual_trec(raw_path, col_path, qids: Sequence[str], D, I, id2doc, tag: str, nthreads: int = 0, groups=None):
     """``bilingual_bytes`` written straight to the raw and the collapsed run file (temporary
-    names, then renamed).  Returns the two file sizes."""
+    names, then renamed).  ``groups`` = the collapsed lists of ``collapse_max_device`` (else the
+    formatter groups on the host).  Returns the two file sizes."""
     import ctypes as C
 
     from . import _lib
@@ -283,10 +317,20 @@ def write_bilingual_trec(raw_path, col_path, qids: Sequence[str], D, I, id2doc, 
     nraw, ncol = C.c_int64(0), C.c_int64(0)
     t_raw, t_col = _tmp_name(raw_path), _tmp_name(col_path)
     try:
-        _lib.check(_lib.lib().cmx_trec_bilingual_file(D.ctypes.data, I.ctypes.data, nq, k, q.buf, q.off.ctypes.data, bt.docs.buf,
-                                                      bt.docs.off.ctypes.data, bt.docs.n, bt.codes.ctypes.data, bt.bases.buf,
-                                                      bt.bases.off.ctypes.data, bt.bases.n, tag.encode("utf-8"), int(nthreads),
-                                                      os.fsencode(t_raw), os.fsencode(t_col), C.byref(nraw), C.byref(ncol)))
+        if groups is not None:
+            gc, gv, gn = (np.ascontiguousarray(groups[0], dtype=np.int32), np.ascontiguousarray(groups[1], dtype=np.int64),
+                          np.ascontiguousarray(groups[2], dtype=np.int32))
+            assert gc.shape == (nq, k) and gv.shape == (nq, k) and gn.shape == (nq,)
+            _lib.check(_lib.lib().cmx_trec_bilingual_file_pre(
+                D.ctypes.data, I.ctypes.data, nq, k, q.buf, q.off.ctypes.data, bt.docs.buf, bt.docs.off.ctypes.data, bt.docs.n,
+                bt.codes.ctypes.data, bt.bases.buf, bt.bases.off.ctypes.data, bt.bases.n, gc.ctypes.data, gv.ctypes.data,
+                gn.ctypes.data, tag.encode("utf-8"), int(nthreads), os.fsencode(t_raw), os.fsencode(t_col), C.byref(nraw),
+                C.byref(ncol)))
+        else:
+            _lib.check(_lib.lib().cmx_trec_bilingual_file(D.ctypes.data, I.ctypes.data, nq, k, q.buf, q.off.ctypes.data, bt.docs.buf,
+                                                          bt.docs.off.ctypes.data, bt.docs.n, bt.codes.ctypes.data, bt.bases.buf,
+                                                          bt.bases.off.ctypes.data, bt.bases.n, tag.encode("utf-8"), int(nthreads),
+                                                          os.fsencode(t_raw), os.fsencode(t_col), C.byref(nraw), C.byref(ncol)))
         os.replace(t_raw, raw_path)
         os.replace(t_col, col_path)
     finally:
@@ -402,6 +446,43 @@ class _SweepIO:
         return slot[0].numpy(), slot[1].numpy()
 
 
+class _DeviceCollapse:
+    """Per-alpha collapse-by-base-id on the GPU for the bilingual sweep: the base code of every corpus row is uploaded
+    once; each alpha's (D, I) is grouped where it lies (device tensors of a single-GPU index, or the pinned host
+    buffer a sharded index delivers, read through its device alias).  ``run`` returns one entry per alpha: the host
+    arrays for ``write_bilingual_trec(groups=...)`` or None (the formatter groups on the host: no CUDA, pageable
+    results, or a score the device keys cannot carry exactly)."""
+
+    def __init__(self, table: "BaseTable"):
+        self.table, self.codes, self.torch = table, {}, None
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                self.torch = torch
+        except Exception:
+            pass
+
+    def run(self, D, I, nA: int):
+        torch = self.torch
+        if torch is None:
+            return [None] * nA
+        try:
+            Dt = D if isinstance(D, torch.Tensor) else torch.from_numpy(np.asarray(D))
+            It = I if isinstance(I, torch.Tensor) else torch.from_numpy(np.asarray(I))
+            if not Dt.is_cuda and not (Dt.is_pinned() and It.is_pinned()):
+                return [None] * nA
+            if It.dtype != torch.int64 or Dt.dtype != torch.float32 or Dt.shape[-1] > 2048:
+                return [None] * nA
+            dev = Dt.device if Dt.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            codes = self.codes.get(dev)
+            if codes is None:
+                codes = self.codes[dev] = torch.from_numpy(self.table.codes).to(dev)
+            return [collapse_max_device(Dt[a].contiguous(), It[a].contiguous(), codes, self.table.docs.n) for a in range(nA)]
+        except Exception:  # any surprise: the host grouping is always right
+            return [None] * nA
+
+
 def run_alpha_sweep(index, id_lookup, qids: Sequence[str], P, S, alphas: Sequence[float], outdir,
                     k: int = 100, qblock: int = 256, tag: str = "onepass-cm", alpha_batch: int = 1,
                     log=None) -> List[pathlib.Path]:
@@ -466,22 +547,24 @@ def run_alpha_sweep_bilingual(index, id2doc: Sequence[str], qids: Sequence[str],
     alphas = [float(a) for a in alphas]
     ntotal, dim = int(index.ntotal), int(index.d)
     sio = _SweepIO(index, P, S)
+    collapse = _DeviceCollapse(table)
     with ThreadPoolExecutor(max_workers=1) as pool:  # text of alpha i overlaps the search of alpha i+1
         pending = None
         for a0 in range(0, len(alphas), max(1, alpha_batch)):
             group = alphas[a0 : a0 + max(1, alpha_batch)]
             D, I = index.search_mixed(sio.P, sio.S, group, topk)
+            groups = collapse.run(D, I, len(group))  # collapse-by-base-id where the results lie
             if pending is not None:
                 pending.result()
             D, I = sio.to_host(D, I)
 
-            def emit(group=group, D=D, I=I):
+            def emit(group=group, D=D, I=I, groups=groups):
                 for gi, alpha in enumerate(group):
                     label = format_alpha(alpha)
                     set_name = f"cm-alpha-{label}"
                     run_raw = outdir / f"{set_name}_raw.trec"
                     run_base = outdir / f"{set_name}.trec"
-                    write_bilingual_trec(run_raw, run_base, qids, D[gi], I[gi], table, tag)
+                    write_bilingual_trec(run_raw, run_base, qids, D[gi], I[gi], table, tag, groups=groups[gi])
                     m = dict(meta or {})
                     m.update({"alpha": label, "runs": {"raw": str(run_raw), "base": str(run_base)},
                               "index": {"type": "IndexIDMap(IndexFlatIP)", "size": ntotal, "dim": dim},

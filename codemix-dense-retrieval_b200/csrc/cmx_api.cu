@@ -1483,6 +1483,35 @@ int cmx_merge_topk_peers(const float* const* D_parts, const int64_t* const* I_pa
   return launch_merge_peers(D_parts, I_parts, nparts, k, q0, q1, D_outs, I_outs, nouts, (cudaStream_t)stream);
 }
 
+int cmx_collapse_max(const float* D, const int64_t* I, int64_t nq, int k, const int32_t* base_code, int64_t ndocs,
+                     int32_t* col_code, int64_t* col_val6, int32_t* col_count, int* needs_host, int device, void* stream) {
+  CMX_CHECK(nq >= 0 && k >= 1 && k <= CMX_MAX_K && ndocs >= 0, "bad shape");
+  CMX_CHECK(needs_host != nullptr, "null status");
+  *needs_host = 0;
+  if (nq == 0) return CMX_OK;
+  CMX_CHECK(D && I && base_code && col_code && col_val6 && col_count, "null buffer");
+  int ndev = 0;
+  CMX_TRY(cmx_device_count(&ndev));
+  CMX_CHECK(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+  DevGuard g(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  CMX_NVTX("cmx:collapse_max");
+  uint32_t* status = nullptr;
+  CMX_CUDA(cudaMalloc((void**)&status, sizeof(uint32_t)));
+  cudaError_t e = cudaMemsetAsync(status, 0, sizeof(uint32_t), st);
+  int rc = e == cudaSuccess ? launch_collapse_max(D, I, nq, k, base_code, ndocs, col_code, col_val6, col_count, status, st) : CMX_ERR_CUDA;
+  uint32_t h = 0;
+  if (rc == CMX_OK) {
+    e = cudaMemcpyAsync(&h, status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = CMX_ERR_CUDA;
+  }
+  cudaFree(status);
+  if (rc == CMX_ERR_CUDA && e != cudaSuccess) set_error("collapse: %s", cudaGetErrorString(e));
+  *needs_host = h ? 1 : 0;
+  return rc;
+}
+
 /* test hook (not in cmx.h): tensor tile width 256 / 128 */
 CMX_API int cmx_debug_set_tensor_tile(int bn) { set_tensor_tile(bn); return CMX_OK; }
 CMX_API int cmx_debug_set_block_order(int on) { g_block_order = on ? 1 : 0; return CMX_OK; }

@@ -153,6 +153,9 @@ int launch_fill_f32(float* out, int64_t n, float v, cudaStream_t st);
 int launch_publish_flag(const uint32_t* overflow, uint32_t extra, uint32_t* flag_out, cudaStream_t st);
 int launch_max_bounds(const float* const* parts, int nparts, float* out2, cudaStream_t st);
 int launch_peer_broadcast(const void* src, void* const* dsts, int ndst, int64_t bytes, cudaStream_t st);
+// collapse-by-base-id, fuse = max (collapse.cu): per query the (base code, 6-decimal value) groups in final order
+int launch_collapse_max(const float* D, const int64_t* I, int64_t nq, int k, const int32_t* base_code, int64_t ndocs,
+                        int32_t* out_code, int64_t* out_val6, int32_t* out_count, uint32_t* status, cudaStream_t st);
 int launch_gather_rows(const float* X, const int64_t* rows_dev, int64_t n, int d, float* dst, cudaStream_t st);
 int launch_decode_keys(const uint64_t* keys, int64_t n, float* scores, int64_t* rows, cudaStream_t st);
 

@@ -234,6 +234,8 @@ void format_mono(const MonoArgs& a, int nthreads, std::vector<Part>& parts) {
 struct BiArgs {
   const float* D; const int64_t* I; int64_t nq; int k;
   StrTable q, dt, bt; const int32_t* base_code; const char* tag;
+  // collapsed groups computed on the device (cmx_collapse_max), or NULL: group here
+  const int32_t* pre_code = nullptr; const int64_t* pre_val6 = nullptr; const int32_t* pre_count = nullptr;
 };
 
 void format_bilingual(const BiArgs& a, int nthreads, std::vector<Part>& raw, std::vector<Part>& col) {
@@ -296,6 +298,7 @@ void format_bilingual(const BiArgs& a, int nthreads, std::vector<Part>& raw, std
         *p++ = ' ';
         p = put_str(p, a.tag, tag_len);
         *p++ = '\n';
+        if (a.pre_code) continue;  // the groups of this query come from the device
         // collapse on the value the raw file carries: the 6-decimal rounded score
         const double ax = std::fabs((double)sc);
         const bool small = std::isfinite(sc) && ax < 1e11;
@@ -314,8 +317,17 @@ void format_bilingual(const BiArgs& a, int nthreads, std::vector<Part>& raw, std
           if (cmp(cand, g) > 0) g = cand;
         }
       }
+      if (a.pre_code) {
+        const int cnt = a.pre_count[r];
+        for (int gi = 0; gi < cnt; ++gi) {
+          const int32_t code = a.pre_code[r * a.k + gi];
+          const int64_t v6 = a.pre_val6[r * a.k + gi];
+          groups.push_back(Grp{code, v6 < 0 ? -v6 : v6, v6 < 0, false, 0.f});
+        }
+      }
       order.resize(groups.size());
       for (size_t i = 0; i < groups.size(); ++i) order[i] = (int)i;
+      if (!a.pre_code)
       std::stable_sort(order.begin(), order.end(),
                        [&](int x, int y) { return cmp(groups[(size_t)x], groups[(size_t)y]) > 0; });
       uint64_t rank = 1;
@@ -427,6 +439,34 @@ int cmx_trec_bilingual_file(const float* D, const int64_t* I, int64_t nq, int k,
   format_bilingual(a, nt, raw, col);
   int rc = write_parts(raw, raw_path, raw_len, "cmx_trec_bilingual_file");
   if (rc == CMX_OK) rc = write_parts(col, col_path, col_len, "cmx_trec_bilingual_file");
+  return rc;
+}
+
+int cmx_trec_bilingual_file_pre(const float* D, const int64_t* I, int64_t nq, int k, const char* qids,
+                                const int64_t* qid_off, const char* docs, const int64_t* doc_off, int64_t ndocs,
+                                const int32_t* base_code, const char* bases, const int64_t* base_off, int64_t nbases,
+                                const int32_t* col_code, const int64_t* col_val6, const int32_t* col_count,
+                                const char* tag, int nthreads, const char* raw_path, const char* col_path,
+                                int64_t* raw_len, int64_t* col_len) {
+  if (!bi_args_ok(D, I, nq, k, qids, qid_off, docs, doc_off, base_code, bases, base_off, tag) || !raw_path || !col_path ||
+      !raw_len || !col_len || !col_code || !col_val6 || !col_count) {
+    cmx::set_error("cmx_trec_bilingual_file_pre: bad argument");
+    return CMX_ERR_INVALID;
+  }
+  for (int64_t r = 0; r < nq; ++r) {
+    if (col_count[r] < 0 || col_count[r] > k) { cmx::set_error("cmx_trec_bilingual_file_pre: bad group count"); return CMX_ERR_INVALID; }
+    for (int g = 0; g < col_count[r]; ++g)
+      if (col_code[r * k + g] < 0 || col_code[r * k + g] >= nbases) { cmx::set_error("cmx_trec_bilingual_file_pre: bad base code"); return CMX_ERR_INVALID; }
+  }
+  BiArgs a{D, I, nq, k, {qids, qid_off, nq}, {docs, doc_off, ndocs}, {bases, base_off, nbases}, base_code, tag};
+  a.pre_code = col_code;
+  a.pre_val6 = col_val6;
+  a.pre_count = col_count;
+  const int nt = pick_threads(nthreads, nq);
+  std::vector<Part> raw((size_t)nt), col((size_t)nt);
+  format_bilingual(a, nt, raw, col);
+  int rc = write_parts(raw, raw_path, raw_len, "cmx_trec_bilingual_file_pre");
+  if (rc == CMX_OK) rc = write_parts(col, col_path, col_len, "cmx_trec_bilingual_file_pre");
   return rc;
 }
 

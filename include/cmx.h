@@ -253,6 +253,27 @@ CMX_API int cmx_trec_bilingual_file(const float* D, const int64_t* I, int64_t nq
                                     const char* raw_path, const char* col_path, int64_t* raw_len,
                                     int64_t* col_len);
 
+/* ---- collapse-by-base-id on the device ------------------------------------------------
+ * replaces the grouping of collapse_run_max (onepass_bilingual_mix_hub_custom_lang.py:165-181), which re-parses
+ * the raw run text: D, I [nq,k] and base_code [ndocs] (the base-id number of every corpus row; derived id =
+ * "<base>#<lang>") are DEVICE pointers (or device aliases of pinned host memory) on `device`; per query the
+ * groups come out in final order: col_code / col_val6 [nq,k] (base code, sign * rint(|score| * 1e6) = the value
+ * the raw file prints), col_count [nq] (device).  Max over the 6-decimal rounded scores, stable descending order
+ * (equal values keep the order in which their bases first appeared), hits with ids outside [0, ndocs) skipped.
+ * *needs_host = 1 when some score cannot be carried exactly (non-finite, |score| >= 2^20, a negative zero): use
+ * the host grouping of cmx_trec_bilingual_file for that batch.  Synchronous.
+ * cmx_trec_bilingual_file_pre = cmx_trec_bilingual_file with the groups given (HOST arrays). */
+CMX_API int cmx_collapse_max(const float* D, const int64_t* I, int64_t nq, int k, const int32_t* base_code,
+                             int64_t ndocs, int32_t* col_code, int64_t* col_val6, int32_t* col_count,
+                             int* needs_host, int device, void* stream);
+CMX_API int cmx_trec_bilingual_file_pre(const float* D, const int64_t* I, int64_t nq, int k, const char* qids,
+                                        const int64_t* qid_off, const char* docs, const int64_t* doc_off,
+                                        int64_t ndocs, const int32_t* base_code, const char* bases,
+                                        const int64_t* base_off, int64_t nbases, const int32_t* col_code,
+                                        const int64_t* col_val6, const int32_t* col_count, const char* tag,
+                                        int nthreads, const char* raw_path, const char* col_path,
+                                        int64_t* raw_len, int64_t* col_len);
+
 /* ---- instrumentation --------------------------------------------------------*/
 typedef struct cmx_search_stats {
   int32_t path;            /* CMX_PATH_STREAM / CMX_PATH_TENSOR actually used       */

@@ -50,3 +50,32 @@ def precision(request):
     _lib.set_default_precision(request.param)
     yield request.param
     _lib.set_default_precision("rescore")
+
+
+def collapse_groups_ref(D, I, codes, ndocs):
+    """numpy restatement of cmx_collapse_max (csrc/collapse.cu): per query the (base code, sign * rint(|score| * 1e6))
+    groups in final order -- max over the 6-decimal values, descending, equal values in first-seen order."""
+    import numpy as np
+
+    nq, k = D.shape
+    out_c = np.full((nq, k), -1, np.int32)
+    out_v = np.zeros((nq, k), np.int64)
+    out_n = np.zeros((nq,), np.int32)
+    for r in range(nq):
+        first, best = {}, {}
+        for j in range(k):
+            ix = int(I[r, j])
+            if ix < 0 or ix >= ndocs:
+                continue
+            s = float(D[r, j])
+            v = int(np.rint(abs(s) * 1e6)) * (-1 if s < 0 else 1)
+            c = int(codes[ix])
+            if c not in first:
+                first[c], best[c] = j, v
+            elif v > best[c]:
+                best[c] = v
+        order = sorted(first, key=lambda c: (-best[c], first[c]))
+        out_n[r] = len(order)
+        for g, c in enumerate(order):
+            out_c[r, g], out_v[r, g] = c, best[c]
+    return out_c, out_v, out_n

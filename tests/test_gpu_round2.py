@@ -351,6 +351,67 @@ def test_mixed_query_norms_in_one_batch_stay_exact():
             assert oracle.compare_topk(Di, Ii, D[i:i + 1], I[i:i + 1], rtol=RTOL, atol=0.0)["ok"]
 
 
+def test_device_collapse_by_base_id(golden_dir, tmp_path):
+    """cmx_collapse_max: grouping by base id with fuse = max on the GPU -- equal to its numpy restatement,
+    and the run files written from it byte-identical to the reference's text round trip (oracle + the golden fixture
+    produced by the reference's own collapse_run_max)."""
+    import json
+
+    import torch
+    from conftest import collapse_groups_ref
+
+    from cmx import runloop
+
+    rng = np.random.default_rng(81)
+    nq, k, nrows = 300, 500, 40_000
+    D = -np.sort(-rng.uniform(0.2, 0.9, (nq, k)).astype(np.float32), axis=1)
+    I = rng.integers(0, nrows, (nq, k)).astype(np.int64)
+    I[:, 1::3] = (I[:, 0::3][:, : I[:, 1::3].shape[1]] + nrows // 2) % nrows  # the other language of the hit before: same base
+    D[:, 10] = D[:, 9]                                   # exact ties
+    D[:, 21] = D[:, 20] - np.float32(3e-8)               # ties after 6-decimal rounding
+    D[7, 300:] = -np.abs(D[7, 300:])                     # negative scores sort last
+    I[2, 5], I[4, 8] = -1, nrows + 3                     # skipped hits
+    id2doc = [f"{i % (nrows // 2)}#{'en' if i < nrows // 2 else 'zh'}" for i in range(nrows)]
+    bt = runloop.BaseTable(id2doc)
+    codes_dev = torch.from_numpy(bt.codes).cuda()
+    want = collapse_groups_ref(D, I, bt.codes, nrows)
+    for Dt, It in ((torch.from_numpy(D).cuda(), torch.from_numpy(I).cuda()),           # device results (one GPU)
+                   (torch.from_numpy(D).pin_memory(), torch.from_numpy(I).pin_memory())):  # pinned host results (shards)
+        got = runloop.collapse_max_device(Dt, It, codes_dev, nrows)
+        assert got is not None
+        assert np.array_equal(got[2], want[2])
+        for r in range(nq):
+            n = int(want[2][r])
+            assert np.array_equal(got[0][r, :n], want[0][r, :n]) and np.array_equal(got[1][r, :n], want[1][r, :n])
+    qids = [str(100 + i) for i in range(nq)]
+    tag = "bilingual-mix-en-zh"
+    runloop.write_bilingual_trec(tmp_path / "raw.trec", tmp_path / "col.trec", qids, D, I, bt, tag, groups=got)
+    raw_lines = oracle.bilingual_raw_lines(qids, D, I, id2doc, tag)
+    assert (tmp_path / "raw.trec").read_text() == "".join(raw_lines)
+    assert (tmp_path / "col.trec").read_text() == oracle.collapse_run_max_text(raw_lines)
+    # scores the 64-bit keys cannot carry exactly are reported, not mangled
+    Dbad = D.copy()
+    Dbad[0, 0] = np.float32(3e7)
+    assert runloop.collapse_max_device(torch.from_numpy(Dbad).cuda(), torch.from_numpy(I).cuda(), codes_dev, nrows) is None
+    Dbad[0, 0] = np.float32(-0.0)
+    assert runloop.collapse_max_device(torch.from_numpy(Dbad).cuda(), torch.from_numpy(I).cuda(), codes_dev, nrows) is None
+    # the golden fixture: raw lines in, the reference's own collapsed text out
+    g = json.loads((golden_dir / "text_golden.json").read_text())["collapse"]
+    rows = [l.split() for l in g["raw"]]
+    gq = sorted({r[0] for r in rows}, key=lambda x: int(x[1:]))
+    dids = sorted({r[2] for r in rows})
+    bt2 = runloop.BaseTable(dids)
+    kk = max(int(r[3]) for r in rows)
+    Dg = np.zeros((len(gq), kk), np.float32)
+    Ig = np.full((len(gq), kk), -1, np.int64)
+    for qid, _, did, rank, sc, _ in rows:
+        Dg[gq.index(qid), int(rank) - 1] = np.float32(sc)
+        Ig[gq.index(qid), int(rank) - 1] = dids.index(did)
+    grp = runloop.collapse_max_device(torch.from_numpy(Dg).cuda(), torch.from_numpy(Ig).cuda(), torch.from_numpy(bt2.codes).cuda(), len(dids))
+    runloop.write_bilingual_trec(tmp_path / "graw.trec", tmp_path / "gcol.trec", gq, Dg, Ig, bt2, "bilingual-mix-en-zh", groups=grp)
+    assert (tmp_path / "gcol.trec").read_text() == g["out"]
+
+
 def test_memory_accounting_is_bounded():
     """Default precision = fp32 store + ONE fp16 plane = 1.5x a FAISS flat index (+ a workspace that does not grow
     with the corpus); the split precision adds the second plane (2x)."""

@@ -137,6 +137,36 @@ def test_bilingual_raw_and_collapse_equal_oracle():
     assert runloop.bilingual_bytes(qids, D, I, id2doc, "x")[1].decode("utf-8") == want
 
 
+def test_bilingual_writer_with_precomputed_groups(tmp_path):
+    """cmx_trec_bilingual_file_pre: the collapsed run written from group lists (what cmx_collapse_max produces on
+    the device; here its numpy restatement) is byte-identical to the host grouping and to the oracle's text round trip."""
+    from conftest import collapse_groups_ref
+
+    rng = np.random.default_rng(8)
+    nq, k, nrows = 11, 70, 90
+    D, I = _fake_results(rng, nq, k, nrows)
+    D[:, 10] = D[:, 9]
+    D[:, 21] = D[:, 20] - np.float32(3e-8)
+    D[3, 40:] = -np.abs(D[3, 40:])  # negative scores
+    I[2, 5] = -1
+    I[4, 8] = nrows + 3
+    id2doc = [f"{i // 2}#{'en' if i % 2 == 0 else 'zh'}" for i in range(nrows)]
+    qids = [f"q{i}" for i in range(nq)]
+    tag = "bilingual-mix-en-zh"
+    bt = runloop.BaseTable(id2doc)
+    groups = collapse_groups_ref(D, I, bt.codes, nrows)
+    runloop.write_bilingual_trec(tmp_path / "raw_a.trec", tmp_path / "col_a.trec", qids, D, I, bt, tag)
+    runloop.write_bilingual_trec(tmp_path / "raw_b.trec", tmp_path / "col_b.trec", qids, D, I, bt, tag, groups=groups)
+    assert (tmp_path / "raw_a.trec").read_bytes() == (tmp_path / "raw_b.trec").read_bytes()
+    assert (tmp_path / "col_a.trec").read_bytes() == (tmp_path / "col_b.trec").read_bytes()
+    raw_lines = oracle.bilingual_raw_lines(qids, D, I, id2doc, tag)
+    assert (tmp_path / "col_b.trec").read_text() == oracle.collapse_run_max_text(raw_lines)
+    bad = (groups[0].copy(), groups[1], groups[2])
+    bad[0][0, 0] = 10**6  # a base code outside the table is refused, not dereferenced
+    with pytest.raises(RuntimeError):
+        runloop.write_bilingual_trec(tmp_path / "r.trec", tmp_path / "c.trec", qids, D, I, bt, tag, groups=bad)
+
+
 class _OracleIndex:
     """Stands in for a cmx.faiss index in the sweep loops (CPU): search_mixed through the oracle."""
 
