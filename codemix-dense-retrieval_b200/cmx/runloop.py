@@ -446,6 +446,9 @@ class _SweepIO:
         return slot[0].numpy(), slot[1].numpy()
 
 
+LAST_SWEEP: dict = {}  # bookkeeping of the last bilingual sweep: how many alphas were collapsed on the device / on the host
+
+
 class _DeviceCollapse:
     """Per-alpha collapse-by-base-id on the GPU for the bilingual sweep: the base code of every corpus row is uploaded
     once; each alpha's (D, I) is grouped where it lies (device tensors of a single-GPU index, or the pinned host
@@ -478,8 +481,11 @@ class _DeviceCollapse:
             codes = self.codes.get(dev)
             if codes is None:
                 codes = self.codes[dev] = torch.from_numpy(self.table.codes).to(dev)
-            return [collapse_max_device(Dt[a].contiguous(), It[a].contiguous(), codes, self.table.docs.n) for a in range(nA)]
-        except Exception:  # any surprise: the host grouping is always right
+            out = [collapse_max_device(Dt[a].contiguous(), It[a].contiguous(), codes, self.table.docs.n) for a in range(nA)]
+            LAST_SWEEP["device_collapse"] = LAST_SWEEP.get("device_collapse", 0) + sum(g is not None for g in out)
+            return out
+        except Exception as exc:  # any surprise: the host grouping is always right
+            LAST_SWEEP["device_collapse_error"] = repr(exc)
             return [None] * nA
 
 
@@ -547,6 +553,7 @@ def run_alpha_sweep_bilingual(index, id2doc: Sequence[str], qids: Sequence[str],
     alphas = [float(a) for a in alphas]
     ntotal, dim = int(index.ntotal), int(index.d)
     sio = _SweepIO(index, P, S)
+    LAST_SWEEP.clear()
     collapse = _DeviceCollapse(table)
     with ThreadPoolExecutor(max_workers=1) as pool:  # text of alpha i overlaps the search of alpha i+1
         pending = None

@@ -111,6 +111,9 @@ def test_bilingual_cli(tmp_path):
     assert oracle.compare_topk(D, I, Dr, Ir, rtol=1e-5, atol=1e-6)["ok"]
     meta = json.loads((out / "cm-alpha-0.5_meta.json").read_text())
     assert meta["index"]["size"] == 2 * N and meta["topk"] == 200
+    from cmx import runloop
+
+    assert runloop.LAST_SWEEP.get("device_collapse") == 1, runloop.LAST_SWEEP  # the collapsed run came from cmx_collapse_max
 
 
 def test_bilingual_cli_sharded_and_unordered_map(tmp_path, monkeypatch):
@@ -136,10 +139,14 @@ def test_bilingual_cli_sharded_and_unordered_map(tmp_path, monkeypatch):
         assert rc == 0
         return {p.name: p.read_bytes() for p in sorted((tmp_path / outname).iterdir()) if p.suffix in (".trec", ".tsv")}
 
+    from cmx import runloop
+
     one = run("one", tmp_path / "idx")
+    assert runloop.LAST_SWEEP.get("device_collapse") == 2, runloop.LAST_SWEEP
     monkeypatch.setenv("CMX_DEVICES", "0,0,0")
     three = run("three", tmp_path / "idx")
     monkeypatch.delenv("CMX_DEVICES")
+    assert runloop.LAST_SWEEP.get("device_collapse") == 2, runloop.LAST_SWEEP  # pinned host results of the shards, read in place
     assert one.keys() == three.keys() and all(one[k] == three[k] for k in one)
     # a map whose lines come in reversed order: the reference sorts each batch of 20 000 lines by int id, so with
     # fewer lines than one batch the combined row order is the storage order again -- same files
