@@ -1066,10 +1066,14 @@ static int g_tc_bn = 256;  // tile width in corpus rows: 256 (2 stages) or 128 (
 static int g_tc_flags = 0;
 static int g_tc_window = 3;  // progress throttle: a CTA may run this many round-robin iterations ahead (0 = off)
 void set_tensor_window(int w) { g_tc_window = w < 0 ? 3 : w; }
-// CTA-pair kernel (cta_group::2) for nq > 128.  Measured on B200 at C2 (profiles/): with three MMA
-// passes both kernels sit at the tensor peak (within 3 %); with one pass and the progress throttle
-// the single-CTA kernel is ahead (116.6 vs 122.3 ms), so it is the default and the pair kernel
-// stays selectable (-1 = default = off).
+// CTA-pair kernel (cta_group::2) for nq > 128: each CTA stages half of the corpus tile, so a third less L2 -> shared
+// memory traffic per FLOP.  Measured alternating in one process, randomised order (profiles/r02_variants_ab.md):
+//   8.8 M rows  single 106.3 ms per step, pair 104.8      4.4 M rows  56.9 / 56.2
+//   2.2 M rows  31.6 / 31.4                                1.1 M rows  18.6 / 19.2 (pair SLOWER)
+// Long launches run at the 1000 W power cap, where fewer bytes moved per FLOP buy clock; short launches are not
+// power-limited and the single-CTA kernel's finer tile granularity wins.  -1 = automatic: pair for slabs of at least
+// kPairMinRows rows, 0 = never, 1 = always.
+constexpr int64_t kPairMinRows = 3 << 20;
 static int g_tc_pair = -1;
 void set_tensor_pair(int on) { g_tc_pair = (on < 0) ? -1 : (on ? 1 : 0); }
 void set_tensor_tile(int bn) { g_tc_bn = (bn == 128) ? 128 : 256; }
@@ -1184,7 +1188,7 @@ int launch_tensor_score(const __half* Bhi, const __half* Blo, int64_t plane_rows
     if (nq <= 16) return launch_tc_small<16, 8, 1>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
     return launch_tc_small<32, 8, 1>(Bhi, Blo, plane_rows, Qhi, Qlo, nq_pad, d_pad, p, st, sm_count);
   }
-  const bool pair = g_tc_pair > 0 && nq > 128;
+  const bool pair = nq > 128 && (g_tc_pair > 0 || (g_tc_pair < 0 && nrows >= kPairMinRows));
   const int bn = pair ? 128 : g_tc_bn;  // pair: each CTA loads a 128-row half of the 256-row tile
   CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;
   CMX_TRY(make_plane_map(&tq_hi, Qhi, nq_pad, d_pad, TC_BM));

@@ -1,0 +1,43 @@
+"""A/B inside one process: scoring-kernel variants (single-CTA 256-wide tile = default, CTA-pair cta_group::2, 128-wide
+tile), alternating, on a shard-sized and on the full corpus.  An 8-GPU shard is NOT power-capped (short bursts,
+~550 W, 1.7-1.9 GHz), the full corpus on one GPU is (1000 W, 1.3 GHz): the best variant may differ."""
+import json, sys, pathlib, statistics
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT), str(ROOT / "codemix-dense-retrieval_b200")]
+import torch, bench
+from cmx import _lib
+from cmx.engine import Shard
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1_105_228
+dev = torch.device("cuda", 0)
+d, nq, k = 1024, 6980, 1000
+sh = Shard(d, 0); sh.reserve(rows); bench.fill_rows(sh.add, 0, rows, d, dev, rows)
+P, S = bench.make_queries(nq, d, dev)
+_lib.set_profiling(True)
+L = _lib.lib()
+variants = {"single256": dict(pair=-1, tile=256), "pair": dict(pair=1, tile=256), "single128": dict(pair=-1, tile=128)}
+if len(sys.argv) > 2:
+    variants = {n: variants[n] for n in sys.argv[2].split(",")}
+rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+import random
+random.seed(1)
+res = {n: [] for n in variants}
+ref = None
+for rnd in range(rounds):
+    order = list(variants.items())
+    random.shuffle(order)  # no variant always runs right after the same other one
+    for name, v in order:
+        _lib.check(L.cmx_debug_set_tensor_pair(v["pair"])); _lib.check(L.cmx_debug_set_tensor_tile(v["tile"]))
+        D, I = sh.search_mixed(P, S, [0.5], k)
+        if ref is None: ref = (D.clone(), I.clone())
+        assert torch.equal(D, ref[0]) and torch.equal(I, ref[1]), name
+        sc = tot = 0.0
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); sh.search_mixed(P, S, [0.5], k); e1.record(); torch.cuda.synchronize()
+            sc += sh.last_stats()["score_ms"]; tot += e0.elapsed_time(e1)
+        res[name].append((tot / 4, sc / 4))
+_lib.check(L.cmx_debug_set_tensor_pair(-1)); _lib.check(L.cmx_debug_set_tensor_tile(256))
+for name in variants:
+    t = [a for a, _ in res[name]]; s = [b for _, b in res[name]]
+    print(json.dumps({"variant": name, "rows": rows, "ms_per_step": [round(x, 2) for x in t], "median_ms": round(statistics.median(t), 2),
+                      "median_score_ms": round(statistics.median(s), 2)}), flush=True)
