@@ -14,7 +14,7 @@ sh = Shard(d, 0); sh.reserve(rows); bench.fill_rows(sh.add, 0, rows, d, dev, row
 P, S = bench.make_queries(nq, d, dev)
 _lib.set_profiling(True)
 L = _lib.lib()
-variants = {"single256": dict(pair=-1, tile=256), "pair": dict(pair=1, tile=256), "single128": dict(pair=-1, tile=128)}
+variants = {"single256": dict(pair=0, tile=256), "pair": dict(pair=1, tile=256), "single128": dict(pair=0, tile=128)}
 if len(sys.argv) > 2:
     variants = {n: variants[n] for n in sys.argv[2].split(",")}
 rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 5
