@@ -18,6 +18,7 @@ variants = {"single256": dict(pair=0, tile=256), "pair": dict(pair=1, tile=256),
 if len(sys.argv) > 2:
     variants = {n: variants[n] for n in sys.argv[2].split(",")}
 rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+block = int(sys.argv[4]) if len(sys.argv) > 4 else 4  # timed steps per variant and round
 import random
 random.seed(1)
 res = {n: [] for n in variants}
@@ -31,11 +32,11 @@ for rnd in range(rounds):
         if ref is None: ref = (D.clone(), I.clone())
         assert torch.equal(D, ref[0]) and torch.equal(I, ref[1]), name
         sc = tot = 0.0
-        for _ in range(4):
+        for _ in range(block):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); sh.search_mixed(P, S, [0.5], k); e1.record(); torch.cuda.synchronize()
             sc += sh.last_stats()["score_ms"]; tot += e0.elapsed_time(e1)
-        res[name].append((tot / 4, sc / 4))
+        res[name].append((tot / block, sc / block))
 _lib.check(L.cmx_debug_set_tensor_pair(-1)); _lib.check(L.cmx_debug_set_tensor_tile(256))
 for name in variants:
     t = [a for a, _ in res[name]]; s = [b for _, b in res[name]]
