@@ -554,6 +554,8 @@ def run_cmx(a) -> None:
 
     d, k, nq, N = a.dim, a.k, a.nq, a.rows
     _lib.set_default_precision(a.precision)
+    if os.environ.get("CMX_PAIR"):  # experiments: force the CTA-pair scorer on (1) / off (0)
+        _lib.check(_lib.lib().cmx_debug_set_tensor_pair(int(os.environ["CMX_PAIR"])))
 
     def make_index(rows_total):
         ix = ShardedIndex(d, rows_total, device=local_rank, exchange=a.exchange)

@@ -77,10 +77,12 @@ __device__ __forceinline__ int next_pow2(int n) {
   return p;
 }
 
+constexpr int kSelBins = 512;      // value bins of the first selection step
+constexpr int kSelListMax = 256;   // keys of the crossing bin that are ranked directly (they reuse hist)
 struct SelectShared {
-  uint32_t hist[256];
-  uint64_t red_min[32];
-  uint64_t red_max[32];
+  uint32_t hist[kSelBins];
+  uint64_t red_min[16];  // one per warp (kSelThreads = 512)
+  uint64_t red_max[16];
   uint64_t kmin, kmax;
   uint32_t bin, above, count, bin_count;
   uint64_t found;
@@ -117,6 +119,69 @@ __device__ uint64_t block_kth_largest(const uint64_t* keys, int n, int k, Select
   const uint64_t kmin = sh.kmin, kmax = sh.kmax;
   const uint64_t diff = kmin ^ kmax;
   if (diff == 0ull) return kmax;  // all keys equal: only possible for the null key
+  // Fast path.  Candidate scores are bell-shaped, so the leading radix digits (sign, exponent) put
+  // nearly all keys into one or two bins -- thousands of shared-memory atomics on one address, and
+  // four or five passes before the k-th is isolated.  Binning the SCORE linearly between the smallest
+  // and the largest spreads the keys over all kSelBins bins; float subtract, multiply and truncation
+  // are monotone, so bin order agrees with key order and the k-th largest key lies in the bin where
+  // the count from the top crosses k.  That bin's keys (a few dozen) are then ranked against each
+  // other on the full 64 bits.  Degenerate inputs (non-finite or padded scores, heavy ties: more than
+  // kSelListMax keys in the crossing bin) take the radix passes below.
+  {
+    const float smin = key_score(kmin), smax = key_score(kmax);
+    const float scale = (float)kSelBins / (smax - smin);
+    if (isfinite(smin) && isfinite(smax) && isfinite(scale) && scale > 0.f) {
+      for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) sh.hist[i] = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int b = min(kSelBins - 1, (int)((key_score(keys[i]) - smin) * scale));
+        atomicAdd(&sh.hist[b], 1u);
+      }
+      __syncthreads();
+      if (warp == 0) {
+        constexpr int kPer = kSelBins / 32;  // lane l owns bins [kPer l, kPer (l + 1))
+        uint32_t s = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) s += sh.hist[lane * kPer + j];
+        uint32_t incl = s;  // inclusive suffix sum over lanes (lane 31 = largest scores)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o);
+          if (lane + o < 32) incl += t;
+        }
+        uint32_t running = incl - s;
+        if (running < (uint32_t)k && (uint32_t)k <= incl) {  // the crossing bin is one of this lane's
+          for (int j = kPer - 1; j >= 0; --j) {
+            const uint32_t h = sh.hist[lane * kPer + j];
+            if ((uint32_t)k <= running + h) { sh.bin = lane * kPer + j; sh.above = running; sh.bin_count = h; break; }
+            running += h;
+          }
+        }
+        if (lane == 0) sh.count = 0;
+      }
+      __syncthreads();
+      const int b_k = (int)sh.bin, m = (int)sh.bin_count, want_in = k - (int)sh.above;
+      __syncthreads();  // hist is reused as the key list below
+      if (m <= kSelListMax) {
+        uint64_t* list = reinterpret_cast<uint64_t*>(sh.hist);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const uint64_t v = keys[i];
+          if (min(kSelBins - 1, (int)((key_score(v) - smin) * scale)) == b_k) list[atomicAdd(&sh.count, 1u)] = v;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < m; t += blockDim.x) {
+          const uint64_t v = list[t];
+          int larger = 0;
+          for (int j = 0; j < m; ++j) larger += list[j] > v;
+          if (larger == want_in - 1) sh.found = v;  // keys are distinct: exactly one thread
+        }
+        __syncthreads();
+        const uint64_t found = sh.found;
+        __syncthreads();  // callers reuse sh (and call again) right away
+        return found;
+      }
+    }
+  }
   const int top_byte = (63 - __clzll((long long)diff)) >> 3;
   // digits above top_byte are common to all keys
   uint64_t mask = (top_byte == 7) ? 0ull : (~0ull << ((top_byte + 1) * 8));
@@ -171,22 +236,54 @@ __device__ uint64_t block_kth_largest(const uint64_t* keys, int n, int k, Select
 // the keys >= kth (exactly k of them when kth is the k-th largest: real keys are distinct;
 // more when kth is a lowered cut-off), or -- when kth is the null key, i.e. fewer than k
 // real candidates exist -- all non-null keys.
-__device__ int block_partition(const uint64_t* keys, int n, uint64_t kth, uint64_t* dst, SelectShared& sh) {
+// INPLACE additionally packs the survivors to the front of `keys` itself.  Survivor number p lands
+// at keys[p] with p < (elements visited so far), so the only hazard is a slot of the chunk being
+// visited that another warp has not read yet: one barrier per chunk between the reads and the
+// writes removes it.
+template <bool INPLACE = false>
+__device__ int block_partition(uint64_t* keys, int n, uint64_t kth, uint64_t* dst, SelectShared& sh) {
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) sh.count = 0;
   __syncthreads();
   for (int base = 0; base < n; base += blockDim.x) {
     const int i = base + threadIdx.x;
     const uint64_t v = (i < n) ? keys[i] : 0ull;
+    if (INPLACE) __syncthreads();
     const bool keep = (i < n) && ((kth != 0ull) ? (v >= kth) : (v != 0ull));
     const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
     uint32_t wbase = 0;
     if (lane == 0 && ballot) wbase = atomicAdd(&sh.count, (uint32_t)__popc(ballot));
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (keep) dst[wbase + __popc(ballot & ((1u << lane) - 1u))] = v;
+    if (keep) {
+      const uint32_t pos = wbase + __popc(ballot & ((1u << lane) - 1u));
+      dst[pos] = v;
+      if (INPLACE) keys[pos] = v;
+    }
   }
   __syncthreads();
   return (int)sh.count;
+}
+
+// ---- list load: one bulk copy by the TMA engine ------------------------------------------------
+// A per-thread "keys[i] = buf[i]" loop keeps ONE 8-byte load in flight per thread (12 KB per SM with three
+// CTAs of 512 threads): ncu showed compact_kernel latency-bound on it (a quarter of all stall samples on the
+// first shared-memory store, DRAM at 1 TB/s).  One cp.async.bulk per CTA puts the whole list in flight.
+__device__ __forceinline__ uint32_t sel_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load_begin(uint64_t* smem_dst, const uint64_t* gsrc, uint32_t nbytes, uint64_t* bar) {
+  const uint32_t b = sel_smem_u32(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(nbytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sel_smem_u32(smem_dst)), "l"(gsrc), "r"(nbytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void bulk_load_wait(uint64_t* bar) {
+  const uint32_t b = sel_smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(b) : "memory");
+  } while (!ok);
 }
 
 // One CTA per query.  Keeps the query's best k candidates (plus, in rescore mode, the margin
@@ -213,6 +310,7 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
                float* __restrict__ D, int64_t* __restrict__ I, int64_t id_base) {
   extern __shared__ __align__(16) uint64_t keys[];
   __shared__ SelectShared sh;
+  __shared__ __align__(8) uint64_t load_bar;
   const int64_t q = blockIdx.x;
   const uint32_t n_raw = cnt[q];
   if (n_raw > (uint32_t)cap && threadIdx.x == 0) atomicOr(overflow, CMX_OVF_BUFFER);
@@ -230,8 +328,10 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
   if (est && est_rank > 0 && threadIdx.x == 0) est[q] = CMX_NEG_PAD;  // no estimate unless set below
   if (!final_pass && n <= k) return;  // nothing to drop yet; tau stays
   uint64_t* buf = cand + q * (int64_t)cap;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = buf[i];
-  __syncthreads();
+  const uint32_t nbytes = (uint32_t)((n + 1) & ~1) * 8u;  // whole 16-byte units (cap is even, so n + 1 <= cap for odd n)
+  if (threadIdx.x == 0 && nbytes) bulk_load_begin(keys, buf, nbytes, &load_bar);
+  __syncthreads();  // the barrier is initialised
+  if (nbytes) bulk_load_wait(&load_bar);
   uint64_t* top = keys + cap;  // survivors (final pass only)
   int kk = n;
   if (n > k) {
@@ -251,15 +351,13 @@ compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* _
       if (!cleared) atomicOr(overflow, CMX_OVF_SPEC);
       spec[q] = CMX_NEG_PAD;
     }
-    kk = block_partition(keys, n, thr, final_pass ? top : buf, sh);
+    // not the final pass: survivors go back to the query's buffer AND to the front of keys (for the order statistics below)
+    kk = final_pass ? block_partition<false>(keys, n, thr, top, sh) : block_partition<true>(keys, n, thr, buf, sh);
     float spec_tau = CMX_NEG_PAD, est_tau = CMX_NEG_PAD;
     const bool want_spec = spec_rank > 0 && spec_rank < k;
     const bool want_est = est != nullptr && est_rank > 0 && est_rank < k;
     if (!final_pass && kth != 0ull && (want_spec || want_est)) {
-      // order statistics of the survivors only (kk << n after a large slab): reload them compacted
-      __syncthreads();
-      for (int i = threadIdx.x; i < kk; i += blockDim.x) keys[i] = buf[i];
-      __syncthreads();
+      // order statistics of the survivors only (kk << n after a large slab), packed at keys[0..kk)
       if (want_spec) {
         // the spec_rank-th best so far estimates (with a 3x safety factor, plan_slabs) where the k-th
         // best of the rows up to the end of the next slab will be
@@ -567,6 +665,7 @@ static int pow2_at_least(int n) {
 int launch_compact(const SearchWs& ws, int64_t nq, int k, int final_pass, float* D, int64_t* I,
                    int64_t id_base, cudaStream_t st, int spec_rank, int verify, int est_rank) {
   if (nq == 0) return CMX_OK;
+  CMX_CHECK(ws.cap % 2 == 0, "compact: candidate capacity %d is odd (lists are loaded in 16-byte units)", ws.cap);
   const size_t smem = ((size_t)ws.cap + pow2_at_least(k)) * sizeof(uint64_t);
   CMX_CUDA(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   compact_kernel<<<(unsigned)nq, kSelThreads, smem, st>>>(ws.cand, ws.cnt, ws.tau, ws.overflow, ws.margin, ws.spec, ws.est,
