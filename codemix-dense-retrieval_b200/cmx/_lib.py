@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
     L.cmx_debug_set_tensor_window.argtypes = [i32]
     L.cmx_debug_set_block_order.argtypes = [i32]
     L.cmx_debug_set_speculate.argtypes = [i32]
+    L.cmx_debug_set_small_first.argtypes = [i32]
     L.cmx_debug_set_mapped_outputs.argtypes = [i32]
     L.cmx_debug_plan_slabs.argtypes = [i64, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp]
     L.cmx_debug_plan_ranks.argtypes = [i64, i32, i32, i32, i32, i32, vp, i32]
@@ -127,7 +128,7 @@ def lib() -> C.CDLL:
         "cmx_device_count cmx_index_create cmx_index_free cmx_index_reserve cmx_index_add cmx_index_reset cmx_index_add_from_file cmx_index_add_gather cmx_read_file "
         "cmx_index_ntotal cmx_index_memory cmx_index_dim cmx_index_device cmx_index_reconstruct cmx_index_data cmx_index_search "
         "cmx_mix_normalize cmx_search_mixed cmx_search_prepare cmx_index_export_bounds cmx_search_begin cmx_search_end cmx_union_kth cmx_peer_broadcast cmx_host_register cmx_host_unregister cmx_enable_peer_access cmx_debug_plan_ranks cmx_debug_set_prescore cmx_debug_inject_begin_status cmx_debug_set_prescore_params cmx_debug_set_prescore_min_rows cmx_debug_approx_scores cmx_merge_topk cmx_merge_topk_peers cmx_trec_mono cmx_trec_bilingual cmx_trec_mono_file cmx_trec_bilingual_file cmx_trec_bilingual_file_pre cmx_collapse_max cmx_index_last_stats cmx_set_profiling "
-        "cmx_index_set_cand_capacity cmx_index_error_bounds cmx_index_raise_error_bounds cmx_index_set_precision cmx_set_default_precision cmx_debug_set_tensor_tile cmx_debug_set_stream_variant cmx_debug_set_tensor_flags cmx_debug_set_tensor_pair cmx_debug_set_tensor_small cmx_debug_set_tensor_window cmx_debug_set_block_order cmx_debug_set_speculate cmx_debug_set_mapped_outputs cmx_debug_plan_slabs"
+        "cmx_index_set_cand_capacity cmx_index_error_bounds cmx_index_raise_error_bounds cmx_index_set_precision cmx_set_default_precision cmx_debug_set_tensor_tile cmx_debug_set_stream_variant cmx_debug_set_tensor_flags cmx_debug_set_tensor_pair cmx_debug_set_tensor_small cmx_debug_set_tensor_window cmx_debug_set_block_order cmx_debug_set_speculate cmx_debug_set_small_first cmx_debug_set_mapped_outputs cmx_debug_plan_slabs"
     ).split():
         getattr(L, name).restype = i32
     _lib = L

@@ -267,7 +267,8 @@ constexpr double kSpecDepth = 2.5;
 constexpr double kSpecMinRank = 32.0;
 static int g_speculate = 1;  // 0: planned geometric slabs only (experiments)
 
-static SlabPlan plan_slabs_one(int64_t N, int k, int cap, int align, bool safe, bool spec, int k_out, bool mid) {
+static SlabPlan plan_slabs_one(int64_t N, int k, int cap, int align, bool safe, bool spec, int k_out, bool mid,
+                               int64_t first_rows = 0) {
   SlabPlan pl;
   int64_t seen = 0;
   const int64_t room = cap - k;
@@ -293,7 +294,7 @@ static SlabPlan plan_slabs_one(int64_t N, int k, int cap, int align, bool safe, 
     }
     int64_t rows;
     if (seen == 0) {
-      rows = round_dn(cap);
+      rows = round_dn(first_rows > 0 ? std::min<int64_t>(first_rows, cap) : cap);
       if (rows > cap) rows = cap;  // align > cap cannot happen (cap >= 256)
     } else if (safe) {
       // no more rows than a buffer has room for; a room smaller than the alignment unit is served
@@ -307,12 +308,26 @@ static SlabPlan plan_slabs_one(int64_t N, int k, int cap, int align, bool safe, 
   return pl;
 }
 
-// a speculative mid slab is used only where it saves launches
+// A speculative mid slab is used only where it saves launches.  With one, the dense first slab need not fill the
+// candidate buffers: it only has to be a sample large enough for the mid slab's guess (its kSpecDepth * kSpecMinRank-th
+// best), and dense rows are the expensive ones -- every score of the slab is written out and read back by the first
+// compaction (0.7 ms for 8192 rows x 6980 queries against 0.06 ms of tensor work).  So among the plans with the fewest
+// slabs the one with the smallest first slab wins; kDenseMinRows keeps the sample at eight or more blocks of the
+// permuted order.
+constexpr int64_t kDenseMinRows = 2048;
+static int g_small_first = 1;  // 0: the first slab always fills the buffers (experiments)
 static SlabPlan plan_slabs(int64_t N, int k, int cap, int align, bool safe, bool spec = false, int k_out = 0) {
   SlabPlan plain = plan_slabs_one(N, k, cap, align, safe, spec, k_out, false);
   if (!spec || safe || !g_speculate) return plain;
   SlabPlan mid = plan_slabs_one(N, k, cap, align, safe, spec, k_out, true);
-  return mid.rows.size() < plain.rows.size() ? mid : plain;
+  SlabPlan best = mid.rows.size() < plain.rows.size() ? mid : plain;
+  if (!g_small_first || best.nspec() == 0) return best;
+  const int64_t f_min = std::max<int64_t>(kDenseMinRows, ((int64_t)k * 3 / 2 + 255) / 256 * 256);
+  for (int64_t f = f_min; f < cap; f += 256) {
+    SlabPlan cand = plan_slabs_one(N, k, cap, align, safe, spec, k_out, true, f);
+    if (cand.rows.size() <= best.rows.size() && cand.nspec() == (int)cand.rows.size() - 1) return cand;
+  }
+  return best;
 }
 
 // Block multiplier of the tensor path's processing order (TcParams::perm): an integer P near
@@ -1516,6 +1531,7 @@ int cmx_collapse_max(const float* D, const int64_t* I, int64_t nq, int k, const 
 CMX_API int cmx_debug_set_tensor_tile(int bn) { set_tensor_tile(bn); return CMX_OK; }
 CMX_API int cmx_debug_set_block_order(int on) { g_block_order = on ? 1 : 0; return CMX_OK; }
 CMX_API int cmx_debug_set_speculate(int on) { g_speculate = on ? 1 : 0; return CMX_OK; }
+CMX_API int cmx_debug_set_small_first(int on) { g_small_first = on ? 1 : 0; return CMX_OK; }
 CMX_API int cmx_debug_set_mapped_outputs(int on) { g_mapped_outputs = on ? 1 : 0; return CMX_OK; }
 /* test hooks (host logic, no GPU needed): the slab schedule of a tensor-path search and the block multiplier */
 CMX_API int cmx_debug_plan_slabs(int64_t ntotal, int k, int cap, int rescore, int safe, int speculate, int64_t* rows_out,

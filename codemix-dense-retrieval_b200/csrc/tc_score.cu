@@ -37,6 +37,26 @@ namespace cmx {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // fp16 elements = 128 bytes = one swizzle-128B row
 constexpr int TC_THREADS = 192;
+// the single-CTA scoring kernel runs TWO epilogue warpgroups (warps 2-5 and 6-9), one per TMEM accumulator buffer:
+// a group then has two MMA tile times for its tile.  The epilogue of the early slabs (a few percent of all scores
+// pass) is a lone warp per SM sub-partition issuing ~3500 dependent instructions per tile at IPC 0.25: 14 k cycles
+// against 8.2 k of MMAs (ncu on the 84 k-row mid slab of a 1.1 M-row shard: tensor pipe 59 % active, the MMA warp
+// waiting for a free accumulator).
+constexpr int TC_THREADS1 = 64 + 2 * 128;
+
+// -DCMX_TC_TIMERS: cycle counters of the single-CTA kernel's roles, summed over CTAs (scripts/exp_tc_timers.py).
+// 0 MMA: wait for a free accumulator   1 MMA: wait for operands   2 MMA: tiles
+// 4 epilogue (warp 2, lane 0): wait for the accumulator   5 accumulator held   8 after release   9 tiles
+#ifdef CMX_TC_TIMERS
+__device__ unsigned long long g_tc_timers[16];
+#define TCT_NOW() clock64()
+#define TCT_ADD(i, t0) atomicAdd(&g_tc_timers[i], (unsigned long long)(clock64() - (t0)))
+#define TCT_COUNT(i) atomicAdd(&g_tc_timers[i], 1ull)
+#else
+#define TCT_COUNT(i) ((void)0)
+#define TCT_NOW() 0ll
+#define TCT_ADD(i, t0) ((void)(t0))
+#endif
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB per Q plane tile
 constexpr int TC_TILE_SLOTS = 4;               // depth of the tile-id ring of the dynamic scheduler
 
@@ -298,7 +318,11 @@ __device__ __forceinline__ void epilogue_filter_tile_two_pass(const TcParams& p,
 
 constexpr int TC_STAGE_SLOTS = 8;
 constexpr int TC_EPI_THREADS = 128;
-constexpr int TC_EPI_SMEM = TC_STAGE_SLOTS * TC_EPI_THREADS * 8;  // float value + int column per slot
+constexpr int TC_EPI_GROUP_SMEM = TC_STAGE_SLOTS * TC_EPI_THREADS * 8;  // float value + int column per slot
+constexpr int TC_POOL = 512;                                            // survivor pool entries per epilogue warp
+constexpr int TC_EPI_SMEM = 8 * TC_POOL * 8;  // eight warp pools (single-CTA kernel, early slabs); the staging slots of the
+                                              // two epilogue groups alias them (a launch runs one kind of epilogue)
+static_assert(2 * TC_EPI_GROUP_SMEM <= TC_EPI_SMEM, "staging slots must fit the epilogue scratch");
 
 struct EpiStage {
   float* val;  // [TC_STAGE_SLOTS][TC_EPI_THREADS]
@@ -362,10 +386,120 @@ __device__ __forceinline__ void epilogue_filter_tile(const TcParams& p, uint32_t
   }
 }
 
+// ---- pool epilogue (early slabs of the single-CTA kernel) ------------------------------------
+// Early slabs let a few percent of all scores pass (tens of survivors per query row and tile).  The TMEM accumulator
+// can only be handed back to the MMA warp when the epilogue has read it for the last time, and with two accumulator
+// buffers MMA(i) waits for epilogue(i - 2): whatever the epilogue does while it holds the buffer beyond one MMA tile
+// time (8192 cycles) is exposed.  The count-then-store epilogue above holds it for ~12 k cycles on a 4 %-pass slab
+// (cycle counters, scripts/exp_tc_timers.py: first pass 2.3 k, second pass 9.9 k -- a divergent per-lane loop over
+// survivors, ~250 cycles per trip).  Here the warp walks the 32 columns of a chunk TOGETHER: one ballot per column
+// (statically indexed register, no select tree, no divergence), survivors appended to a per-warp pool in shared
+// memory as (raw value, column | owner lane | rank within the owner's row).  The buffer is released right after
+// the single pass; the per-row atomicAdd and the global stores follow, all 32 lanes busy, outside the critical path.
+struct EpiPool {
+  float* val;      // [TC_POOL]
+  uint32_t* meta;  // [TC_POOL]: column (8 bits) | owner lane << 8 | rank << 13
+};
+
+__device__ __forceinline__ void epilogue_pool_store(uint32_t* cnt, uint64_t* cand, int cap, const float* val, const uint32_t* meta_a,
+                                                    int lane, int64_t q0, uint32_t mycnt, uint32_t fill, float inv, int64_t tile_row0) {
+  uint32_t pos = 0;
+  if (mycnt) pos = atomicAdd(&cnt[q0 + lane], mycnt);
+  __syncwarp();  // the other lanes' entries are visible
+  for (uint32_t i0 = 0; i0 < fill; i0 += 32) {
+    const uint32_t i = i0 + (uint32_t)lane;
+    const bool on = i < fill;
+    const uint32_t meta = on ? meta_a[i] : 0u;
+    const float raw = on ? val[i] : 0.f;
+    const int owner = (int)((meta >> 8) & 31u);
+    const uint32_t at = __shfl_sync(0xffffffffu, pos, owner) + (meta >> 13);
+    if (on && at < (uint32_t)cap)
+      cand[(q0 + owner) * (int64_t)cap + at] = make_key(raw * inv, (uint32_t)(tile_row0 + (meta & 255u)));
+  }
+  __syncwarp();  // before the pool is refilled
+}
+__device__ __forceinline__ void epilogue_pool_flush(const TcParams& p, const EpiPool& pl, int lane, int64_t q0,
+                                                    uint32_t& mycnt, uint32_t& fill, float inv, int64_t tile_row0) {
+  if (fill == 0) return;  // warp-uniform
+  epilogue_pool_store(p.cnt, p.cand, p.cap, pl.val, pl.meta, lane, q0, mycnt, fill, inv, tile_row0);
+  fill = 0;
+  mycnt = 0;
+}
+// Out-of-line pieces of the overflow path (the unrolled column loop must not contain calls: the 32 accumulator
+// registers would live on the stack).
+__device__ __noinline__ void epilogue_pool_store_full(uint32_t* cnt, uint64_t* cand, int cap, const float* val, int lane, int64_t q0,
+                                                      uint32_t mycnt, uint32_t fill, float inv, int64_t tile_row0) {
+  epilogue_pool_store(cnt, cand, cap, val, reinterpret_cast<const uint32_t*>(val + TC_POOL), lane, q0, mycnt, fill, inv, tile_row0);
+}
+// one chunk whose survivors alone exceed the pool (more than half of its 1024 scores pass): every lane appends its own
+__device__ __noinline__ void epilogue_chunk_direct(uint32_t* cnt_q, uint64_t* qcand, int cap, uint32_t taddr_chunk, float tau_raw,
+                                                   float inv, int64_t row_c, int jmax) {
+  uint32_t v[32];
+  __syncwarp();
+  tmem_ld_x32(taddr_chunk, v);
+  tmem_ld_wait();
+  uint32_t mask = survivor_mask(v, tau_raw, jmax);
+  if (!mask) return;
+  uint32_t pos = atomicAdd(cnt_q, (uint32_t)__popc(mask));
+  while (mask) {
+    const int j = __ffs(mask) - 1;
+    mask &= mask - 1u;
+    if (pos < (uint32_t)cap) qcand[pos] = make_key(__uint_as_float(select32(v, j)) * inv, (uint32_t)(row_c + j));
+    ++pos;
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_filter_tile_pool(const TcParams& p, uint32_t taddr_row, const EpiPool& pl, int lane,
+                                                          int64_t q0, float tau_raw, float inv, int64_t tile_row0,
+                                                          int64_t cols_valid, uint32_t& mycnt, uint32_t& fill) {
+  constexpr int NC = BN / 32;
+  const uint32_t lt = (1u << lane) - 1u;
+  int c = 0;
+#pragma unroll 1
+  while (c < NC) {
+    const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
+    if (jmax <= 0) break;  // warp-uniform: columns past the corpus end
+    const uint32_t fill0 = fill, cnt0 = mycnt;
+    {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld_x32(taddr_row + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+      const uint32_t meta_c = (uint32_t)(c * 32) | ((uint32_t)lane << 8);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const bool pass = __uint_as_float(v[j]) > tau_raw && j < jmax;
+        const uint32_t b = __ballot_sync(0xffffffffu, pass);
+        const uint32_t slot = fill + (uint32_t)__popc(b & lt);
+        if (pass && slot < (uint32_t)TC_POOL) {
+          pl.val[slot] = __uint_as_float(v[j]);
+          pl.meta[slot] = (meta_c + (uint32_t)j) | (mycnt << 13);
+        }
+        mycnt += pass ? 1u : 0u;
+        fill += (uint32_t)__popc(b);
+      }
+    }
+    if (fill <= (uint32_t)TC_POOL) { ++c; continue; }
+    // the chunk did not fit (warp-uniform, rare): forget it, empty the pool in place, and take the chunk again
+    fill = fill0;
+    mycnt = cnt0;
+    if (fill0 == 0) {
+      epilogue_chunk_direct(&p.cnt[q0 + lane], p.cand + (q0 + lane) * (int64_t)p.cap, p.cap, taddr_row + (uint32_t)(c * 32), tau_raw, inv,
+                            tile_row0 + c * 32, jmax);
+      ++c;
+      continue;
+    }
+    epilogue_pool_store_full(p.cnt, p.cand, p.cap, pl.val, lane, q0, mycnt, fill, inv, tile_row0);
+    fill = 0;
+    mycnt = 0;
+  }
+}
+
 // PASSES = 3: split precision (Qlo*Bhi + Qhi*Blo + Qhi*Bhi); PASSES = 1: Qhi*Bhi only
 // (approximate filter scores of the rescore mode; the lo tiles are neither staged nor read)
 template <int BN, int STAGES, int PASSES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS1, 1)
 tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant__ CUtensorMap tmQlo,
                 const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
                 const TcParams p) {
@@ -439,10 +573,13 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
         const int64_t t = (int64_t)t_next;
         const bool live = t < p.ntiles;
         if (dyn) {
-          mbar_wait(tid_empty_bar(slot), sphase ^ 1u);
-          tile_ring[slot] = live ? (int)t : -1;
-          mbar_arrive(tid_full_bar(slot));  // release: the id is visible to whoever sees this phase complete
-          if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
+          // the end marker goes into two consecutive slots: one for each epilogue group (slots alternate between them)
+          for (int rep = 0; rep < (live ? 1 : 2); ++rep) {
+            mbar_wait(tid_empty_bar(slot), sphase ^ 1u);
+            tile_ring[slot] = live ? (int)t : -1;
+            mbar_arrive(tid_full_bar(slot));  // release: the id is visible to whoever sees this phase complete
+            if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
+          }
         }
         if (!live) break;
         if (dyn) t_next = atomicAdd(p.done, 1ull);  // the next id travels while this tile's loads are issued
@@ -487,11 +624,16 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
           if (t_static >= p.ntiles) break;
           t_static += gridDim.x;
         }
+        [[maybe_unused]] long long tw = TCT_NOW();
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        TCT_ADD(0, tw);
+        TCT_COUNT(2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.kblocks; ++kb) {
+          tw = TCT_NOW();
           mbar_wait(full_bar(stage), phase);
+          TCT_ADD(1, tw);
           tc_fence_after();
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           const uint64_t qhi = make_smem_desc(sbase);
@@ -522,17 +664,24 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
     const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may touch
     const float inv = p.q_inv_scale[0] * p.b_inv_scale;
     const float fwd = 1.0f / inv;  // power of two
+    // group g (warps 2-5: 0, warps 6-9: 1) takes this CTA's tiles g, g + 2, ...: always accumulator buffer g
+    const int grp = (warp - 2) >> 2;
     EpiStage stg;
-    stg.val = reinterpret_cast<float*>(epi_smem);
-    stg.col = reinterpret_cast<int*>(epi_smem + TC_STAGE_SLOTS * TC_EPI_THREADS * 4);
-    stg.e = (warp - 2) * 32 + lane;
+    stg.val = reinterpret_cast<float*>(epi_smem + grp * TC_EPI_GROUP_SMEM);
+    stg.col = reinterpret_cast<int*>(epi_smem + grp * TC_EPI_GROUP_SMEM + TC_STAGE_SLOTS * TC_EPI_THREADS * 4);
+    stg.e = ((warp - 2) & 3) * 32 + lane;
     int nst = 0;
-    int acc = 0;
+    EpiPool pool;
+    pool.val = reinterpret_cast<float*>(epi_smem + (warp - 2) * (TC_POOL * 8));
+    pool.meta = reinterpret_cast<uint32_t*>(pool.val + TC_POOL);
+    uint32_t pool_cnt = 0, pool_fill = 0;
+    const int acc = grp;
     uint32_t acc_phase = 0;
-    int slot = 0;
+    int slot = grp;
     uint32_t sphase = 0;
     const bool dyn = p.window == 0;
-    int64_t t_static = blockIdx.x;
+    int64_t t_static = (int64_t)blockIdx.x + (int64_t)grp * gridDim.x;
+    static_assert(TC_TILE_SLOTS % 2 == 0, "ring slots alternate between the two epilogue groups");
     for (;;) {
       int64_t t;
       if (dyn) {
@@ -540,12 +689,13 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
         t = tile_ring[slot];
         __syncwarp();  // every lane has its copy before the slot goes back to the producer
         if (lane == 0) mbar_arrive(tid_empty_bar(slot));
-        if (++slot == TC_TILE_SLOTS) { slot = 0; sphase ^= 1u; }
+        slot += 2;
+        if (slot >= TC_TILE_SLOTS) { slot -= TC_TILE_SLOTS; sphase ^= 1u; }
         if (t < 0) break;
       } else {
         t = t_static;
         if (t >= p.ntiles) break;
-        t_static += gridDim.x;
+        t_static += 2 * (int64_t)gridDim.x;
       }
       const int m = (int)(t % mtiles);
       const int64_t n = t / mtiles;
@@ -557,18 +707,25 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       const bool qvalid = q < p.nq;
       // compare raw accumulators against tau expressed in accumulator units
       const float tau_raw = qvalid ? p.tau[q] * fwd : __int_as_float(0x7f800000);
+      [[maybe_unused]] long long tw = TCT_NOW();
       mbar_wait(tfull_bar(acc), acc_phase);
+      if (threadIdx.x == 64) { TCT_ADD(4, tw); TCT_COUNT(9); }
+      tw = TCT_NOW();
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
       if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid, n * BN);
-      else if (p.two_pass) epilogue_filter_tile_two_pass<BN>(p, taddr_row, q, tau_raw, inv, tile_row0, cols_valid);
+      else if (p.two_pass) epilogue_filter_tile_pool<BN>(p, taddr_row, pool, lane, q - lane, tau_raw, inv, tile_row0, cols_valid, pool_cnt, pool_fill);
       else epilogue_filter_tile<BN>(p, taddr_row, stg, nst, q, tau_raw, inv, tile_row0, cols_valid);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));  // TMEM buffer back to the MMA warp ...
-      if (!dyn && threadIdx.x == 64) throttle_tile_done(p.done);
+      if (threadIdx.x == 64) TCT_ADD(5, tw);
+      tw = TCT_NOW();
+      if (!dyn && ((warp - 2) & 3) == 0 && lane == 0) throttle_tile_done(p.done);
       epilogue_flush(p, stg, nst, q, inv, tile_row0);  // ... before the atomic round trip
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      epilogue_pool_flush(p, pool, lane, q - lane, pool_cnt, pool_fill, inv, tile_row0);
+      if (threadIdx.x == 64) TCT_ADD(8, tw);
+      acc_phase ^= 1u;
     }
   }
 
@@ -1078,6 +1235,14 @@ static int g_tc_pair = -1;
 void set_tensor_pair(int on) { g_tc_pair = (on < 0) ? -1 : (on ? 1 : 0); }
 void set_tensor_tile(int bn) { g_tc_bn = (bn == 128) ? 128 : 256; }
 void set_tensor_flags(int f) { g_tc_flags = f; }
+#ifdef CMX_TC_TIMERS
+extern "C" __attribute__((visibility("default"))) int cmx_debug_tc_timers(unsigned long long* out16, int reset) {
+  if (out16 && cudaMemcpyFromSymbol(out16, g_tc_timers, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+  static const unsigned long long zeros[16] = {};
+  if (reset && cudaMemcpyToSymbol(g_tc_timers, zeros, sizeof(zeros)) != cudaSuccess) return 1;
+  return 0;
+}
+#endif
 
 template <int BN, int STAGES, int PASSES>
 static int launch_tc(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const CUtensorMap& tb_hi,
@@ -1088,7 +1253,7 @@ static int launch_tc(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const C
   CMX_CUDA(cudaFuncSetAttribute(tc_score_kernel<BN, STAGES, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = p.ntiles < sm_count ? p.ntiles : sm_count;
   if (grid < 1) return CMX_OK;
-  tc_score_kernel<BN, STAGES, PASSES><<<(unsigned)grid, TC_THREADS, smem, st>>>(tq_hi, tq_lo, tb_hi, tb_lo, p);
+  tc_score_kernel<BN, STAGES, PASSES><<<(unsigned)grid, TC_THREADS1, smem, st>>>(tq_hi, tq_lo, tb_hi, tb_lo, p);
   CMX_LAUNCHED();
   return CMX_OK;
 }

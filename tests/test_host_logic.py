@@ -505,36 +505,54 @@ def _plan_ranks(n, k, cap, rescore=1, safe=0, spec=1, nslabs=16):
 def test_slab_schedule_invariants():
     """Host logic of the tensor path's slab schedule: whole 256-row blocks, dense first slab,
     geometric growth, speculative slabs only when their rank estimate is trustworthy, safe slabs bounded."""
+    from cmx import _lib
+
     n = 8_841_823
     npad = (n + 255) // 256 * 256
-    # C2: dense slab, ONE speculative mid slab up to the row count where the final k'-th best is expected at
-    # rank 32 of the dense slab, then the rest of the corpus under a second guess -- 3 launches instead of 5
+    # C2: a dense SAMPLE slab (the smallest first slab that still gives a 3-launch plan), ONE speculative mid slab up
+    # to the row count its rank-80 guess can serve (k' * f / 32), then the rest of the corpus under a second guess
     rows, ns, ss, sr = _plan(n, 1000, 8192)
-    mid = 1341 * 8192 // 32 - 8192
-    assert rows == [8192, mid // 256 * 256, npad - 8192 - mid // 256 * 256] and ns == 3 and ss == 2
+    f = rows[0]
+    assert ns == 3 and ss == 2 and 2048 <= f < 8192 and f % 256 == 0
+    mid = 1341 * f // 32 - f
+    assert rows == [f, mid // 256 * 256, npad - f - mid // 256 * 256]
     assert _plan_ranks(n, 1000, 8192)[:3] == [0, 80, sr]
     seen = sum(rows[:2])
     r0 = 1341 * seen / npad
     assert r0 >= 32 and sr == int(np.ceil(2.5 * r0)) and sr < 750
+    # ... and f - 256 would not do: the final guess would rest on a rank below 32
+    f2 = f - 256
+    assert 1341 * (1341 * f2 // 32 // 256 * 256) / npad < 32
+    # the first slab fills the buffers when it is asked to (experiments) or when nothing is speculative
+    _lib.check(_lib.lib().cmx_debug_set_small_first(0))
+    try:
+        rows_b, ns_b, ss_b, sr_b = _plan(n, 1000, 8192)
+        mid_b = 1341 * 8192 // 32 - 8192
+        assert rows_b == [8192, mid_b // 256 * 256, npad - 8192 - mid_b // 256 * 256] and ns_b == 3 and ss_b == 2
+        rows8b, ns8b, ss8b, _ = _plan(1_105_228, 1000, 8192)
+        assert ns8b == 3 and ss8b == 2 and rows8b[:2] == [8192, 20736]
+    finally:
+        _lib.check(_lib.lib().cmx_debug_set_small_first(1))
     rows_g, ns_g, ss_g, _ = _plan(n, 1000, 8192, spec=0)
     assert ss_g == -1 and ns_g == 7 and rows_g[:4] == [8192, 20736, 73728, 262144] and sum(rows_g) == npad
     for a, b in zip(rows_g[1:-1], rows_g[2:-1]):
         assert 3.0 < b / a < 3.7  # x(1 + (C - k') / 2k') per slab
-    # shards of a 2- and 4-GPU search: 3 launches as well
-    for g in (2, 4):
+    # shards of a 2-, 4- and 8-GPU search: 3 launches as well, the sample slab shrinks with the shard
+    firsts = [f]
+    for g in (2, 4, 8):
         rows_s, ns_s, ss_s, sr_s = _plan(n // g, 1000, 8192)
-        assert ns_s == 3 and ss_s == 2 and rows_s[1] == rows[1] and 80 < sr_s < 750
-    # a 1.1 M-row shard of an 8-GPU search: a mid slab would not save a launch, the plan stays
-    # dense, one geometric slab, guess after the second slab
+        assert ns_s == 3 and ss_s == 2 and 80 < sr_s < 750 and rows_s[1] == (1341 * rows_s[0] // 32 - rows_s[0]) // 256 * 256
+        assert _plan_ranks(n // g, 1000, 8192)[:2] == [0, 80]
+        firsts.append(rows_s[0])
+    assert firsts == sorted(firsts, reverse=True) and firsts[-1] == 2048
     rows8, ns8, ss8, sr8 = _plan(1_105_228, 1000, 8192)
-    assert ns8 == 3 and ss8 == 2 and rows8[:2] == [8192, 20736] and 80 <= sr8 < 1000
     # small k: the geometric plan is already 3-4 slabs and the rank estimate never qualifies
     assert _plan(n, 100, 8192)[2] == -1 and _plan(n, 10, 8192)[2] == -1
     # split precision plans on k itself
     rows_s, _, ss_s, sr_s = _plan(n, 1000, 8192, rescore=0)
     assert sum(rows_s) == npad and ss_s >= 1 and sr_s < 1000
     for r in (rows, rows_g, rows8, rows_s):
-        assert all(v % 256 == 0 and v > 0 for v in r) and r[0] == 8192 and sum(r) == ((sum(r) + 255) // 256) * 256
+        assert all(v % 256 == 0 and v > 0 for v in r) and 2048 <= r[0] <= 8192 and sum(r) == ((sum(r) + 255) // 256) * 256
     # worst-case-safe schedule: no slab larger than the free room; tiny buffers get pieces of one block
     rows_safe, ns_safe, ss_safe, _ = _plan(100_000, 1000, 8192, rescore=0, safe=1)
     assert ss_safe == -1 and max(rows_safe[1:]) <= 8192 - 1000 and sum(rows_safe) == (100_000 + 255) // 256 * 256
