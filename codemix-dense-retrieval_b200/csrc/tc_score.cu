@@ -139,14 +139,19 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void throttle_wait(const unsigned long long* done, long long t, long long window) {
+// `seen` is the producer's last observation of the counter.  It can only lag behind the truth, so a tile it admits
+// is admitted; the fresh read that follows is not waited for -- its round trip to L2 (~700 cycles, once per tile,
+// between the last operand request of one tile and the first of the next) overlaps the tile's TMA requests and the
+// value is first looked at when the next tile starts.
+__device__ __forceinline__ void throttle_wait(const unsigned long long* done, long long t, long long window,
+                                              unsigned long long& seen) {
   if (window <= 0) return;
-  unsigned long long d;
-  for (;;) {
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(d) : "l"(done) : "memory");
-    if (t < (long long)d + window) break;
+  while (!(t < (long long)seen + window)) {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(done) : "memory");
+    if (t < (long long)seen + window) break;
     __nanosleep(200);
   }
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(done) : "memory");
 }
 __device__ __forceinline__ void throttle_tile_done(unsigned long long* done) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(done) : "memory");
@@ -568,6 +573,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       const uint64_t pol_q = (p.flags & 1) ? kL2EvictLast : kL2EvictNormal;
       const uint64_t pol_b = (p.flags & 2) ? kL2EvictFirst : kL2EvictNormal;
       const bool dyn = p.window == 0;  // window > 0: static round-robin tiles + progress throttle (round-1 scheduler, kept for A/B)
+      unsigned long long done_seen = 0;
       unsigned long long t_next = dyn ? atomicAdd(p.done, 1ull) : (unsigned long long)blockIdx.x;
       for (;;) {
         const int64_t t = (int64_t)t_next;
@@ -583,7 +589,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
         }
         if (!live) break;
         if (dyn) t_next = atomicAdd(p.done, 1ull);  // the next id travels while this tile's loads are issued
-        else { t_next = (unsigned long long)(t + gridDim.x); throttle_wait(p.done, t, p.window); }
+        else { t_next = (unsigned long long)(t + gridDim.x); throttle_wait(p.done, t, p.window, done_seen); }
         const int m = (int)(t % mtiles);
         const int64_t n = t / mtiles;
         const int32_t qrow = m * TC_BM;
@@ -844,12 +850,13 @@ tc_score_pair_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_con
       uint32_t phase = 0;
       const uint64_t pol_q = (p.flags & 1) ? kL2EvictLast : kL2EvictNormal;
       const uint64_t pol_b = (p.flags & 2) ? kL2EvictFirst : kL2EvictNormal;
+      unsigned long long done_seen = 0;
       for (int64_t t = cid; t < p.ntiles; t += ncl) {
         const int m = (int)(t % mtiles);
         const int64_t n = t / mtiles;
         const int32_t qrow = m * 256 + (int32_t)rank * 128;
         const int32_t brow = (int32_t)perm_row(p, p.row0 + n * BN) + (int32_t)rank * 128;
-        throttle_wait(p.done, t, p.window);
+        throttle_wait(p.done, t, p.window, done_seen);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
