@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -c 600 --csv
 echo "launch list exit $?"
 grep '^{' gpurun_out/r2n_plain.log | cut -c1-300
 # full captures: launches 3.. (after the warm-up searches) = dense, mid, final slab of one step
-ncu --set full --clock-control none --import-source on -k regex:tc_score_kernel -s 9 -c 3 -f -o gpurun_out/prof_tc_r2 $CMD > gpurun_out/r2n_ncu_tc.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tc_score_ -s 9 -c 3 -f -o gpurun_out/prof_tc_r2 $CMD > gpurun_out/r2n_ncu_tc.log 2>&1
 echo "tc capture exit $?"
 ncu --set full --clock-control none --import-source on -k regex:rescore_kernel -s 3 -c 1 -f -o gpurun_out/prof_rescore_r2 $CMD > gpurun_out/r2n_ncu_rescore.log 2>&1
 echo "rescore capture exit $?"
