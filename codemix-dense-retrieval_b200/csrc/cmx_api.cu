@@ -280,7 +280,9 @@ static SlabPlan plan_slabs_one(int64_t N, int k, int cap, int align, bool safe, 
       const int rank_min = (int)std::ceil(kSpecDepth * kSpecMinRank);
       const double r0 = (double)k * (double)seen / (double)N;  // expected rank of the final k-th best
       // final: worth it only if the geometric plan still needs two or more slabs
-      if (r0 >= kSpecMinRank && std::ceil(kSpecDepth * r0) < (double)k_out && kSpecDepth * r0 < 0.75 * k && (double)(N - seen) > g) {
+      // (a guess admits ~kSpecDepth * k rows on top of the k kept ones: only with a buffer that has room for them)
+      if (r0 >= kSpecMinRank && std::ceil(kSpecDepth * r0) < (double)k_out && kSpecDepth * r0 < 0.75 * k && 4.5 * k <= cap &&
+          (double)(N - seen) > g) {
         push(N - seen, (int)std::ceil(kSpecDepth * r0));
         break;
       }

@@ -47,6 +47,7 @@ constexpr int TC_THREADS1 = 64 + 2 * 128;
 // -DCMX_TC_TIMERS: cycle counters of the single-CTA kernel's roles, summed over CTAs (scripts/exp_tc_timers.py).
 // 0 MMA: wait for a free accumulator   1 MMA: wait for operands   2 MMA: tiles
 // 4 epilogue (warp 2, lane 0): wait for the accumulator   5 accumulator held   8 after release   9 tiles
+// 10 pool emptied in place (all epilogue warps)   11 chunks appended lane by lane
 #ifdef CMX_TC_TIMERS
 __device__ unsigned long long g_tc_timers[16];
 #define TCT_NOW() clock64()
@@ -490,11 +491,13 @@ __device__ __forceinline__ void epilogue_filter_tile_pool(const TcParams& p, uin
     fill = fill0;
     mycnt = cnt0;
     if (fill0 == 0) {
+      if (lane == 0) TCT_COUNT(11);
       epilogue_chunk_direct(&p.cnt[q0 + lane], p.cand + (q0 + lane) * (int64_t)p.cap, p.cap, taddr_row + (uint32_t)(c * 32), tau_raw, inv,
                             tile_row0 + c * 32, jmax);
       ++c;
       continue;
     }
+    if (lane == 0) TCT_COUNT(10);
     epilogue_pool_store_full(p.cnt, p.cand, p.cap, pl.val, lane, q0, mycnt, fill, inv, tile_row0);
     fill = 0;
     mycnt = 0;

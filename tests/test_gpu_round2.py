@@ -297,6 +297,53 @@ def test_repeated_runs_are_bit_identical_across_kernel_variants():
         assert oracle.compare_topk(ref[0].cpu().numpy(), ref[1].cpu().numpy(), Dr, Ir, rtol=RTOL, atol=ATOL)["ok"]
 
 
+def test_early_slab_epilogue_paths_agree():
+    """The pool epilogue of the early slabs (csrc/tc_score.cu) has three regimes: everything fits the 512-entry warp
+    pool (a few percent pass: the sample-slab plan), the pool fills up inside a tile and is emptied in place (a third
+    of all scores pass: a 4096-entry candidate buffer), and a single 32-column chunk overflows the empty pool (half of
+    all scores pass: split precision with a buffer of 2k entries).  Every regime, with and without speculation and
+    with either first-slab rule, must return the (D, I) of the default plan of its precision bit for bit, and that
+    must be the exact top-k.  (scripts/exp_pool_paths.py counts the paths with the -DCMX_TC_TIMERS build on exactly
+    these inputs -- profiles/r02_pool_epilogue_paths.jsonl: 0 / 1295 / 1549 pools emptied in place, 58 chunks appended
+    lane by lane in the split / 2048 case.)"""
+    import torch
+
+    from cmx import _lib
+    from cmx.engine import Shard
+
+    L = _lib.lib()
+    N, d, k, nq = 400_000, 256, 1000, 300
+    X = _unit_cuda(N, d, 71)
+    Q = _unit_cuda(nq, d, 72)
+    Dr, Ir = _brute(X, Q, k)
+    for precision, caps in (("rescore", (0, 4096)), ("split", (0, 2048))):
+        sh = Shard(d, 0)
+        sh.set_precision(precision)
+        sh.add(X)
+        ref = None
+        plans = set()
+        try:
+            for cap in caps:  # 0: default capacity (8192)
+                for small_first in (1, 0):
+                    for spec in (1, 0):
+                        _lib.check(L.cmx_debug_set_small_first(small_first))
+                        _lib.check(L.cmx_debug_set_speculate(spec))
+                        sh.set_cand_capacity(cap)
+                        D, I = sh.search(Q, k, path="tensor")
+                        st = sh.last_stats()
+                        assert st["reruns"] == 0, (precision, cap, small_first, spec, st)
+                        plans.add(st["slabs"])
+                        if ref is None:
+                            ref = (D.clone(), I.clone())
+                        else:
+                            assert torch.equal(I, ref[1]) and torch.equal(D, ref[0]), (precision, cap, small_first, spec, st)
+        finally:
+            _lib.check(L.cmx_debug_set_small_first(1))
+            _lib.check(L.cmx_debug_set_speculate(1))
+        assert len(plans) >= 3, plans  # the settings really produced different slab plans
+        assert oracle.compare_topk(ref[0].cpu().numpy(), ref[1].cpu().numpy(), Dr, Ir, rtol=RTOL, atol=ATOL)["ok"], precision
+
+
 def test_large_pageable_add_is_staged_and_exact():
     """add() of a large pageable host array (index_cpu_to_gpu of a read_index'ed corpus) goes through the page-locked
     staging pipeline (parallel memcpy + overlapped H2D); the stored rows and the corpus statistics are the same as for
