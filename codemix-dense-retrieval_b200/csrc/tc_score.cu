@@ -15,15 +15,16 @@
 // (products of fp16 pairs are exact in fp32; only lo*lo ~ 2^-22 is dropped).  Either way the
 // accumulator is rescaled by the exact power of two 2^-(eq+eb) in the epilogue.
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 320 threads -- 192 in the CTA-pair and small-batch kernels --, warp-specialised):
 //   warp 0    TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of Qhi(/Qlo)
 //             [128 x 64] and Bhi(/Blo) [BN x 64] into a ring of smem stages; corpus tiles
 //             are visited in a golden-ratio block order (TcParams::perm)
 //   warp 1    TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16)
 //   warps 2-5 epilogue: tcgen05.ld the 128 x BN fp32 accumulator (one query row per
-//             thread), compare with the row's threshold tau and append survivors
+//   (and 6-9) thread), compare with the row's threshold tau and append survivors
 //             (score,row keys) to the query's candidate buffer -- the score matrix
-//             never leaves the SM.
+//             never leaves the SM.  The single-CTA kernel has two such groups, one per
+//             accumulator buffer.
 // Accumulators are double-buffered in TMEM (2 x BN columns) so the epilogue of tile
 // i overlaps the MMAs of tile i+1.  Tiles are ordered m-fastest so that CTAs running
 // concurrently share the same corpus tile through L2: each corpus byte is read from
