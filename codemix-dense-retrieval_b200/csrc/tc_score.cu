@@ -456,6 +456,43 @@ __device__ __noinline__ void epilogue_chunk_direct(uint32_t* cnt_q, uint64_t* qc
   }
 }
 
+// Dense epilogue through the warp pool (single-CTA kernel).  epilogue_dense_tile has every lane store its own row's
+// keys: one store instruction touches 32 rows 8 bytes each -- 32 sectors, a quarter used -- and the first slab was
+// bound by that (53 k cycles per tile, ncu: stall_lg).  Here 8 columns at a time are transposed through shared
+// memory (row stride 9 keys: conflict-free both ways), so that a store instruction writes 64 contiguous bytes for
+// each of 4 rows: 8 sectors, all used.
+template <int BN>
+__device__ __forceinline__ void epilogue_dense_tile_pool(const TcParams& p, uint32_t taddr_row, uint64_t* tr, int lane, int64_t q0,
+                                                         float inv, int64_t tile_row0, int64_t cols_valid, int64_t slot0) {
+  static_assert(32 * 9 * 8 <= TC_POOL * 8, "transposition buffer must fit the warp pool");
+  const int sub = lane >> 3, jj = lane & 7;  // read side: row sub (+4 per trip), column jj of the piece
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(taddr_row + (uint32_t)(c * 32), v);
+    tmem_ld_wait();
+    const int jmax = (int)min((int64_t)32, cols_valid - c * 32);
+#pragma unroll
+    for (int piece = 0; piece < 4; ++piece) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = piece * 8 + u;
+        const float s = __uint_as_float(v[j]) * inv;
+        tr[lane * 9 + u] = (j < jmax && s > CMX_NEG_PAD) ? make_key(s, (uint32_t)(tile_row0 + c * 32 + j)) : 0ull;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + sub;
+        const uint64_t key = tr[row * 9 + jj];
+        if (q0 + row < p.nq) p.cand[(q0 + row) * (int64_t)p.cap + slot0 + c * 32 + piece * 8 + jj] = key;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_filter_tile_pool(const TcParams& p, uint32_t taddr_row, const EpiPool& pl, int lane,
                                                           int64_t q0, float tau_raw, float inv, int64_t tile_row0,
@@ -723,7 +760,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant
       tw = TCT_NOW();
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(acc * BN);
-      if (p.dense) epilogue_dense_tile<BN>(p, taddr_row, q, qvalid, inv, tile_row0, cols_valid, n * BN);
+      if (p.dense) epilogue_dense_tile_pool<BN>(p, taddr_row, reinterpret_cast<uint64_t*>(pool.val), lane, q - lane, inv, tile_row0, cols_valid, n * BN);
       else if (p.two_pass) epilogue_filter_tile_pool<BN>(p, taddr_row, pool, lane, q - lane, tau_raw, inv, tile_row0, cols_valid, pool_cnt, pool_fill);
       else epilogue_filter_tile<BN>(p, taddr_row, stg, nst, q, tau_raw, inv, tile_row0, cols_valid);
       tc_fence_before();
